@@ -1,0 +1,260 @@
+// Host-side driver of the transformer path: workspace carving, one forward pass over a chunk
+// of sequences, the decode/scoring loop of *_uncertainty, and the C ABI around them.
+// Reference control flow: src/libs/active_learning.py:38-155 and :209; src/model/transformer.py:349-375.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bfb {
+
+struct Workspace {
+  int32_t* tokens;  // (S, max_len)
+  float* x;         // (R, d) block input / output
+  float* qkv;       // (R, 3d)
+  float* att;       // (R, d) concatenated heads
+  float* y;         // (R, d) branch output (W_out / FFN)
+  float* x1;        // (R, d) LayerNorm1 output
+  float* h;         // (R, F)
+  float* logits;    // (S or R, V)
+  float* seq_scores;  // (S)
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// bytes for n_seq sequences of at most max_len tokens; full_logits: logits for every row
+static size_t workspace_bytes(const bfb200_transformer& m, int64_t n_seq, int max_len, bool full_logits) {
+  const size_t R = (size_t)n_seq * max_len;
+  const size_t d = m.d_model, F = m.d_ff, V = m.ntoken;
+  size_t b = 256;
+  b += align256((size_t)n_seq * max_len * sizeof(int32_t));
+  b += 4 * align256(R * d * sizeof(float));
+  b += align256(R * 3 * d * sizeof(float));
+  b += align256(R * F * sizeof(float));
+  b += align256((full_logits ? R : (size_t)n_seq) * V * sizeof(float));
+  b += align256((size_t)n_seq * sizeof(float));
+  return b;
+}
+
+static Workspace carve(void* base, const bfb200_transformer& m, int64_t n_seq, int max_len, bool full_logits) {
+  const size_t R = (size_t)n_seq * max_len;
+  const size_t d = m.d_model, F = m.d_ff, V = m.ntoken;
+  char* p = (char*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  Workspace w;
+  auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return q; };
+  w.tokens = (int32_t*)take((size_t)n_seq * max_len * sizeof(int32_t));
+  w.x = (float*)take(R * d * sizeof(float));
+  w.att = (float*)take(R * d * sizeof(float));
+  w.y = (float*)take(R * d * sizeof(float));
+  w.x1 = (float*)take(R * d * sizeof(float));
+  w.qkv = (float*)take(R * 3 * d * sizeof(float));
+  w.h = (float*)take(R * F * sizeof(float));
+  w.logits = (float*)take((full_logits ? R : (size_t)n_seq) * V * sizeof(float));
+  w.seq_scores = (float*)take((size_t)n_seq * sizeof(float));
+  return w;
+}
+
+static int validate_model(const bfb200_transformer* m) {
+  BFB_REQUIRE(m != nullptr, BFB200_ERR_INVALID_ARG, "model is NULL");
+  BFB_REQUIRE(m->ntoken >= 1 && m->d_model >= 1 && m->n_heads >= 1 && m->d_ff >= 1 && m->n_layers >= 0,
+              BFB200_ERR_INVALID_ARG, "bad model dimensions");
+  BFB_REQUIRE(m->d_model % m->n_heads == 0, BFB200_ERR_INVALID_ARG, "d_model must be divisible by n_heads");
+  BFB_REQUIRE((m->d_model & 3) == 0 && (m->d_ff & 3) == 0, BFB200_ERR_UNSUPPORTED,
+              "d_model (%d) and dim_feedforward (%d) must be multiples of 4", m->d_model, m->d_ff);
+  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_BF16,
+              BFB200_ERR_INVALID_ARG, "unknown compute type %d", m->compute);
+  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32, BFB200_ERR_UNSUPPORTED,
+              "compute=bf16 is not available in this build");
+  if (m->site_flags != 0)
+    BFB_REQUIRE(m->p_drop >= 0.f && m->p_drop < 1.f, BFB200_ERR_INVALID_ARG, "p_drop %f outside [0, 1)", m->p_drop);
+  BFB_DEV(m->embedding); BFB_DEV(m->pe); BFB_DEV(m->head_w); BFB_DEV(m->head_b);
+  if (m->n_layers > 0) {
+    BFB_DEV(m->w_qkv); BFB_DEV(m->w_out); BFB_DEV(m->ln1_w); BFB_DEV(m->ln1_b); BFB_DEV(m->ff1_w);
+    BFB_DEV(m->ff1_b); BFB_DEV(m->ff2_w); BFB_DEV(m->ff2_b); BFB_DEV(m->ln2_w); BFB_DEV(m->ln2_b);
+  }
+  return BFB200_OK;
+}
+
+static MaskSource make_mask_source(const bfb200_transformer& m, const bfb200_masks* masks) {
+  MaskSource ms;
+  memset(&ms, 0, sizeof(ms));
+  const float p = m.site_flags != 0 ? m.p_drop : 0.f;
+  ms.bits = masks != nullptr ? masks->bits : nullptr;
+  const uint64_t seed = masks != nullptr ? masks->seed : 0ull;
+  ms.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  ms.threshold = keep_threshold(p);
+  ms.scale = 1.0f / (1.0f - p);
+  ms.n_sites = 1 + BFB200_SITES_PER_LAYER * m.n_layers;
+  ms.max_len = masks != nullptr ? masks->max_len : 0;
+  ms.words = (m.d_model + 31) / 32;
+  ms.n_draws = 1;
+  return ms;
+}
+
+// One forward pass over S sequences of `len` tokens (rows r = s * len + t); leaves the last
+// block's output in ws.x.
+static int forward_chunk(const bfb200_transformer& m, Workspace& ws, int64_t S, int len,
+                         int tok_stride, const MaskSource& ms, cudaStream_t st) {
+  const int d = m.d_model, F = m.d_ff;
+  const int64_t R = S * len;
+  const uint32_t fl = m.site_flags;
+  BFB_REQUIRE(len <= m.pe_len, BFB200_ERR_INVALID_ARG, "sequence length %d exceeds the positional table (%d)",
+              len, m.pe_len);
+  BFB_CALL(launch_embed(ws.tokens, tok_stride, m.embedding, m.pe, S, len, d, ms,
+                        (fl & BFB200_SITE_EMBED) ? 0 : -1, ws.x, st));
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int sb = 1 + BFB200_SITES_PER_LAYER * l;
+    const float* wqkv = m.w_qkv + (size_t)l * 3 * d * d;
+    const float* wout = m.w_out + (size_t)l * d * d;
+    BFB_CALL(launch_sgemm(ws.x, wqkv, nullptr, ws.qkv, R, 3 * d, d, 1, 0, 0, st));
+    BFB_CALL(launch_attention(ws.qkv, ws.att, S, len, d, m.n_heads, ms,
+                              (fl & BFB200_SITE_HEAD_OUT) ? sb + 4 : -1, st));
+    BFB_CALL(launch_sgemm(ws.att, wout, nullptr, ws.y, R, d, d, 1, 0, 0, st));
+    BFB_CALL(launch_resid_ln(ws.x, ws.y, ws.x1, R, len, d, m.ln1_w + (size_t)l * d, m.ln1_b + (size_t)l * d,
+                             m.ln_eps, ms, (fl & BFB200_SITE_ATTN_RESID) ? sb + 1 : -1,
+                             (fl & BFB200_SITE_FFN_IN) ? sb + 2 : -1, st));
+    BFB_CALL(launch_sgemm(ws.x1, m.ff1_w + (size_t)l * F * d, m.ff1_b + (size_t)l * F, ws.h, R, F, d, 1, 0, 1, st));
+    BFB_CALL(launch_sgemm(ws.h, m.ff2_w + (size_t)l * d * F, m.ff2_b + (size_t)l * d, ws.y, R, d, F, 1, 0, 0, st));
+    // both residuals start from the BLOCK INPUT x (transformer.py:231-233)
+    BFB_CALL(launch_resid_ln(ws.x, ws.y, ws.att, R, len, d, m.ln2_w + (size_t)l * d, m.ln2_b + (size_t)l * d,
+                             m.ln_eps, ms, (fl & BFB200_SITE_FFN_RESID) ? sb + 3 : -1,
+                             (fl & BFB200_SITE_LAYER_OUT) ? sb + 0 : -1, st));
+    float* next = ws.att;  // the block output becomes the next block's input; `att` is free again
+    ws.att = ws.x;
+    ws.x = next;
+  }
+  return BFB200_OK;
+}
+
+}  // namespace bfb
+
+using namespace bfb;
+
+extern "C" size_t bfb200_transformer_workspace_bytes(const bfb200_transformer* model, int64_t n_sequences,
+                                                     int32_t max_len) {
+  if (model == nullptr || n_sequences < 0 || max_len < 0) return 0;
+  return workspace_bytes(*model, n_sequences, max_len, true);
+}
+
+extern "C" int bfb200_transformer_forward(const bfb200_transformer* model, const int64_t* src, int32_t len,
+                                          int64_t batch, const bfb200_masks* masks, uint32_t draw,
+                                          int64_t index_base, float* logp_out, void* workspace,
+                                          size_t workspace_bytes_, void* stream) {
+  BFB_CALL(validate_model(model));
+  BFB_REQUIRE(len >= 0 && batch >= 0, BFB200_ERR_INVALID_ARG, "bad shape (%d, %lld)", len, (long long)batch);
+  if (len == 0 || batch == 0) return BFB200_OK;
+  BFB_DEV(src);
+  BFB_DEV(logp_out);
+  BFB_DEV(workspace);
+  if (masks != nullptr) BFB_DEV_OPT(masks->bits);
+  const bfb200_transformer& m = *model;
+  BFB_REQUIRE(workspace_bytes_ >= workspace_bytes(m, batch, len, true), BFB200_ERR_WORKSPACE,
+              "workspace too small: %zu < %zu", workspace_bytes_, workspace_bytes(m, batch, len, true));
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws = carve(workspace, m, batch, len, true);
+  MaskSource ms = make_mask_source(m, masks);
+  ms.n_seq = batch;
+  ms.seq_base = 0;
+  ms.step = 0;
+  ms.n_draws = 1;
+  ms.draw_base = draw;
+  ms.item_base = index_base;
+  if (ms.bits != nullptr)
+    BFB_REQUIRE(ms.max_len >= len, BFB200_ERR_INVALID_ARG, "masks.max_len %d < len %d", ms.max_len, len);
+  BFB_CALL(launch_init_tokens(src, batch, 0, batch, 1, len, len, m.ntoken, ws.tokens, st));
+  BFB_CALL(forward_chunk(m, ws, batch, len, len, ms, st));
+  BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, batch * len, m.ntoken, m.d_model, 1, 0, 0, st));
+  BFB_CALL(launch_logsoftmax_seqfirst(ws.logits, batch, len, m.ntoken, logp_out, st));
+  return BFB200_OK;
+}
+
+static int validate_mc(const bfb200_transformer* model, const bfb200_mc_args* a) {
+  BFB_REQUIRE(a != nullptr, BFB200_ERR_INVALID_ARG, "args is NULL");
+  BFB_REQUIRE(a->n_items >= 0 && a->prompt_len >= 1 && a->new_tokens >= 0 && a->n_draws >= 1,
+              BFB200_ERR_INVALID_ARG, "bad shape (B=%lld, P=%d, N=%d, T=%d)", (long long)a->n_items,
+              a->prompt_len, a->new_tokens, a->n_draws);
+  BFB_REQUIRE(a->scheme >= BFB200_SCHEME_GREEDY && a->scheme <= BFB200_SCHEME_DROPOUT, BFB200_ERR_INVALID_ARG,
+              "Unknown compute scheme %d", a->scheme);
+  BFB_REQUIRE(a->mode >= BFB200_MODE_MAX && a->mode <= BFB200_MODE_ENTROPY, BFB200_ERR_INVALID_ARG,
+              "Unknown mode %d. Available modes are 'max', 'margin' and 'entropy'.", a->mode);
+  if (a->scheme == BFB200_SCHEME_SAMPLING)
+    BFB_REQUIRE(a->temperature > 0.f, BFB200_ERR_INVALID_ARG, "temperature must be > 0");
+  BFB_REQUIRE(a->prompt_len + a->new_tokens - 1 <= model->pe_len || a->new_tokens == 0, BFB200_ERR_INVALID_ARG,
+              "P + N - 1 = %d exceeds the positional table (%d)", a->prompt_len + a->new_tokens - 1, model->pe_len);
+  BFB_REQUIRE(a->prompt_len + a->new_tokens < 65536, BFB200_ERR_UNSUPPORTED, "sequence too long for the RNG counter");
+  return BFB200_OK;
+}
+
+static int64_t max_chunk_items(const bfb200_transformer& m, const bfb200_mc_args& a, size_t bytes) {
+  const int max_len = a.prompt_len + a.new_tokens;
+  const size_t per_item = workspace_bytes(m, a.n_draws, max_len, false) - 256;
+  const size_t fixed = 256 + 9 * 256;
+  if (bytes <= fixed) return 0;
+  int64_t n = (int64_t)((bytes - fixed) / per_item);
+  // one item's buffers were aligned individually in per_item; the estimate is conservative
+  return n;
+}
+
+extern "C" size_t bfb200_mc_workspace_bytes(const bfb200_transformer* model, const bfb200_mc_args* args,
+                                            int64_t items_per_chunk) {
+  if (model == nullptr || args == nullptr || items_per_chunk < 1) return 0;
+  const int max_len = args->prompt_len + args->new_tokens;
+  // sized so that max_chunk_items(bytes) >= items_per_chunk
+  const size_t per_item = workspace_bytes(*model, args->n_draws, max_len, false) - 256;
+  return 256 + 9 * 256 + per_item * (size_t)items_per_chunk;
+}
+
+extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc_args* args,
+                                           void* workspace, size_t workspace_bytes_, void* stream) {
+  BFB_CALL(validate_model(model));
+  BFB_CALL(validate_mc(model, args));
+  const bfb200_transformer& m = *model;
+  const bfb200_mc_args& a = *args;
+  if (a.n_items == 0 || a.new_tokens == 0) return BFB200_OK;
+  BFB_DEV(a.prompts);
+  BFB_DEV(a.step_scores);
+  BFB_DEV(workspace);
+  BFB_DEV_OPT(a.pool_scores); BFB_DEV_OPT(a.logp_out); BFB_DEV_OPT(a.tokens_out);
+  BFB_DEV_OPT(a.forced_tokens); BFB_DEV_OPT(a.masks.bits);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = a.n_draws, P = a.prompt_len, N = a.new_tokens;
+  const int max_len = P + N;  // room for the last appended token (only returned, never embedded)
+  int64_t chunk = max_chunk_items(m, a, workspace_bytes_);
+  BFB_REQUIRE(chunk >= 1, BFB200_ERR_WORKSPACE, "workspace too small for one pool item: %zu < %zu",
+              workspace_bytes_, bfb200_mc_workspace_bytes(model, args, 1));
+  if (chunk > a.n_items) chunk = a.n_items;
+  if (a.masks.bits != nullptr)
+    BFB_REQUIRE(a.masks.max_len >= P + N - 1, BFB200_ERR_INVALID_ARG, "masks.max_len %d < P + N - 1 = %d",
+                a.masks.max_len, P + N - 1);
+  const int64_t S_total = a.n_items * T;
+
+  for (int64_t item0 = 0; item0 < a.n_items; item0 += chunk) {
+    const int64_t items = (a.n_items - item0 < chunk) ? a.n_items - item0 : chunk;
+    const int64_t S = items * T;
+    Workspace ws = carve(workspace, m, S, max_len, false);
+    BFB_CALL(launch_init_tokens(a.prompts, a.n_items, item0, S, T, P, max_len, m.ntoken, ws.tokens, st));
+    for (int step = 0; step < N; ++step) {
+      const int len = P + step;
+      MaskSource ms = make_mask_source(m, &a.masks);
+      ms.n_seq = S_total;
+      ms.seq_base = item0 * T;
+      ms.step = (uint32_t)step;
+      ms.n_draws = (uint32_t)T;
+      ms.draw_base = 0;
+      ms.item_base = a.index_base + item0;
+      BFB_CALL(forward_chunk(m, ws, S, len, max_len, ms, st));
+      // vocabulary head on the last position only (active_learning.py:62, :103, :146)
+      BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, S, m.ntoken, m.d_model, len, len - 1, 0, st));
+      const int32_t* forced = a.forced_tokens != nullptr ? a.forced_tokens + (int64_t)step * S_total + item0 * T : nullptr;
+      float* logp = a.logp_out != nullptr ? a.logp_out + ((int64_t)step * S_total + item0 * T) * m.ntoken : nullptr;
+      BFB_CALL(launch_score_step(ws.logits, S, m.ntoken, a.scheme, a.mode, a.temperature, ms, forced, ws.tokens,
+                                 max_len, len, ws.seq_scores, logp, st));
+      BFB_CALL(launch_reduce_draws(ws.seq_scores, items, T, a.step_scores + (int64_t)step * a.n_items + item0, st));
+    }
+    if (a.tokens_out != nullptr) {
+      cudaError_t e = cudaMemcpyAsync(a.tokens_out + item0 * T * max_len, ws.tokens,
+                                      (size_t)S * max_len * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+      BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "token copy failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (a.pool_scores != nullptr) BFB_CALL(launch_step_mean(a.step_scores, a.n_items, N, a.pool_scores, st));
+  return BFB200_OK;
+}

@@ -1,0 +1,584 @@
+// Layer-by-layer kernels of the MC-batched transformer forward (fp32 path).
+//
+// Activations are row-major (R, d) with row r = s * len + t: `s` is the sequence inside
+// the chunk (item-major, draw-minor: s = item * n_draws + draw), `t` the position, so one
+// sequence's rows are contiguous (attention) and one item's draws are adjacent (acquisition).
+// Reference arithmetic: src/model/transformer.py (cited per kernel).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bfb {
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static int stride_grid(int64_t blocks_needed, int blocks_per_sm) {
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  if (blocks_needed < 1) blocks_needed = 1;
+  return (int)(blocks_needed < cap ? blocks_needed : cap);
+}
+
+// ---------------------------------------------------------------------------
+// prompts (P, B_total) int64 seq-first -> tokens (S, stride) int32, replicated over draws
+// ---------------------------------------------------------------------------
+__global__ void init_tokens_kernel(const int64_t* __restrict__ prompts, int64_t n_items_total,
+                                   int64_t item0, int64_t n_seq, int n_draws, int prompt_len,
+                                   int stride, int vocab, int32_t* __restrict__ tokens) {
+  const int64_t total = n_seq * prompt_len;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / prompt_len;
+    const int t = (int)(i - s * prompt_len);
+    int64_t tok = prompts[(int64_t)t * n_items_total + item0 + s / n_draws];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);  // nn.Embedding would raise; stay in bounds
+    tokens[s * stride + t] = (int32_t)tok;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// x = dropout_E(embedding[tok]) * sqrt(d) + pe[t]      (transformer.py:355-362, :269-272)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ tokens, int tok_stride,
+                                                    const float* __restrict__ emb,
+                                                    const float* __restrict__ pe, int64_t n_seq, int len,
+                                                    int d, float sqrt_d, MaskSource ms, int site,
+                                                    float* __restrict__ x) {
+  const int d4 = d >> 2;
+  const int64_t total = n_seq * len * d4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d4;
+    const int f4 = (int)(i - r * d4);
+    const int64_t s = r / len;
+    const int t = (int)(r - s * len);
+    const int tok = tokens[s * tok_stride + t];
+    float4 e = __ldg(reinterpret_cast<const float4*>(emb + (int64_t)tok * d) + f4);
+    if (site >= 0) {
+      const uint32_t keep = keep4(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)f4);
+      e.x = (keep & 1u) ? e.x * ms.scale : 0.f;
+      e.y = (keep & 2u) ? e.y * ms.scale : 0.f;
+      e.z = (keep & 4u) ? e.z * ms.scale : 0.f;
+      e.w = (keep & 8u) ? e.w * ms.scale : 0.f;
+    }
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)t * d) + f4);
+    float4 o;
+    o.x = e.x * sqrt_d + p.x;
+    o.y = e.y * sqrt_d + p.y;
+    o.z = e.z * sqrt_d + p.z;
+    o.w = e.w * sqrt_d + p.w;
+    reinterpret_cast<float4*>(x)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// C[M,N] = A[M,K] * W[N,K]^T (+ bias) (ReLU)     nn.Linear (transformer.py:33-35,100,152-154,336)
+// fp32 CUDA-core GEMM: 128x64 block tile, 8x4 register tile, K staged 16 at a time
+// through shared memory (stored k-major so the inner product reads are conflict-free
+// float4 loads).  A row m lives at A + (m * a_row_mul + a_row_off) * K, which lets the
+// vocabulary head read only each sequence's last position.
+// ---------------------------------------------------------------------------
+constexpr int GB_M = 128, GB_N = 64, GB_K = 16, GT_M = 8, GT_N = 4;
+
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A,
+                                                       const float* __restrict__ W,
+                                                       const float* __restrict__ bias,
+                                                       float* __restrict__ C, int64_t M, int N, int K,
+                                                       int64_t a_row_mul, int64_t a_row_off, int relu) {
+  __shared__ __align__(16) float As[GB_K][GB_M + 4];
+  __shared__ __align__(16) float Ws[GB_K][GB_N + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GB_M;
+  const int n0 = blockIdx.y * GB_N;
+
+  float acc[GT_M][GT_N];
+#pragma unroll
+  for (int i = 0; i < GT_M; ++i)
+#pragma unroll
+    for (int j = 0; j < GT_N; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GB_K) {
+    // A tile: 128 rows x 16 k = 512 float4, two per thread
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * 256;
+      const int row = idx >> 2, kq = (idx & 3) << 2;
+      const int64_t m = m0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + kq < K)
+        v = __ldg(reinterpret_cast<const float4*>(A + (m * a_row_mul + a_row_off) * K + k0 + kq));
+      As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+    }
+    // W tile: 64 rows x 16 k = 256 float4, one per thread
+    {
+      const int row = tid >> 2, kq = (tid & 3) << 2;
+      const int n = n0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < N && k0 + kq < K) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K + k0 + kq));
+      Ws[kq + 0][row] = v.x; Ws[kq + 1][row] = v.y; Ws[kq + 2][row] = v.z; Ws[kq + 3][row] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GB_K; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * GT_M]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * GT_M + 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * GT_N]);
+      const float a[GT_M] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[GT_N] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < GT_M; ++i)
+#pragma unroll
+        for (int j = 0; j < GT_N; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < GT_M; ++i) {
+    const int64_t m = m0 + ty * GT_M + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < GT_N; ++j) {
+      const int n = n0 + tx * GT_N + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += __ldg(bias + n);
+      if (relu) v = fmaxf(v, 0.f);
+      C[m * N + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// causal multi-head attention (transformer.py:58-65, :123-124)
+//   scores = Q K^T / sqrt(dh) + causal(-inf); softmax; @ V; heads concatenated
+// one block per (sequence, head); K/V of that head staged in shared memory; each warp owns
+// query rows t = warp, warp + 4, ...; keys are spread over lanes.
+// ---------------------------------------------------------------------------
+template <int MAXJ>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv,
+                                                        float* __restrict__ out, int len, int d, int dh,
+                                                        float sqrt_dh, MaskSource ms, int site) {
+  extern __shared__ float sm[];
+  const int h = blockIdx.y;
+  const int64_t s = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ldk = dh + 1;
+  float* Ks = sm;                    // len * (dh + 1)
+  float* Vs = Ks + len * ldk;        // len * dh
+  float* Qs = Vs + len * dh;         // 4 * dh
+  float* Ps = Qs + 4 * dh;           // 4 * len
+  const float* base = qkv + s * len * 3 * (int64_t)d + h * dh;
+  for (int i = threadIdx.x; i < len * dh; i += blockDim.x) {
+    const int t = i / dh, c = i - t * dh;
+    Ks[t * ldk + c] = __ldg(base + (int64_t)t * 3 * d + d + c);
+    Vs[t * dh + c] = __ldg(base + (int64_t)t * 3 * d + 2 * d + c);
+  }
+  __syncthreads();
+  float* q = Qs + warp * dh;
+  float* p = Ps + warp * len;
+  for (int t = warp; t < len; t += 4) {
+    for (int c = lane; c < dh; c += 32) q[c] = __ldg(base + (int64_t)t * 3 * d + c);
+    __syncwarp();
+    float sc[MAXJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      const int j = lane + 32 * jj;
+      float a = -INFINITY;
+      if (j <= t) {
+        a = 0.f;
+        for (int c = 0; c < dh; ++c) a = fmaf(q[c], Ks[j * ldk + c], a);
+        a = a / sqrt_dh;
+      }
+      sc[jj] = a;
+      mx = fmaxf(mx, a);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      const int j = lane + 32 * jj;
+      const float e = (j <= t) ? expf(sc[jj] - mx) : 0.f;
+      sc[jj] = e;
+      z += e;
+    }
+    z = warp_sum(z);
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j <= t) p[j] = sc[jj] / z;
+    }
+    __syncwarp();
+    for (int c = lane; c < dh; c += 32) {
+      float a = 0.f;
+      for (int j = 0; j <= t; ++j) a = fmaf(p[j], Vs[j * dh + c], a);
+      if (site >= 0) {
+        const int f = h * dh + c;
+        const uint32_t keep = keep4(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)(f >> 2));
+        a = ((keep >> (f & 3)) & 1u) ? a * ms.scale : 0.f;
+      }
+      out[(s * len + t) * (int64_t)d + h * dh + c] = a;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out = dropout_out( LayerNorm(x + dropout_branch(y)) )     (transformer.py:226-233, :370)
+// one warp per row, 128-bit loads, statistics by warp shuffle; biased variance, eps inside
+// the square root (nn.LayerNorm).
+// ---------------------------------------------------------------------------
+template <int NPL4>
+__global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ y,
+                                                       float* __restrict__ out, int64_t n_rows, int len,
+                                                       int d, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps,
+                                                       MaskSource ms, int branch_site, int out_site) {
+  const int lane = threadIdx.x & 31;
+  const int d4 = d >> 2;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
+       r += warps_total) {
+    const int64_t s = r / len;
+    const uint32_t t = (uint32_t)(r - s * len);
+    const float4* xr = reinterpret_cast<const float4*>(x + r * d);
+    const float4* yr = reinterpret_cast<const float4*>(y + r * d);
+    float4 v[NPL4];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL4; ++j) {
+      const int f4 = lane + 32 * j;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f4 < d4) {
+        const float4 a = __ldg(xr + f4);
+        float4 b = __ldg(yr + f4);
+        if (branch_site >= 0) {
+          const uint32_t keep = keep4(ms, s, t, (uint32_t)branch_site, (uint32_t)f4);
+          b.x = (keep & 1u) ? b.x * ms.scale : 0.f;
+          b.y = (keep & 2u) ? b.y * ms.scale : 0.f;
+          b.z = (keep & 4u) ? b.z * ms.scale : 0.f;
+          b.w = (keep & 8u) ? b.w * ms.scale : 0.f;
+        }
+        v[j] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL4; ++j) {
+      if (lane + 32 * j < d4) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+        sq += (a * a + b * b) + (c * c + e * e);
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+    for (int j = 0; j < NPL4; ++j) {
+      const int f4 = lane + 32 * j;
+      if (f4 < d4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + f4);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + f4);
+        float4 o;
+        o.x = (v[j].x - mean) * rstd * g.x + bb.x;
+        o.y = (v[j].y - mean) * rstd * g.y + bb.y;
+        o.z = (v[j].z - mean) * rstd * g.z + bb.z;
+        o.w = (v[j].w - mean) * rstd * g.w + bb.w;
+        if (out_site >= 0) {
+          const uint32_t keep = keep4(ms, s, t, (uint32_t)out_site, (uint32_t)f4);
+          o.x = (keep & 1u) ? o.x * ms.scale : 0.f;
+          o.y = (keep & 2u) ? o.y * ms.scale : 0.f;
+          o.z = (keep & 4u) ? o.z * ms.scale : 0.f;
+          o.w = (keep & 8u) ? o.w * ms.scale : 0.f;
+        }
+        reinterpret_cast<float4*>(out + r * d)[f4] = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// last-position logits -> log-softmax -> probabilities -> per-draw score + next token
+// (transformer.py:375; active_learning.py:62-68, :103-112, :146-152)
+// one warp per sequence.
+// ---------------------------------------------------------------------------
+template <int NPL>
+__global__ void __launch_bounds__(256) score_step_kernel(
+    const float* __restrict__ logits, int64_t n_seq, int vocab, int scheme, int mode, float temperature,
+    MaskSource ms, const int32_t* __restrict__ forced, int32_t* __restrict__ tokens, int tok_stride,
+    int write_pos, float* __restrict__ seq_scores, float* __restrict__ logp_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_seq;
+       s += warps_total) {
+    float l[NPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int c = lane + 32 * j;
+      l[j] = c < vocab ? __ldg(logits + s * vocab + c) : -INFINITY;
+      mx = fmaxf(mx, l[j]);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) z += (lane + 32 * j) < vocab ? expf(l[j] - mx) : 0.f;
+    const float lse = logf(warp_sum(z));
+    // log-probs + greedy arg-max (first index wins ties)
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < vocab) {
+        l[j] = (l[j] - mx) - lse;
+        if (logp_out != nullptr) logp_out[s * vocab + c] = l[j];
+        if (l[j] > best) { best = l[j]; best_i = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    // probs = softmax(log-probs [/ temperature])
+    float p[NPL];
+    float pm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      p[j] = (scheme == BFB200_SCHEME_SAMPLING) ? l[j] / temperature : l[j];
+      if ((lane + 32 * j) < vocab) pm = fmaxf(pm, p[j]);
+    }
+    pm = warp_max(pm);
+    float pz = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      p[j] = (lane + 32 * j) < vocab ? expf(p[j] - pm) : 0.f;
+      pz += p[j];
+    }
+    pz = warp_sum(pz);
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) p[j] = p[j] / pz;
+
+    int token = best_i;
+    if (scheme == BFB200_SCHEME_SAMPLING) {
+      // inverse-CDF draw in class order from one Philox word
+      const uint64_t item = (uint64_t)(ms.item_base + s / ms.n_draws);
+      const uint32_t draw = ms.draw_base + (uint32_t)(s % ms.n_draws);
+      const uint4 r = philox4x32_10(
+          make_uint4((uint32_t)item, draw, ms.step << 16, BFB200_SITE_SAMPLING_TOKEN << 16), ms.key);
+      const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      float running = 0.f;
+      token = vocab - 1;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) {
+        float c = p[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float up = __shfl_up_sync(0xffffffffu, c, o);
+          if (lane >= o) c += up;
+        }
+        c += running;
+        const unsigned hit = __ballot_sync(0xffffffffu, c > u && (lane + 32 * j) < vocab);
+        if (!found && hit != 0u) { token = 32 * j + (__ffs(hit) - 1); found = true; }
+        running = __shfl_sync(0xffffffffu, c, 31);
+      }
+    }
+    float s0, s1, s2;
+    warp_scores<NPL>(p, vocab, lane, s0, s1, s2);
+    if (lane == 0) {
+      seq_scores[s] = mode == BFB200_MODE_MAX ? s0 : (mode == BFB200_MODE_MARGIN ? s1 : s2);
+      if (forced != nullptr) token = forced[s];
+      if (tokens != nullptr && write_pos < tok_stride) tokens[s * tok_stride + write_pos] = token;
+    }
+  }
+}
+
+// logits (R, V) rows r = b * len + t -> log-probs written seq-first (len, B, V)
+template <int NPL>
+__global__ void __launch_bounds__(256) logsoftmax_seqfirst_kernel(const float* __restrict__ logits,
+                                                                  int64_t n_seq, int len, int vocab,
+                                                                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_rows = n_seq * len;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
+       r += warps_total) {
+    const int64_t b = r / len;
+    const int64_t t = r - b * len;
+    float l[NPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int c = lane + 32 * j;
+      l[j] = c < vocab ? __ldg(logits + r * vocab + c) : -INFINITY;
+      mx = fmaxf(mx, l[j]);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) z += (lane + 32 * j) < vocab ? expf(l[j] - mx) : 0.f;
+    const float lse = logf(warp_sum(z));
+    float* dst = out + (t * n_seq + b) * vocab;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < vocab) dst[c] = (l[j] - mx) - lse;
+    }
+  }
+}
+
+// step_scores[step, item] = (sum over draws in order) / T       (active_learning.py:154-155)
+__global__ void reduce_draws_kernel(const float* __restrict__ seq_scores, int64_t n_items_chunk,
+                                    int n_draws, float* __restrict__ step_scores_row) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items_chunk) return;
+  float acc = 0.f;
+  for (int t = 0; t < n_draws; ++t) acc += seq_scores[i * n_draws + t];
+  step_scores_row[i] = acc / (float)n_draws;
+}
+
+// pool_scores[item] = mean over steps                            (active_learning.py:209)
+__global__ void step_mean_kernel(const float* __restrict__ step_scores, int64_t n_items, int n_steps,
+                                 float* __restrict__ pool_scores) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  float acc = 0.f;
+  for (int t = 0; t < n_steps; ++t) acc += step_scores[(int64_t)t * n_items + i];
+  pool_scores[i] = acc / (float)n_steps;
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t item0, int64_t n_seq,
+                       int n_draws, int prompt_len, int stride, int vocab, int32_t* tokens,
+                       cudaStream_t st) {
+  const int grid = stride_grid((n_seq * prompt_len + 255) / 256, 8);
+  init_tokens_kernel<<<grid, 256, 0, st>>>(prompts, n_items_total, item0, n_seq, n_draws, prompt_len,
+                                           stride, vocab, tokens);
+  BFB_LAUNCH_CHECK("init_tokens_kernel");
+  return BFB200_OK;
+}
+
+int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const float* pe, int64_t n_seq,
+                 int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st) {
+  const int64_t total = n_seq * len * (d >> 2);
+  const int grid = stride_grid((total + 255) / 256, 8);
+  embed_kernel<<<grid, 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d, sqrtf((float)d), ms, site, x);
+  BFB_LAUNCH_CHECK("embed_kernel");
+  return BFB200_OK;
+}
+
+int launch_sgemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
+                 int64_t a_row_mul, int64_t a_row_off, int relu, cudaStream_t st) {
+  if (M == 0) return BFB200_OK;
+  BFB_REQUIRE((K & 3) == 0, BFB200_ERR_UNSUPPORTED, "GEMM K=%d must be a multiple of 4", K);
+  dim3 grid((unsigned)((M + GB_M - 1) / GB_M), (unsigned)((N + GB_N - 1) / GB_N));
+  sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, a_row_mul, a_row_off, relu);
+  BFB_LAUNCH_CHECK("sgemm_tn_kernel");
+  return BFB200_OK;
+}
+
+int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d, int n_heads,
+                     const MaskSource& ms, int site, cudaStream_t st) {
+  const int dh = d / n_heads;
+  const size_t smem = ((size_t)len * (2 * dh + 1) + 4 * (size_t)dh + 4 * (size_t)len) * sizeof(float);
+  BFB_REQUIRE(len <= 1024, BFB200_ERR_UNSUPPORTED, "sequence length %d > 1024", len);
+  BFB_REQUIRE(smem <= 227 * 1024, BFB200_ERR_UNSUPPORTED,
+              "attention tile (len=%d, dh=%d) does not fit shared memory", len, dh);
+  BFB_REQUIRE(n_heads <= 65535, BFB200_ERR_UNSUPPORTED, "n_heads %d > 65535", n_heads);
+  dim3 grid((unsigned)n_seq, (unsigned)n_heads);
+#define LAUNCH_ATT(MAXJ)                                                                              \
+  do {                                                                                                \
+    if (smem > 48 * 1024)                                                                             \
+      cudaFuncSetAttribute(attention_kernel<MAXJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    attention_kernel<MAXJ><<<grid, 128, smem, st>>>(qkv, out, len, d, dh, sqrtf((float)dh), ms, site); \
+  } while (0)
+  if (len <= 32) LAUNCH_ATT(1);
+  else if (len <= 64) LAUNCH_ATT(2);
+  else if (len <= 128) LAUNCH_ATT(4);
+  else if (len <= 256) LAUNCH_ATT(8);
+  else LAUNCH_ATT(32);
+#undef LAUNCH_ATT
+  BFB_LAUNCH_CHECK("attention_kernel");
+  return BFB200_OK;
+}
+
+int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,
+                    const float* gamma, const float* beta, float eps, const MaskSource& ms,
+                    int branch_site, int out_site, cudaStream_t st) {
+  BFB_REQUIRE(d <= 4096, BFB200_ERR_UNSUPPORTED, "d_model %d > 4096", d);
+  const int grid = stride_grid((n_rows + 7) / 8, 8);
+#define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site)
+  const int d4 = d >> 2;
+  if (d4 <= 32) LAUNCH_LN(1);
+  else if (d4 <= 64) LAUNCH_LN(2);
+  else if (d4 <= 128) LAUNCH_LN(4);
+  else if (d4 <= 256) LAUNCH_LN(8);
+  else LAUNCH_LN(32);
+#undef LAUNCH_LN
+  BFB_LAUNCH_CHECK("resid_ln_kernel");
+  return BFB200_OK;
+}
+
+int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme, int mode,
+                      float temperature, const MaskSource& ms, const int32_t* forced, int32_t* tokens,
+                      int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st) {
+  BFB_REQUIRE(vocab <= 1024, BFB200_ERR_UNSUPPORTED, "ntoken %d > 1024", vocab);
+  const int grid = stride_grid((n_seq + 7) / 8, 8);
+#define LAUNCH_SC(NPL) score_step_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, vocab, scheme, mode, temperature, ms, forced, tokens, tok_stride, write_pos, seq_scores, logp_out)
+  if (vocab <= 32) LAUNCH_SC(1);
+  else if (vocab <= 64) LAUNCH_SC(2);
+  else if (vocab <= 128) LAUNCH_SC(4);
+  else if (vocab <= 256) LAUNCH_SC(8);
+  else LAUNCH_SC(32);
+#undef LAUNCH_SC
+  BFB_LAUNCH_CHECK("score_step_kernel");
+  return BFB200_OK;
+}
+
+int launch_logsoftmax_seqfirst(const float* logits, int64_t n_seq, int len, int vocab, float* out,
+                               cudaStream_t st) {
+  BFB_REQUIRE(vocab <= 1024, BFB200_ERR_UNSUPPORTED, "ntoken %d > 1024", vocab);
+  const int grid = stride_grid((n_seq * len + 7) / 8, 8);
+#define LAUNCH_LS(NPL) logsoftmax_seqfirst_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, len, vocab, out)
+  if (vocab <= 32) LAUNCH_LS(1);
+  else if (vocab <= 64) LAUNCH_LS(2);
+  else if (vocab <= 128) LAUNCH_LS(4);
+  else if (vocab <= 256) LAUNCH_LS(8);
+  else LAUNCH_LS(32);
+#undef LAUNCH_LS
+  BFB_LAUNCH_CHECK("logsoftmax_seqfirst_kernel");
+  return BFB200_OK;
+}
+
+int launch_reduce_draws(const float* seq_scores, int64_t n_items_chunk, int n_draws, float* dst,
+                        cudaStream_t st) {
+  reduce_draws_kernel<<<(unsigned)((n_items_chunk + 255) / 256), 256, 0, st>>>(seq_scores, n_items_chunk,
+                                                                                n_draws, dst);
+  BFB_LAUNCH_CHECK("reduce_draws_kernel");
+  return BFB200_OK;
+}
+
+int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, float* pool_scores,
+                     cudaStream_t st) {
+  step_mean_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(step_scores, n_items, n_steps,
+                                                                       pool_scores);
+  BFB_LAUNCH_CHECK("step_mean_kernel");
+  return BFB200_OK;
+}
+
+}  // namespace bfb

@@ -1,0 +1,433 @@
+"""Host side of the native path: packs module weights for the C ABI, owns (torch-allocated)
+workspaces and wraps every entry point of include/bayesformer_b200.h in a tensor-level call.
+
+PyTorch is used here for device memory, streams and (in sharding.py) torch.distributed only;
+all arithmetic of the hot path happens inside libbayesformer_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+
+import torch
+
+from bayesformer_b200 import _lib
+
+# Monotonic counter giving every stochastic native call its own Philox stream, the way each
+# F.dropout call of the reference advances the global generator.
+_call_counter = 0
+
+
+def _next_call_id() -> int:
+    global _call_counter
+    _call_counter += 1
+    return _call_counter
+
+
+def default_seed() -> int:
+    """Philox key of the next stochastic call: torch's CUDA seed (torch.manual_seed drives it)."""
+    return int(torch.cuda.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: bayesformer_b200 has no CPU path")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# acquisition / top-k
+# ---------------------------------------------------------------------------
+
+
+def compute_uncertainty(probs: torch.Tensor, mode: str = "max") -> torch.Tensor:
+    """Native `compute_uncertainty` (reference src/libs/active_learning.py:10-35) for (B, C) CUDA tensors."""
+    if mode not in _lib.MODE:
+        raise ValueError(f"Unknown mode {mode}. Available modes are 'max', 'margin' and 'entropy'.")
+    _require_cuda(probs, "probs")
+    if probs.dim() != 2:
+        raise IndexError("compute_uncertainty expects a 2-D (batch, classes) tensor")
+    p = _f32c(probs)
+    out = torch.empty(p.shape[0], dtype=torch.float32, device=p.device)
+    lib = _lib.load()
+    with torch.cuda.device(p.device):
+        _lib.check(lib.bfb200_compute_uncertainty(p.data_ptr(), p.shape[0], p.shape[1], _lib.MODE[mode],
+                                                  out.data_ptr(), _stream_ptr(p.device)))
+    return out
+
+
+@dataclass
+class Acquisition:
+    mean_p: torch.Tensor          # (B, C)
+    score_of_mean: torch.Tensor   # (3, B): max, margin, entropy of the predictive mean
+    mean_of_scores: torch.Tensor  # (3, B): mean over draws of the per-draw scores
+
+
+def acquire(x: torch.Tensor, is_logp: bool = False) -> Acquisition:
+    """Reduce MC outputs x (T, B, C) to predictive mean + all three scores in one pass."""
+    _require_cuda(x, "x")
+    if x.dim() != 3:
+        raise ValueError("acquire expects (draws, items, classes)")
+    x = _f32c(x)
+    T, B, Cn = x.shape
+    mean_p = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
+    som = torch.empty(3, B, dtype=torch.float32, device=x.device)
+    mos = torch.empty(3, B, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.bfb200_acquire(x.data_ptr(), int(is_logp), T, B, Cn, mean_p.data_ptr(), som.data_ptr(),
+                                      mos.data_ptr(), _stream_ptr(x.device)))
+    return Acquisition(mean_p, som, mos)
+
+
+def topk_keys(scores: torch.Tensor, k: int, index_base: int = 0) -> torch.Tensor:
+    """k packed (score, index) keys of the largest scores, descending, lowest index first on ties."""
+    _require_cuda(scores, "scores")
+    s = _f32c(scores).reshape(-1)
+    n = s.numel()
+    if k > n:
+        raise RuntimeError("selected index k out of range")
+    lib = _lib.load()
+    keys = torch.empty(k, dtype=torch.int64, device=s.device)
+    ws_bytes = lib.bfb200_topk_workspace_bytes(n, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(lib.bfb200_topk(s.data_ptr(), n, k, index_base, keys.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   _stream_ptr(s.device)))
+    return keys
+
+
+def merge_topk_keys(keys: torch.Tensor, k: int) -> torch.Tensor:
+    """Final k of already packed candidate keys (e.g. the all-gathered per-GPU top-k)."""
+    _require_cuda(keys, "keys")
+    kk = keys.contiguous().reshape(-1)
+    n = kk.numel()
+    if k > n:
+        raise RuntimeError("selected index k out of range")
+    lib = _lib.load()
+    out = torch.empty(k, dtype=torch.int64, device=kk.device)
+    ws_bytes = lib.bfb200_topk_workspace_bytes(n, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=kk.device)
+    with torch.cuda.device(kk.device):
+        _lib.check(lib.bfb200_merge_topk(kk.data_ptr(), n, k, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         _stream_ptr(kk.device)))
+    return out
+
+
+def unpack_keys(keys: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """keys -> (scores fp32, indices int64)"""
+    _require_cuda(keys, "keys")
+    k = keys.numel()
+    scores = torch.empty(k, dtype=torch.float32, device=keys.device)
+    idx = torch.empty(k, dtype=torch.int64, device=keys.device)
+    lib = _lib.load()
+    with torch.cuda.device(keys.device):
+        _lib.check(lib.bfb200_unpack_keys(keys.data_ptr(), k, scores.data_ptr(), idx.data_ptr(),
+                                          _stream_ptr(keys.device)))
+    return scores, idx
+
+
+def topk(scores: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for `torch.topk(scores, k)` on a 1-D CUDA tensor (reference active_learning.py:210)."""
+    return unpack_keys(topk_keys(scores, k))
+
+
+# ---------------------------------------------------------------------------
+# toy classifiers (src/model/bayesian_classification.py)
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class ClassifierScores:
+    probs: torch.Tensor | None    # (T, B) per-draw sigmoid outputs
+    mean_p: torch.Tensor          # (B,)
+    score_of_mean: torch.Tensor   # (3, B)
+    mean_of_scores: torch.Tensor  # (3, B)
+
+
+def mlp_mc_score(x, w1, b1, w2, b2, p_drop: float, n_draws: int, seed: int | None = None, index_base: int = 0,
+                 mask_bits: torch.Tensor | None = None, return_probs: bool = True) -> ClassifierScores:
+    """n_draws stochastic passes of MLP.forward (bayesian_classification.py:184-198) + sigmoid + reductions."""
+    _require_cuda(x, "x")
+    x = _f32c(x)
+    w1, b1, w2, b2 = (_f32c(t).to(x.device) for t in (w1, b1, w2, b2))
+    B, in_dim = x.shape
+    hidden = w1.shape[0]
+    if w2.numel() != hidden:
+        raise NotImplementedError("native MLP scoring supports output_dimension == 1")
+    dev = x.device
+    probs = torch.empty(n_draws, B, dtype=torch.float32, device=dev) if return_probs else None
+    mean_p = torch.empty(B, dtype=torch.float32, device=dev)
+    som = torch.empty(3, B, dtype=torch.float32, device=dev)
+    mos = torch.empty(3, B, dtype=torch.float32, device=dev)
+    if seed is None:
+        seed = default_seed() ^ (_next_call_id() << 32)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.bfb200_mlp_mc_score(
+            x.data_ptr(), B, in_dim, hidden, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            float(p_drop), n_draws, seed & 0xFFFFFFFFFFFFFFFF, index_base, _ptr(mask_bits), _ptr(probs),
+            mean_p.data_ptr(), som.data_ptr(), mos.data_ptr(), _stream_ptr(dev)))
+    return ClassifierScores(probs, mean_p, som, mos)
+
+
+def vmlp_mc_score(x, w1_mu, w1_rho, b1, w2_mu, w2_rho, b2, eps: torch.Tensor,
+                  return_probs: bool = True) -> ClassifierScores:
+    """VariationalMLP draws (bayesian_classification.py:118-130); eps (T, in*hidden + hidden) N(0,1) noise."""
+    _require_cuda(x, "x")
+    x = _f32c(x)
+    dev = x.device
+    w1_mu, w1_rho, b1, w2_mu, w2_rho, b2, eps = (_f32c(t).to(dev) for t in (w1_mu, w1_rho, b1, w2_mu, w2_rho, b2, eps))
+    B, in_dim = x.shape
+    hidden = w1_mu.shape[1]
+    if w2_mu.numel() != hidden:
+        raise NotImplementedError("native VariationalMLP scoring supports output_dimension == 1")
+    n_draws = eps.shape[0]
+    if eps.shape[1] != in_dim * hidden + hidden:
+        raise ValueError("eps must be (T, in_dim * hidden + hidden)")
+    probs = torch.empty(n_draws, B, dtype=torch.float32, device=dev) if return_probs else None
+    mean_p = torch.empty(B, dtype=torch.float32, device=dev)
+    som = torch.empty(3, B, dtype=torch.float32, device=dev)
+    mos = torch.empty(3, B, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.bfb200_vmlp_mc_score(
+            x.data_ptr(), B, in_dim, hidden, w1_mu.data_ptr(), w1_rho.data_ptr(), b1.data_ptr(), w2_mu.data_ptr(),
+            w2_rho.data_ptr(), b2.data_ptr(), eps.data_ptr(), n_draws, _ptr(probs), mean_p.data_ptr(),
+            som.data_ptr(), mos.data_ptr(), _stream_ptr(dev)))
+    return ClassifierScores(probs, mean_p, som, mos)
+
+
+# ---------------------------------------------------------------------------
+# transformer
+# ---------------------------------------------------------------------------
+
+
+class PackedTransformer:
+    """Device-resident, C-ABI-shaped copy of a MyTransformer's weights.
+
+    Per-head W_q/W_k/W_v (reference transformer.py:33-35) are concatenated into one (3d, d)
+    matrix per layer.  The pack is cached on the module and rebuilt when any parameter's
+    `_version` or storage changes (weights change between active-learning rounds).
+    """
+
+    def __init__(self, module, device: torch.device, compute: str = "fp32"):
+        self.device = device
+        L = len(module.layers)
+        d = module.d_model
+        first = module.layers[0] if L else None
+        H = first.self_attn.n_heads if L else 1
+        F = first.ff.net[0].out_features if L else 4
+
+        def dev(t):
+            return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+        def stack(fn):
+            return torch.stack([dev(fn(layer)) for layer in module.layers]).contiguous() if L else None
+
+        self.embedding = dev(module.embedding.weight)
+        self.pe = dev(module.pos_enc.pe[:, 0, :])
+        self.w_qkv = stack(lambda l: torch.cat(
+            [torch.cat([getattr(h, name).weight for h in l.self_attn.heads], 0) for name in ("W_q", "W_k", "W_v")], 0))
+        self.w_out = stack(lambda l: l.self_attn.W_out.weight)
+        self.ln1_w = stack(lambda l: l.norm1.weight)
+        self.ln1_b = stack(lambda l: l.norm1.bias)
+        self.ff1_w = stack(lambda l: l.ff.net[0].weight)
+        self.ff1_b = stack(lambda l: l.ff.net[0].bias)
+        self.ff2_w = stack(lambda l: l.ff.net[2].weight)
+        self.ff2_b = stack(lambda l: l.ff.net[2].bias)
+        self.ln2_w = stack(lambda l: l.norm2.weight)
+        self.ln2_b = stack(lambda l: l.norm2.bias)
+        self.head_w = dev(module.linear_out.weight)
+        self.head_b = dev(module.linear_out.bias)
+
+        flags, p = site_flags_of(module)
+        eps = first.norm1.eps if L else 1e-5
+        self.desc = _lib.Transformer(
+            ntoken=module.ntoken, d_model=d, n_heads=H, d_ff=F, n_layers=L, pe_len=self.pe.shape[0],
+            p_drop=float(p), site_flags=flags,
+            embedding=self.embedding.data_ptr(), pe=self.pe.data_ptr(),
+            w_qkv=_ptr(self.w_qkv), w_out=_ptr(self.w_out), ln1_w=_ptr(self.ln1_w), ln1_b=_ptr(self.ln1_b),
+            ff1_w=_ptr(self.ff1_w), ff1_b=_ptr(self.ff1_b), ff2_w=_ptr(self.ff2_w), ff2_b=_ptr(self.ff2_b),
+            ln2_w=_ptr(self.ln2_w), ln2_b=_ptr(self.ln2_b), head_w=self.head_w.data_ptr(),
+            head_b=self.head_b.data_ptr(), ln_eps=float(eps), compute=_lib.COMPUTE[compute])
+        self.ntoken = module.ntoken
+        self.d_model = d
+        self.n_layers = L
+        self.compute = compute
+        self._workspace: torch.Tensor | None = None
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+
+def site_flags_of(module) -> tuple[int, float]:
+    """Which always-on dropout sites of reference transformer.py are live for this module tree.
+
+    Under the public MyTransformer constructor only the embedding and layer-output sites can be
+    live (reference :324-335 never forwards `bayes` to the blocks); the block-level sites are
+    reachable by setting the sub-modules' attributes by hand and are honoured when every layer
+    agrees and a single rate is used.
+    """
+    flags = 0
+    rates = set()
+    if getattr(module, "bayes", False):
+        flags |= _lib.SITE_EMBED | _lib.SITE_LAYER_OUT
+        rates.add(module.bayes_dropout)
+    per_layer = []
+    for layer in module.layers:
+        lf = 0
+        if getattr(layer, "bayes", False):
+            lf |= _lib.SITE_ATTN_RESID | _lib.SITE_FFN_RESID
+            rates.add(layer.bayes_dropout)
+        if layer.ff.bayes_dropout is not None:
+            lf |= _lib.SITE_FFN_IN
+            rates.add(layer.ff.bayes_dropout)
+        if getattr(layer.self_attn, "bayes", False):
+            lf |= _lib.SITE_HEAD_OUT
+            rates.add(layer.self_attn.bayes_dropout)
+        if any(getattr(h, "bayes", False) for h in layer.self_attn.heads):
+            raise NotImplementedError(
+                "per-head Q/K/V input dropout (Head.bayes, reference transformer.py:50-53) is not on the native path")
+        per_layer.append(lf)
+    if len(set(per_layer)) > 1:
+        raise NotImplementedError("native path needs the same latent dropout sites in every layer")
+    if per_layer:
+        flags |= per_layer[0]
+    if not flags:
+        return 0, 0.0
+    if len(rates) != 1:
+        raise NotImplementedError(f"native path needs one dropout rate for all sites, got {sorted(map(str, rates))}")
+    p = rates.pop()
+    if p is None or not (0.0 <= float(p) < 1.0):
+        raise ValueError(f"dropout probability has to be in [0, 1), but got {p}")
+    return flags, float(p)
+
+
+# module -> (signature, pack).  Kept outside the module so copy.deepcopy / pickling of the
+# nn.Module (active_learning.ipynb cell 24) never sees ctypes pointers.
+_PACKS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _param_signature(module, device) -> tuple:
+    return (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + (
+        getattr(module, "bayes", False), getattr(module, "bayes_dropout", None))
+
+
+def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransformer:
+    """Cached PackedTransformer of `module` for `device` (rebuilt after any in-place weight update)."""
+    sig = _param_signature(module, device) + (compute,)
+    cache = _PACKS.get(module)
+    if cache is None or cache[0] != sig:
+        cache = (sig, PackedTransformer(module, device, compute))
+        _PACKS[module] = cache
+    return cache[1]
+
+
+def transformer_forward(pack: PackedTransformer, src: torch.Tensor, seed: int | None = None, draw: int | None = None,
+                        index_base: int = 0, mask_bits: torch.Tensor | None = None) -> torch.Tensor:
+    """MyTransformer.forward under eval/no_grad: src (len, B) int64 CUDA -> log-probs (len, B, V)."""
+    _require_cuda(src, "src")
+    if src.dim() != 2:
+        raise ValueError("src must be (T, B)")
+    src = src.to(torch.int64).contiguous()
+    length, batch = src.shape
+    dev = src.device
+    out = torch.empty(length, batch, pack.ntoken, dtype=torch.float32, device=dev)
+    if length == 0 or batch == 0:
+        return out
+    lib = _lib.load()
+    nbytes = lib.bfb200_transformer_workspace_bytes(C.byref(pack.desc), batch, length)
+    ws = pack.workspace(nbytes)
+    masks = _lib.Masks(seed=(default_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF,
+                       bits=_ptr(mask_bits), max_len=length)
+    if draw is None:
+        draw = _next_call_id() & 0xFFFFFFFF
+    with torch.cuda.device(dev):
+        _lib.check(lib.bfb200_transformer_forward(C.byref(pack.desc), src.data_ptr(), length, batch, C.byref(masks),
+                                                  draw, index_base, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  _stream_ptr(dev)))
+    return out
+
+
+@dataclass
+class McResult:
+    step_scores: torch.Tensor        # (N, B)
+    pool_scores: torch.Tensor        # (B,)
+    logp: torch.Tensor | None        # (N, B*T, V)
+    tokens: torch.Tensor | None      # (B*T, P+N)
+
+
+def mc_score_transformer(pack: PackedTransformer, prompts: torch.Tensor, new_tokens: int, n_draws: int,
+                         scheme: str, mode: str, temperature: float = 0.8, seed: int | None = None,
+                         index_base: int = 0, mask_bits: torch.Tensor | None = None, mask_max_len: int = 0,
+                         forced_tokens: torch.Tensor | None = None, return_logp: bool = False,
+                         return_tokens: bool = False, workspace_bytes: int | None = None) -> McResult:
+    """The loops of greedy/sampling/dropout_uncertainty (reference active_learning.py:38-155) with the
+    draws folded into the batch; prompts (P, B) int64 CUDA, seq-first as `get_batch` returns."""
+    if mode not in _lib.MODE:
+        raise ValueError(f"Unknown mode {mode}. Available modes are 'max', 'margin' and 'entropy'.")
+    if scheme not in _lib.SCHEME:
+        raise ValueError(
+            f"Unknown compute mode: {scheme}. For Transformer, use 'greedy' or 'sampling'. For BayesFormer, use 'dropout'.")
+    _require_cuda(prompts, "prompts")
+    prompts = prompts.to(torch.int64).contiguous()
+    P, B = prompts.shape
+    dev = prompts.device
+    N, T, V = int(new_tokens), int(n_draws), pack.ntoken
+    step_scores = torch.zeros(N, B, dtype=torch.float32, device=dev)
+    pool_scores = torch.zeros(B, dtype=torch.float32, device=dev)
+    logp = torch.empty(N, B * T, V, dtype=torch.float32, device=dev) if return_logp else None
+    tokens = torch.empty(B * T, P + N, dtype=torch.int32, device=dev) if return_tokens else None
+    if forced_tokens is not None:
+        forced_tokens = forced_tokens.to(device=dev, dtype=torch.int32).contiguous()
+        if tuple(forced_tokens.shape) != (N, B * T):
+            raise ValueError("forced_tokens must be (new_tokens, B * n_draws)")
+    if seed is None:
+        seed = default_seed() ^ (_next_call_id() << 32)
+    args = _lib.McArgs(
+        prompts=prompts.data_ptr(), n_items=B, prompt_len=P, new_tokens=N, n_draws=T, scheme=_lib.SCHEME[scheme],
+        mode=_lib.MODE[mode], temperature=float(temperature), index_base=index_base,
+        masks=_lib.Masks(seed=seed & 0xFFFFFFFFFFFFFFFF, bits=_ptr(mask_bits), max_len=mask_max_len),
+        forced_tokens=_ptr(forced_tokens), step_scores=step_scores.data_ptr(), pool_scores=pool_scores.data_ptr(),
+        logp_out=_ptr(logp), tokens_out=_ptr(tokens))
+    if B == 0 or N == 0:
+        return McResult(step_scores, pool_scores, logp, tokens)
+    lib = _lib.load()
+    if workspace_bytes is None:
+        workspace_bytes = default_mc_workspace_bytes(pack, args, B)
+    ws = pack.workspace(workspace_bytes)
+    with torch.cuda.device(dev):
+        _lib.check(lib.bfb200_mc_score_transformer(C.byref(pack.desc), C.byref(args), ws.data_ptr(), workspace_bytes,
+                                                   _stream_ptr(dev)))
+    return McResult(step_scores, pool_scores, logp, tokens)
+
+
+# Activations of one chunk are sized to stay well inside the 126 MB L2 where possible and never
+# above a few GB of the 180 GB HBM; the C side loops over chunks.
+_MAX_WORKSPACE_BYTES = 8 << 30
+
+
+def default_mc_workspace_bytes(pack: PackedTransformer, args, n_items: int) -> int:
+    lib = _lib.load()
+    full = lib.bfb200_mc_workspace_bytes(C.byref(pack.desc), C.byref(args), max(1, n_items))
+    if full <= _MAX_WORKSPACE_BYTES:
+        return full
+    one = lib.bfb200_mc_workspace_bytes(C.byref(pack.desc), C.byref(args), 1)
+    return max(one, _MAX_WORKSPACE_BYTES)

@@ -1,0 +1,244 @@
+/*
+ * bayesformer_b200.h — C ABI of libbayesformer_b200.so
+ *
+ * B200 (sm_100a) implementation of ONE hot path of Suzie14/Bayesformer:
+ * Monte-Carlo-dropout scoring of an unlabeled pool + uncertainty acquisition +
+ * top-k.  The reference has no FFI of its own (pure Python/PyTorch); each entry
+ * point below names the reference function (file:line under the reference tree)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer marked [dev] must be CUDA device memory of the current device;
+ *    the library has NO CPU path: host pointers are rejected with
+ *    BFB200_ERR_NOT_DEVICE_PTR.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    All work is enqueued asynchronously on it; nothing synchronises.
+ *  - functions return a BFB200_* status; bfb200_last_error() gives the message
+ *    of the last failure on the calling thread.
+ *  - no allocation happens inside: callers pass workspaces sized by the
+ *    *_workspace_bytes queries (torch owns all memory).
+ */
+#ifndef BAYESFORMER_B200_H
+#define BAYESFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFB200_ABI_VERSION 1
+
+enum {
+  BFB200_OK = 0,
+  BFB200_ERR_INVALID_ARG = 1,
+  BFB200_ERR_NOT_DEVICE_PTR = 2,
+  BFB200_ERR_WORKSPACE = 3,
+  BFB200_ERR_CUDA = 4,
+  BFB200_ERR_UNSUPPORTED = 5
+};
+
+/* uncertainty score, src/libs/active_learning.py:25-31 */
+enum { BFB200_MODE_MAX = 0, BFB200_MODE_MARGIN = 1, BFB200_MODE_ENTROPY = 2 };
+
+/* stochastic-prediction scheme, src/libs/active_learning.py:38,73,118 */
+enum { BFB200_SCHEME_GREEDY = 0, BFB200_SCHEME_SAMPLING = 1, BFB200_SCHEME_DROPOUT = 2 };
+
+/* arithmetic of the contractions */
+enum {
+  BFB200_COMPUTE_FP32 = 0, /* fp32 CUDA-core FMA everywhere (1e-3 parity class) */
+  BFB200_COMPUTE_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate,
+                              fp32 softmax / LayerNorm statistics (1e-2 parity class) */
+};
+
+/* always-on dropout sites of src/model/transformer.py (bit set = site live) */
+enum {
+  BFB200_SITE_EMBED = 1u << 0,      /* :355-358, mask (l,B,d) before the sqrt(d) scale   */
+  BFB200_SITE_LAYER_OUT = 1u << 1,  /* :368-370, mask (l,B,d) after every block          */
+  BFB200_SITE_ATTN_RESID = 1u << 2, /* :226, latent: TransformerBlock.bayes              */
+  BFB200_SITE_FFN_IN = 1u << 3,     /* :167-168, latent: FeedForward.bayes_dropout       */
+  BFB200_SITE_FFN_RESID = 1u << 4,  /* :228, latent: TransformerBlock.bayes              */
+  BFB200_SITE_HEAD_OUT = 1u << 5    /* :116-122, latent: MultiHeadAttention.bayes        */
+};
+
+/* site ids used in the Philox counter and in the packed-mask layout:
+ *   0                : embedding
+ *   1 + 5*i + 0      : layer i output        (LAYER_OUT)
+ *   1 + 5*i + 1      : layer i attn residual (ATTN_RESID)
+ *   1 + 5*i + 2      : layer i FFN input     (FFN_IN)
+ *   1 + 5*i + 3      : layer i FFN residual  (FFN_RESID)
+ *   1 + 5*i + 4      : layer i head outputs  (HEAD_OUT, all heads concatenated)
+ */
+#define BFB200_SITES_PER_LAYER 5
+#define BFB200_SITE_SAMPLING_TOKEN 0xFFFFu /* multinomial draw of the sampling scheme */
+#define BFB200_SITE_MLP_HIDDEN 0x100u      /* MLP hidden-layer dropout                 */
+#define BFB200_SITE_VMLP_EPS 0x101u        /* VariationalMLP weight noise              */
+
+/*
+ * Weights of src/model/transformer.py:MyTransformer (:290-375), fp32, row-major
+ * exactly as nn.Linear / nn.Embedding / nn.LayerNorm store them; the per-head
+ * W_q/W_k/W_v (:33-35) are concatenated: rows [0,d) = Q of heads 0..H-1,
+ * [d,2d) = K, [2d,3d) = V.
+ */
+typedef struct bfb200_transformer {
+  int32_t ntoken;   /* V */
+  int32_t d_model;  /* d */
+  int32_t n_heads;  /* H, d % H == 0 */
+  int32_t d_ff;     /* F */
+  int32_t n_layers; /* L */
+  int32_t pe_len;   /* rows of `pe` (5000 in the reference, :238) */
+  float p_drop;     /* bayes_dropout; ignored when site_flags == 0 */
+  uint32_t site_flags;
+  const float* embedding; /* [dev] (V, d) */
+  const float* pe;        /* [dev] (pe_len, d) */
+  const float* w_qkv;     /* [dev] (L, 3d, d) */
+  const float* w_out;     /* [dev] (L, d, d) */
+  const float* ln1_w;     /* [dev] (L, d) */
+  const float* ln1_b;     /* [dev] (L, d) */
+  const float* ff1_w;     /* [dev] (L, F, d) */
+  const float* ff1_b;     /* [dev] (L, F) */
+  const float* ff2_w;     /* [dev] (L, d, F) */
+  const float* ff2_b;     /* [dev] (L, d) */
+  const float* ln2_w;     /* [dev] (L, d) */
+  const float* ln2_b;     /* [dev] (L, d) */
+  const float* head_w;    /* [dev] (V, d) */
+  const float* head_b;    /* [dev] (V) */
+  float ln_eps;           /* 1e-5 (nn.LayerNorm default) */
+  int32_t compute;        /* BFB200_COMPUTE_* */
+} bfb200_transformer;
+
+/*
+ * Source of dropout masks.
+ *  - bits == NULL: counter-based Philox4x32-10, key = (seed_lo, seed_hi), counter =
+ *      (global item index, draw, (step << 16) | position, (site << 16) | (feature >> 2));
+ *      feature f uses output word f & 3 and is KEPT iff word >= keep_threshold(p) =
+ *      min(2^32 - 1, floor(p * 2^32)).  Results do not depend on batching, chunking
+ *      or the GPU a pool item lands on.
+ *  - bits != NULL (mask-injection mode used by the parity tests): bit-packed keep
+ *      masks, little-endian bit order inside uint32 words, laid out
+ *      [step][site][sequence][position < max_len][ceil(d/32) words]
+ *      with sequence = item * n_draws + draw, `n_sites` = 1 + 5 * L.
+ */
+typedef struct bfb200_masks {
+  uint64_t seed;
+  const uint32_t* bits; /* [dev] or NULL */
+  int32_t max_len;      /* position stride of `bits` */
+} bfb200_masks;
+
+/*
+ * One pool-scoring call: the loops of greedy_uncertainty / sampling_uncertainty /
+ * dropout_uncertainty (src/libs/active_learning.py:38-155) with the n_draws MC
+ * draws folded into the batch, followed by the step mean of select_samples (:209).
+ */
+typedef struct bfb200_mc_args {
+  const int64_t* prompts; /* [dev] (P, B) seq-first, as preprocessing.get_batch returns */
+  int64_t n_items;        /* B */
+  int32_t prompt_len;     /* P */
+  int32_t new_tokens;     /* N = answers_length + 1 */
+  int32_t n_draws;        /* T_mc (1 for greedy) */
+  int32_t scheme;         /* BFB200_SCHEME_* */
+  int32_t mode;           /* BFB200_MODE_* */
+  float temperature;      /* sampling scheme only (:104), 0.8 in the reference */
+  int64_t index_base;     /* global pool index of item 0 (RNG counter; sharding) */
+  bfb200_masks masks;
+  const int32_t* forced_tokens; /* [dev] (N, B * n_draws) or NULL: teacher-forced appended tokens */
+  float* step_scores;           /* [dev] (N, B): mean over draws of the per-draw score (:155) */
+  float* pool_scores;           /* [dev] (B) or NULL: mean over steps (:209) */
+  float* logp_out;              /* [dev] (N, B * n_draws, V) or NULL: last-position log-probs */
+  int32_t* tokens_out;          /* [dev] (B * n_draws, P + N) or NULL: full trajectories */
+} bfb200_mc_args;
+
+int bfb200_abi_version(void);
+const char* bfb200_last_error(void);
+
+/* compute_uncertainty, src/libs/active_learning.py:10-35. probs (B, C) -> out (B). */
+int bfb200_compute_uncertainty(const float* probs, int64_t n_rows, int32_t n_classes,
+                               int32_t mode, float* out, void* stream);
+
+/*
+ * Acquisition reduction over MC draws. x is (T, B, C) probabilities (is_logp = 0)
+ * or log-probabilities (is_logp = 1).  Any output may be NULL.
+ *   mean_p          (B, C) : predictive mean (src/libs/visualization.py:113)
+ *   score_of_mean   (3, B) : max / margin / entropy of mean_p
+ *   mean_of_scores  (3, B) : mean over draws of the per-draw score
+ *                            (what dropout_uncertainty accumulates, active_learning.py:152-155)
+ */
+int bfb200_acquire(const float* x, int32_t is_logp, int32_t n_draws, int64_t n_items,
+                   int32_t n_classes, float* mean_p, float* score_of_mean,
+                   float* mean_of_scores, void* stream);
+
+/*
+ * torch.topk(scores, k) of select_samples (active_learning.py:210), largest first,
+ * ties broken towards the LOWEST index.  Output: k packed 64-bit keys, descending:
+ *   key = (orderable(score) << 32) | (0xFFFFFFFF - (index_base + i))
+ * so that keys from several GPUs merge by plain integer comparison.
+ */
+size_t bfb200_topk_workspace_bytes(int64_t n, int32_t k);
+int bfb200_topk(const float* scores, int64_t n, int32_t k, int64_t index_base,
+                uint64_t* keys_out, void* workspace, size_t workspace_bytes, void* stream);
+/* top-k of already packed keys (the all-gathered per-GPU candidates). */
+int bfb200_merge_topk(const uint64_t* keys, int64_t n, int32_t k, uint64_t* keys_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* keys -> (scores, int64 indices) */
+int bfb200_unpack_keys(const uint64_t* keys, int32_t k, float* scores, int64_t* indices,
+                       void* stream);
+
+/*
+ * MC-dropout MLP classifier, src/model/bayesian_classification.py:184-198 driven by
+ * the loop of src/libs/visualization.py:105-113: n_draws x sigmoid(W2 drop(relu(W1 x + b1)) + b2).
+ *   x (B, in_dim); w1 (hidden, in_dim); b1 (hidden); w2 (1, hidden); b2 (1)
+ *   mask_bits: NULL (Philox) or [draw][item][ceil(hidden/32)] keep bits
+ *   probs_out (T, B) or NULL; mean_p (B) or NULL;
+ *   score_of_mean / mean_of_scores (3, B) over the 2-class distribution [1 - p, p], or NULL
+ */
+int bfb200_mlp_mc_score(const float* x, int64_t n_items, int32_t in_dim, int32_t hidden,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        float p_drop, int32_t n_draws, uint64_t seed, int64_t index_base,
+                        const uint32_t* mask_bits, float* probs_out, float* mean_p,
+                        float* score_of_mean, float* mean_of_scores, void* stream);
+
+/*
+ * Bayes-by-backprop MLP, src/model/bayesian_classification.py:118-130 with
+ * LinearVariational.sampling (:31-44): per draw W = mu + eps * log1p(exp(rho)), one
+ * weight draw shared by the whole pool.  eps (T, in_dim*hidden + hidden*1) fp32 [dev]
+ * holds the N(0,1) noise for (hidden_layer.w, output_layer.w) of every draw.
+ *   w1_mu/w1_rho (in_dim, hidden); b1 (hidden); w2_mu/w2_rho (hidden, 1); b2 (1)
+ */
+int bfb200_vmlp_mc_score(const float* x, int64_t n_items, int32_t in_dim, int32_t hidden,
+                         const float* w1_mu, const float* w1_rho, const float* b1,
+                         const float* w2_mu, const float* w2_rho, const float* b2,
+                         const float* eps, int32_t n_draws, float* probs_out, float* mean_p,
+                         float* score_of_mean, float* mean_of_scores, void* stream);
+
+/*
+ * MyTransformer.forward under eval()/no_grad (src/model/transformer.py:349-375):
+ * src (len, B) int64 seq-first -> log-probs (len, B, V).  `draw` selects the Philox
+ * stream of this call (masks->bits uses step 0, n_draws 1).
+ */
+size_t bfb200_transformer_workspace_bytes(const bfb200_transformer* model, int64_t n_sequences,
+                                          int32_t max_len);
+int bfb200_transformer_forward(const bfb200_transformer* model, const int64_t* src,
+                               int32_t len, int64_t batch, const bfb200_masks* masks,
+                               uint32_t draw, int64_t index_base, float* logp_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The MC scoring loop (see bfb200_mc_args).  The pool is processed in chunks that
+ * fit `workspace_bytes`; bfb200_mc_workspace_bytes(items_per_chunk) sizes it and any
+ * workspace >= the size for 1 item is accepted.
+ */
+size_t bfb200_mc_workspace_bytes(const bfb200_transformer* model, const bfb200_mc_args* args,
+                                 int64_t items_per_chunk);
+int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc_args* args,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches issued by this library on the calling thread since
+ * the last bfb200_reset_launch_count() (bench.py's gpu_launches). */
+int64_t bfb200_launch_count(void);
+void bfb200_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESFORMER_B200_H */
