@@ -115,8 +115,11 @@ _SIGNATURES = {
     ),
     "bfb200_mc_workspace_bytes": (C.c_size_t, [C.POINTER(Transformer), C.POINTER(McArgs), C.c_int64]),
     "bfb200_mc_score_transformer": (C.c_int, [C.POINTER(Transformer), C.POINTER(McArgs), _P, C.c_size_t, _P]),
+    "bfb200_step_mean": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "bfb200_launch_count": (C.c_int64, []),
     "bfb200_reset_launch_count": (None, []),
+    "bfb200_profile_begin": (C.c_int, [_P]),
+    "bfb200_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

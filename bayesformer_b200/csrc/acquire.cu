@@ -303,7 +303,7 @@ extern "C" int bfb200_compute_uncertainty(const float* probs, int64_t n_rows, in
   else if (n_classes <= 256) LAUNCH_CU(8);
   else LAUNCH_CU(32);
 #undef LAUNCH_CU
-  BFB_LAUNCH_CHECK("compute_uncertainty_kernel");
+  BFB_LAUNCH_CHECK("compute_uncertainty_kernel", st);
   return BFB200_OK;
 }
 
@@ -327,7 +327,7 @@ extern "C" int bfb200_acquire(const float* x, int32_t is_logp, int32_t n_draws, 
   else if (n_classes <= 256) LAUNCH_AQ(8);
   else LAUNCH_AQ(32);
 #undef LAUNCH_AQ
-  BFB_LAUNCH_CHECK("acquire_kernel");
+  BFB_LAUNCH_CHECK("acquire_kernel", st);
   return BFB200_OK;
 }
 
@@ -362,7 +362,7 @@ extern "C" int bfb200_mlp_mc_score(const float* x, int64_t n_items, int32_t in_d
   if (hidden <= 64) LAUNCH_MLP(64);
   else LAUNCH_MLP(128);
 #undef LAUNCH_MLP
-  BFB_LAUNCH_CHECK("mlp_mc_kernel");
+  BFB_LAUNCH_CHECK("mlp_mc_kernel", st);
   return BFB200_OK;
 }
 
@@ -386,6 +386,6 @@ extern "C" int bfb200_vmlp_mc_score(const float* x, int64_t n_items, int32_t in_
   const int grid = grid_for(n_items, 128, 8);
   vmlp_mc_kernel<<<grid, 128, smem, st>>>(x, n_items, in_dim, hidden, w1_mu, w1_rho, b1, w2_mu, w2_rho, b2,
                                           eps, n_draws, probs_out, mean_p, score_of_mean, mean_of_scores);
-  BFB_LAUNCH_CHECK("vmlp_mc_kernel");
+  BFB_LAUNCH_CHECK("vmlp_mc_kernel", st);
   return BFB200_OK;
 }

@@ -16,7 +16,7 @@ namespace bfb {
 // ----------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_device_ptr(const void* p, const char* name);  // BFB200_OK or error (message set)
-void count_launch();
+void count_launch(const char* name, cudaStream_t st);  // launch accounting + optional per-kernel event timing
 
 #define BFB_REQUIRE(cond, code, ...)      \
   do {                                    \
@@ -40,9 +40,9 @@ void count_launch();
     }                                                             \
   } while (0)
 
-#define BFB_LAUNCH_CHECK(name)                                                     \
+#define BFB_LAUNCH_CHECK(name, stream_)                                            \
   do {                                                                             \
-    ::bfb::count_launch();                                                         \
+    ::bfb::count_launch((name), (stream_));                                        \
     cudaError_t _e = cudaGetLastError();                                           \
     if (_e != cudaSuccess) {                                                       \
       ::bfb::set_error("launch of %s failed: %s", (name), cudaGetErrorString(_e)); \
@@ -70,7 +70,9 @@ __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
   constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = mulhi32(M0, c.x), lo0 = M0 * c.x;
     const uint32_t hi1 = mulhi32(M1, c.z), lo1 = M1 * c.z;

@@ -91,7 +91,7 @@ static int run_topk(const float* scores, const uint64_t* keys, int64_t n, int k,
       topk_chunk_kernel<true><<<(int)nb, TOPK_THREADS, smem, st>>>(scores, nullptr, cur_n, k, index_base, dst);
     else
       topk_chunk_kernel<false><<<(int)nb, TOPK_THREADS, smem, st>>>(nullptr, cur_keys, cur_n, k, 0, dst);
-    BFB_LAUNCH_CHECK("topk_chunk_kernel");
+    BFB_LAUNCH_CHECK("topk_chunk_kernel", st);
     if (nb == 1) break;
     from_scores = false;
     cur_keys = dst;
@@ -131,7 +131,8 @@ extern "C" int bfb200_unpack_keys(const uint64_t* keys, int32_t k, float* scores
   BFB_DEV(keys);
   BFB_DEV_OPT(scores);
   BFB_DEV_OPT(indices);
-  unpack_keys_kernel<<<(k + 255) / 256, 256, 0, (cudaStream_t)stream>>>(keys, k, scores, indices);
-  BFB_LAUNCH_CHECK("unpack_keys_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  unpack_keys_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys, k, scores, indices);
+  BFB_LAUNCH_CHECK("unpack_keys_kernel", st);
   return BFB200_OK;
 }

@@ -258,3 +258,13 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
   if (a.pool_scores != nullptr) BFB_CALL(launch_step_mean(a.step_scores, a.n_items, N, a.pool_scores, st));
   return BFB200_OK;
 }
+
+extern "C" int bfb200_step_mean(const float* step_scores, int32_t n_steps, int64_t n_items, float* pool_scores,
+                                void* stream) {
+  BFB_REQUIRE(n_steps >= 1 && n_items >= 0, BFB200_ERR_INVALID_ARG, "bad shape (N=%d, B=%lld)", n_steps,
+              (long long)n_items);
+  if (n_items == 0) return BFB200_OK;
+  BFB_DEV(step_scores);
+  BFB_DEV(pool_scores);
+  return launch_step_mean(step_scores, n_items, n_steps, pool_scores, (cudaStream_t)stream);
+}

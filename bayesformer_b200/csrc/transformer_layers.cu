@@ -469,7 +469,7 @@ int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t it
   const int grid = stride_grid((n_seq * prompt_len + 255) / 256, 8);
   init_tokens_kernel<<<grid, 256, 0, st>>>(prompts, n_items_total, item0, n_seq, n_draws, prompt_len,
                                            stride, vocab, tokens);
-  BFB_LAUNCH_CHECK("init_tokens_kernel");
+  BFB_LAUNCH_CHECK("init_tokens_kernel", st);
   return BFB200_OK;
 }
 
@@ -478,7 +478,7 @@ int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const 
   const int64_t total = n_seq * len * (d >> 2);
   const int grid = stride_grid((total + 255) / 256, 8);
   embed_kernel<<<grid, 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d, sqrtf((float)d), ms, site, x);
-  BFB_LAUNCH_CHECK("embed_kernel");
+  BFB_LAUNCH_CHECK("embed_kernel", st);
   return BFB200_OK;
 }
 
@@ -488,7 +488,7 @@ int launch_sgemm(const float* A, const float* W, const float* bias, float* C, in
   BFB_REQUIRE((K & 3) == 0, BFB200_ERR_UNSUPPORTED, "GEMM K=%d must be a multiple of 4", K);
   dim3 grid((unsigned)((M + GB_M - 1) / GB_M), (unsigned)((N + GB_N - 1) / GB_N));
   sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, a_row_mul, a_row_off, relu);
-  BFB_LAUNCH_CHECK("sgemm_tn_kernel");
+  BFB_LAUNCH_CHECK("sgemm_tn_kernel", st);
   return BFB200_OK;
 }
 
@@ -513,7 +513,7 @@ int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d
   else if (len <= 256) LAUNCH_ATT(8);
   else LAUNCH_ATT(32);
 #undef LAUNCH_ATT
-  BFB_LAUNCH_CHECK("attention_kernel");
+  BFB_LAUNCH_CHECK("attention_kernel", st);
   return BFB200_OK;
 }
 
@@ -530,7 +530,7 @@ int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, 
   else if (d4 <= 256) LAUNCH_LN(8);
   else LAUNCH_LN(32);
 #undef LAUNCH_LN
-  BFB_LAUNCH_CHECK("resid_ln_kernel");
+  BFB_LAUNCH_CHECK("resid_ln_kernel", st);
   return BFB200_OK;
 }
 
@@ -546,7 +546,7 @@ int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme,
   else if (vocab <= 256) LAUNCH_SC(8);
   else LAUNCH_SC(32);
 #undef LAUNCH_SC
-  BFB_LAUNCH_CHECK("score_step_kernel");
+  BFB_LAUNCH_CHECK("score_step_kernel", st);
   return BFB200_OK;
 }
 
@@ -561,7 +561,7 @@ int launch_logsoftmax_seqfirst(const float* logits, int64_t n_seq, int len, int 
   else if (vocab <= 256) LAUNCH_LS(8);
   else LAUNCH_LS(32);
 #undef LAUNCH_LS
-  BFB_LAUNCH_CHECK("logsoftmax_seqfirst_kernel");
+  BFB_LAUNCH_CHECK("logsoftmax_seqfirst_kernel", st);
   return BFB200_OK;
 }
 
@@ -569,7 +569,7 @@ int launch_reduce_draws(const float* seq_scores, int64_t n_items_chunk, int n_dr
                         cudaStream_t st) {
   reduce_draws_kernel<<<(unsigned)((n_items_chunk + 255) / 256), 256, 0, st>>>(seq_scores, n_items_chunk,
                                                                                 n_draws, dst);
-  BFB_LAUNCH_CHECK("reduce_draws_kernel");
+  BFB_LAUNCH_CHECK("reduce_draws_kernel", st);
   return BFB200_OK;
 }
 
@@ -577,7 +577,7 @@ int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, flo
                      cudaStream_t st) {
   step_mean_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(step_scores, n_items, n_steps,
                                                                        pool_scores);
-  BFB_LAUNCH_CHECK("step_mean_kernel");
+  BFB_LAUNCH_CHECK("step_mean_kernel", st);
   return BFB200_OK;
 }
 

@@ -145,6 +145,19 @@ def topk(scores: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
     return unpack_keys(topk_keys(scores, k))
 
 
+def step_mean(step_scores: torch.Tensor) -> torch.Tensor:
+    """`torch.mean(uncertainties, dim=0)` of select_samples (reference active_learning.py:209): (N, B) -> (B,)."""
+    _require_cuda(step_scores, "step_scores")
+    s = _f32c(step_scores)
+    if s.dim() != 2:
+        raise ValueError("step_scores must be (new_tokens, B)")
+    out = torch.empty(s.shape[1], dtype=torch.float32, device=s.device)
+    lib = _lib.load()
+    with torch.cuda.device(s.device):
+        _lib.check(lib.bfb200_step_mean(s.data_ptr(), s.shape[0], s.shape[1], out.data_ptr(), _stream_ptr(s.device)))
+    return out
+
+
 # ---------------------------------------------------------------------------
 # toy classifiers (src/model/bayesian_classification.py)
 # ---------------------------------------------------------------------------
@@ -364,6 +377,29 @@ def transformer_forward(pack: PackedTransformer, src: torch.Tensor, seed: int | 
                                                   draw, index_base, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                                   _stream_ptr(dev)))
     return out
+
+
+class profile:
+    """Context manager around bfb200_profile_begin/_end: per-kernel launch counts and device milliseconds
+    of everything the library launched on the current stream inside the block (bench.py's roofline leg)."""
+
+    def __init__(self, device: torch.device):
+        self.device = torch.device(device)
+        self.kernels: dict = {}
+
+    def __enter__(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().bfb200_profile_begin(_stream_ptr(self.device)))
+        return self
+
+    def __exit__(self, *exc):
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().bfb200_profile_end(buf, len(buf)))
+        self.kernels = json.loads(buf.value.decode())
+        return False
 
 
 @dataclass

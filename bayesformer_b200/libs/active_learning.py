@@ -5,7 +5,8 @@ error behaviour).  When the model lives on a CUDA device the three `*_uncertaint
 `compute_uncertainty` / `topk` run inside libbayesformer_b200.so: the `nb_samples` MC draws are
 folded into the batch, masks come from a counter-based Philox stream, and the whole greedy decode
 (no KV cache — fresh masks hit every position at every step, reference :145) is driven natively.
-On CPU tensors, or with autograd enabled, the eager loops below run — they restate the reference.
+There is no CPU fallback: a model or tensor that is not on a CUDA device raises RuntimeError, and so does a
+missing / stale libbayesformer_b200.so.
 
 Semantics kept on purpose: `mode="max"` returns the max probability and
 `mode="margin"` p(1) - p(2); `select_samples` then takes the LARGEST k, i.e. the most confident
@@ -27,36 +28,47 @@ def _bad_mode(mode) -> ValueError:
     return ValueError(f"Unknown mode {mode}. Available modes are 'max', 'margin' and 'entropy'.")
 
 
+def _no_cpu_path(what: str) -> RuntimeError:
+    return RuntimeError(
+        f"{what}: bayesformer_b200 runs the MC-scoring path only on a CUDA device (sm_100a) — there is no CPU "
+        "fallback. Move the model and tensors to a CUDA device.")
+
+
 def compute_uncertainty(probs: torch.Tensor, mode: str = "max") -> torch.Tensor:
-    """Score a batch of categorical distributions `probs (B, C)` → `(B,)` (reference :10-35)."""
+    """Score a batch of categorical distributions `probs (B, C)` → `(B,)` (reference :10-35).
+
+    Runs `bfb200_compute_uncertainty`.  Under autograd (training-time use, outside the hot path) the
+    same formulas are applied with differentiable ATen ops on the tensor's own device."""
     if mode not in _MODES:
         raise _bad_mode(mode)
-    if probs.is_cuda and not torch.is_grad_enabled() and probs.dim() == 2 and probs.shape[1] <= 1024:
-        from bayesformer_b200 import engine
-
-        return engine.compute_uncertainty(probs, mode)
-    if mode == "max":
-        return probs.max(dim=-1).values
-    if mode == "margin":
-        ranked = torch.sort(probs, dim=-1, descending=True).values
-        return ranked[:, 0] - ranked[:, 1]
-    return -(probs * torch.log(probs + 1e-10)).sum(dim=-1)
-
-
-def _native(model, prompts: torch.Tensor, device) -> bool:
-    """Native route: our MyTransformer, weights on a CUDA device, autograd off, inference semantics."""
-    if not isinstance(model, MyTransformer) or torch.is_grad_enabled():
-        return False
-    dev = torch.device(device)
-    if dev.type != "cuda" or not model.embedding.weight.is_cuda:
-        return False
-    return model._use_native(torch.empty(0, device=model.embedding.weight.device))
-
-
-def _native_scores(model, prompts, new_tokens, device, mode, scheme, n_draws, temperature=0.8):
+    if torch.is_grad_enabled() and probs.requires_grad:
+        if mode == "max":
+            return probs.max(dim=-1).values
+        if mode == "margin":
+            ranked = torch.sort(probs, dim=-1, descending=True).values
+            return ranked[:, 0] - ranked[:, 1]
+        return -(probs * torch.log(probs + 1e-10)).sum(dim=-1)
+    if not probs.is_cuda:
+        raise _no_cpu_path("compute_uncertainty")
     from bayesformer_b200 import engine
 
+    return engine.compute_uncertainty(probs, mode)
+
+
+def _scores(model, prompts, new_tokens, device, mode, scheme, n_draws, temperature=0.8):
+    """Common body of the three `*_uncertainty` functions: one `bfb200_mc_score_transformer` call."""
+    if mode not in _MODES:
+        raise _bad_mode(mode)
+    if not isinstance(model, MyTransformer):
+        raise TypeError("model must be a bayesformer_b200 MyTransformer")
     dev = model.embedding.weight.device
+    if dev.type != "cuda" or torch.device(device).type != "cuda":
+        raise _no_cpu_path(f"{scheme}_uncertainty")
+    if model.training and not model._train_only_dropout_inactive():
+        raise RuntimeError("call model.eval() first: the native path implements inference semantics "
+                           "(nn.Dropout sites off, always-on bayes sites live)")
+    from bayesformer_b200 import engine
+
     pack = model.native_pack(dev)
     res = engine.mc_score_transformer(pack, prompts.to(dev), new_tokens, n_draws, scheme, mode,
                                       temperature=temperature)
@@ -66,61 +78,19 @@ def _native_scores(model, prompts, new_tokens, device, mode, scheme, n_draws, te
 def greedy_uncertainty(model: MyTransformer, prompts: torch.Tensor, new_tokens: int, device: str,
                        mode: str = "max") -> torch.Tensor:
     """Deterministic greedy decode; per-step score of the next-token distribution → `(new_tokens, B)` (reference :38-70)."""
-    if mode not in _MODES:
-        raise _bad_mode(mode)
-    if _native(model, prompts, device):
-        return _native_scores(model, prompts, new_tokens, device, mode, "greedy", 1)
-    seq = prompts.to(device)
-    rows = []
-    for _ in range(new_tokens):
-        last = model(seq)[-1, :, :]
-        nxt = torch.argmax(last, -1).view(1, -1)
-        seq = torch.cat((seq, nxt), 0)
-        rows.append(compute_uncertainty(torch.softmax(last, dim=-1), mode).unsqueeze(0))
-    return torch.cat(rows, dim=0)
+    return _scores(model, prompts, new_tokens, device, mode, "greedy", 1)
 
 
 def sampling_uncertainty(model: MyTransformer, prompts: torch.Tensor, new_tokens: int, device: str,
                          mode: str = "max", temperature: float = 0.8, nb_samples: int = 20) -> torch.Tensor:
     """`nb_samples` temperature-sampled continuations; mean per-step score of the tempered distribution (reference :73-115)."""
-    if mode not in _MODES:
-        raise _bad_mode(mode)
-    if _native(model, prompts, device):
-        return _native_scores(model, prompts, new_tokens, device, mode, "sampling", nb_samples, temperature)
-    total = torch.zeros(new_tokens, prompts.shape[1]).to(device)
-    for _ in range(nb_samples):
-        seq = prompts
-        rows = []
-        for _ in range(new_tokens):
-            last = model(seq)[-1, :, :]
-            last /= temperature  # in place on the model output view, as the reference does (:104)
-            probs = torch.softmax(last, dim=-1)
-            nxt = torch.multinomial(probs, num_samples=1).view(1, -1)
-            seq = torch.cat((seq, nxt), dim=0)
-            rows.append(compute_uncertainty(probs, mode).unsqueeze(0))
-        total += torch.cat(rows, dim=0)
-    return total / nb_samples
+    return _scores(model, prompts, new_tokens, device, mode, "sampling", nb_samples, temperature)
 
 
 def dropout_uncertainty(model: MyTransformer, prompts: torch.Tensor, new_tokens: int, device: str,
                         mode: str = "max", nb_samples: int = 20) -> torch.Tensor:
     """`nb_samples` MC-dropout passes, each greedily decoding its own trajectory; mean per-step score (reference :118-155)."""
-    if mode not in _MODES:
-        raise _bad_mode(mode)
-    if _native(model, prompts, device):
-        return _native_scores(model, prompts, new_tokens, device, mode, "dropout", nb_samples)
-    total = torch.zeros(new_tokens, prompts.shape[1]).to(device)
-    for _ in range(nb_samples):
-        seq = prompts
-        rows = []
-        for _ in range(new_tokens):
-            last = model(seq)[-1, :, :]
-            probs = torch.softmax(last, dim=-1)
-            nxt = torch.argmax(last, -1).view(1, -1)
-            seq = torch.cat((seq, nxt), dim=0)
-            rows.append(compute_uncertainty(probs, mode).unsqueeze(0))
-        total += torch.cat(rows, dim=0)
-    return total / nb_samples
+    return _scores(model, prompts, new_tokens, device, mode, "dropout", nb_samples)
 
 
 _SCHEMES = {
@@ -144,13 +114,9 @@ def select_samples_from_tokens(model: MyTransformer, prompts: torch.Tensor, new_
     with torch.no_grad():
         prompts = prompts.to(device, non_blocking=True)
         scores = _SCHEMES[compute](model, prompts, new_tokens, device, mode)
-        pooled = torch.mean(scores, dim=0)
-        if pooled.is_cuda:
-            from bayesformer_b200 import engine
+        from bayesformer_b200 import engine
 
-            _, picked = engine.topk(pooled, nb_samples)
-        else:
-            _, picked = torch.topk(pooled, nb_samples)
+        _, picked = engine.topk(engine.step_mean(scores), nb_samples)
         return picked.tolist()
 
 

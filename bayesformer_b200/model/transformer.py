@@ -191,14 +191,19 @@ class MyTransformer(nn.Module):
         nn.init.zeros_(self.linear_out.bias)
 
     # -- routing ---------------------------------------------------------------------------
+    def _train_only_dropout_inactive(self) -> bool:
+        """True when the train-only nn.Dropout sites (:231, :233, :272) cannot fire: eval mode or rate 0."""
+        if not self.training:
+            return True
+        return self.pos_enc.dropout.p == 0 and all(l.dropout.p == 0 for l in self.layers)
+
     def _use_native(self, src: torch.Tensor) -> bool:
-        """CUDA tensors and no autograd → the sm_100a library; the train-only nn.Dropout sites must be
-        inactive (eval mode or rate 0), since the native path implements inference semantics."""
+        """CUDA tensors and no autograd → the sm_100a library (inference semantics).  Anything that needs
+        autograd (utils.train) runs the nn.Module stack below; that is the training path, not a fallback
+        of the scoring path — `active_learning.*` never uses it."""
         if not src.is_cuda or torch.is_grad_enabled():
             return False
-        if self.training and (self.pos_enc.dropout.p > 0 or any(l.dropout.p > 0 for l in self.layers)):
-            return False
-        return True
+        return self._train_only_dropout_inactive()
 
     def native_pack(self, device: torch.device | None = None, compute: str = "fp32"):
         """Device-resident packed weights for the C ABI (cached; see engine.packed)."""

@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""MC-scored pool samples/s of the BayesFormer acquisition hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): notebook-default BayesFormer
+`MyTransformer(114, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True)`, MC-dropout T=20, greedy decode of
+N=5 tokens from P=4-token prompts, margin scoring, top-k 200, over a synthetic pool of 100,000 3-digit
+addition prompts per GPU (weak scaling: rank r owns global indices [r*100k, (r+1)*100k); one NCCL
+all-gather of 200 candidate keys per rank merges the per-GPU top-k).  One "step" = one full
+score-and-select pass over the pool.
+
+Printed JSON (one line, rank 0): `value` = device-resident throughput (inputs already in HBM, CUDA events,
+max over ranks); `e2e` = the same pass through the reference-shaped public call
+(`sharding.select_samples_sharded` == `active_learning.select_samples` after tokenisation) with PINNED HOST
+prompts copied in and the acquired indices read back inside the timed region; `roofline` = the dominant
+kernel's algorithmic work / its CUDA-event time (per-kernel events recorded by the library on its launch
+stream in a separate instrumented pass of the same steps); `cpu_baseline` = the oracle port of the same
+workload timed on this box's host cores on a bounded sample.
+
+`--impl reference` times the CPU implementation (oracle port, torch CPU kernels on all host threads — the
+reference itself is Python driving torch and does not travel to the GPU box) and prints the same line shape.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "mc_scored_pool_samples_per_sec"
+UNIT = "pool samples/s"
+POOL_PER_GPU = 100_000
+T_MC, K_TOP, MODE, SCHEME = 20, 200, "margin", "dropout"
+D_MODEL, N_HEADS, D_FF, N_LAYERS, P_DROP = 64, 8, 8, 2, 0.3
+SEED = 42
+PAD_ID, EQ_ID, VOCAB = 112, 111, 114
+
+
+def synthetic_addition_prompts(n: int, seed: int, num_digits: int = 3) -> np.ndarray:
+    """(P=num_digits+1, n) int64 prompt ids of random `abc+def=` problems, identical to what
+    `preprocessing.get_batch(create_dataset(...), ReversedPairingTokenizer())` produces for the same operands
+    (units-first digit-pair tokens, '=', left-padded with PAD; tests/test_bench_inputs.py pins this)."""
+    rng = np.random.RandomState(seed)
+    digits = rng.randint(0, 10, size=(n, 2, num_digits))          # most significant digit first
+    sig = np.maximum(num_digits - (np.cumsum(digits, axis=2) == 0).sum(axis=2), 1)  # length without leading zeros (>= 1)
+    width = sig.max(axis=1)                                        # pairs per prompt
+    pair = (digits[:, 0, ::-1] * 10 + digits[:, 1, ::-1])          # units first
+    P = num_digits + 1
+    out = np.full((n, P), PAD_ID, dtype=np.int64)
+    for w in range(1, num_digits + 1):
+        rows = np.nonzero(width == w)[0]
+        out[rows, P - 1 - w:P - 1] = pair[rows, :w]
+    out[:, P - 1] = EQ_ID
+    return np.ascontiguousarray(out.T)
+
+
+def build_model():
+    """The notebook-default BayesFormer with the trained fixture weights (tests/golden/c2_transformer.npz,
+    recorded from the reference's own `utils.train`; throughput does not depend on the values)."""
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(SEED)
+    model = MyTransformer(VOCAB, D_MODEL, N_HEADS, D_FF, N_LAYERS, bayes_dropout=P_DROP, bayes=True)
+    path = os.path.join(ROOT, "tests", "golden", "c2_transformer.npz")
+    weights = "random-init(seed 42)"
+    if os.path.exists(path):
+        z = np.load(path)
+        sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+        sd["pos_enc.pe"] = model.pos_enc.pe.clone()
+        model.load_state_dict(sd)
+        weights = "trained fixture (tests/golden/c2_transformer.npz)"
+    return model.eval(), weights
+
+
+def flops_per_pool_sample(P: int, N: int) -> float:
+    """flops_forward(l) = L(8 l d^2 + 4 l d F + 2 l (l+1) d) + 2 d V, summed over the N decode steps, x T."""
+    d, F, L, V = D_MODEL, D_FF, N_LAYERS, VOCAB
+    return T_MC * sum(L * (8 * l * d * d + 4 * l * d * F + 2 * l * (l + 1) * d) + 2 * d * V for l in range(P, P + N))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+        return False
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+
+
+def cpu_port_pass(sd, prompts: torch.Tensor, N: int, k: int):
+    """One score-and-select pass of the oracle restatement (oracle/restatement.py — the checker, here the
+    thing timed as the CPU baseline) with fresh Bernoulli masks drawn the way F.dropout draws them."""
+    from oracle import restatement as R
+
+    live = R.default_live_sites(N_LAYERS, True)
+    S = prompts.shape[1] * T_MC
+
+    def step_fn(_step):
+        def fn(site, n_pos):
+            if site not in live:
+                return None
+            return torch.empty(n_pos, S, D_MODEL).bernoulli_(1 - P_DROP).bool()
+        return fn
+
+    with torch.no_grad():
+        out = R.mc_scores(sd, prompts, N, T_MC, SCHEME, MODE, P_DROP, step_fn)
+        return R.topk_lowest_index(out["pool_scores"].numpy(), min(k, prompts.shape[1]))
+
+
+def time_cpu_port(model, prompts_np: np.ndarray, N: int, sample: int, steps: int, warmup: int) -> dict:
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    prompts = torch.from_numpy(prompts_np[:, :sample])
+    for _ in range(warmup):
+        cpu_port_pass(sd, prompts[:, : max(64, sample // 8)], N, K_TOP)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_port_pass(sd, prompts, N, K_TOP)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} pool items x T={T_MC} x N={N} steps per pass ({dt:.2f} s/pass, mean of {steps}), "
+                      f"oracle/restatement.py on torch {torch.__version__} CPU kernels, {cores} threads",
+            "seconds_per_pass": dt}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, weights = build_model()
+    P, N = 4, 5
+    sample = 2000
+    prompts_np = synthetic_addition_prompts(sample, SEED)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    base = time_cpu_port(model, prompts_np, N, sample, min(steps, 5), min(warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": min(steps, 5), "warmup": min(warmup, 1), "ms_per_step": base["seconds_per_pass"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(P, N, args.gpus, weights) | {"bounded_sample_items": sample},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(P: int, N: int, gpus: int, weights: str) -> dict:
+    return {
+        "workload": "BASELINE configs[1] / SURVEY C2ii: MyTransformer(114,64,8,8,2,bayes_dropout=0.3,bayes=True), "
+                    "MC-dropout T=20, greedy decode N=5 from P=4 prompts, margin score, top-k 200, "
+                    f"{POOL_PER_GPU} synthetic addition prompts per GPU",
+        "pool_per_gpu": POOL_PER_GPU, "pool_total": POOL_PER_GPU * gpus, "T_mc": T_MC, "prompt_len": P,
+        "new_tokens": N, "mode": MODE, "scheme": SCHEME, "k": K_TOP, "weights": weights,
+        "parallelism": f"pool-sharded x{gpus} (replicated weights, all-gather of {K_TOP} keys/rank)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL_PER_GPU, help="pool items per GPU (default = the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+
+    from bayesformer_b200 import _lib, engine, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the CUDA path has no CPU fallback); "
+                           "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    W, K = max(3, args.warmup), max(1, args.steps)
+    pool = args.pool
+    P, N = 4, 5
+
+    model, weights = build_model()
+    model = model.to(dev)
+    pack = model.native_pack(dev)
+    # this rank's shard of the global pool: global indices [rank*pool, (rank+1)*pool)
+    prompts_np = synthetic_addition_prompts(pool, SEED + rank)
+    index_base = rank * pool
+    prompts_host = torch.from_numpy(prompts_np).pin_memory()
+    prompts_dev = prompts_host.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def resident_step():
+        res = engine.mc_score_transformer(pack, prompts_dev, N, T_MC, SCHEME, MODE, seed=SEED, index_base=index_base)
+        keys = engine.topk_keys(res.pool_scores, K_TOP, index_base=index_base)
+        if world > 1:
+            keys = engine.merge_topk_keys(sharding.gather_candidate_keys(keys, K_TOP), K_TOP)
+        return keys
+
+    def e2e_step():
+        return sharding.select_samples_sharded(model, prompts_host, N, dev, nb_samples=K_TOP, compute=SCHEME, mode=MODE,
+                                               index_base=index_base, n_total=pool * world, seed=SEED, n_draws=T_MC)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- device-resident throughput ---------------------------------------------------------------
+    for _ in range(W):
+        keys = resident_step()
+    barrier()
+    lib.bfb200_reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(K):
+            keys = resident_step()
+        ev1.record(stream)
+        barrier()
+    launches = int(lib.bfb200_launch_count())
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / K
+    value = pool * world / (ms_step * 1e-3)
+    picked_resident = engine.unpack_keys(keys)[1].tolist()
+
+    # --- end to end through the public call, host buffers in / indices out ---------------------------
+    for _ in range(W):
+        picked = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(K):
+        picked = e2e_step()
+    ev1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms)) / K
+    e2e_value = pool * world / (e2e_ms * 1e-3)
+    assert picked == picked_resident, "e2e and resident passes must acquire the same indices (same seed)"
+
+    # --- per-kernel timing (instrumented pass of the same steps) and roofline of the dominant kernel ----
+    barrier()
+    with engine.profile(dev) as prof:
+        for _ in range(min(K, 3)):
+            resident_step()
+    kernels = prof.kernels
+    total_kernel_ms = sum(v["ms"] for v in kernels.values()) or 1.0
+    top_name = max(kernels, key=lambda n: kernels[n]["ms"])
+    shares = {n: round(v["ms"] / total_kernel_ms, 4) for n, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks, peak_src = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+    if os.path.exists(peaks_path):
+        peaks.update(json.load(open(peaks_path)))
+        peak_src = "measured"
+    roofline = kernel_roofline(top_name, kernels[top_name], min(K, 3), pool, P, N, peaks, peak_src)
+    roofline["kernel_shares"] = shares
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(P, N, world, weights) | {
+            "pool_per_gpu": pool,
+            "l2": "no explicit flush: each step streams its multi-GB activation workspace, far above the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(prompts_host.numel() * prompts_host.element_size()) * world,
+                "d2h_bytes_per_step": K_TOP * 8 * world},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "whole_path_tensor_roofline": {
+            "flops_per_pool_sample": flops_per_pool_sample(P, N),
+            "achieved_tflops_per_gpu": value / world * flops_per_pool_sample(P, N) / 1e12,
+            "peak_tflops": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
+            "frac": value / world * flops_per_pool_sample(P, N) / 1e12 / peaks["bf16_tflops_sustained"]},
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in
+                                    time_cpu_port(model, prompts_np, N, 2000, 2, 1).items() if k != "seconds_per_pass"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(name: str, stat: dict, passes: int, pool: int, P: int, N: int, peaks: dict, peak_src: str) -> dict:
+    """Roofline entry of the dominant kernel: algorithmic bytes or flops of ALL its launches in the instrumented
+    passes / its total CUDA-event time (DESIGN.md §Kernels gives the per-unit figures used here)."""
+    d, F, L, V = D_MODEL, D_FF, N_LAYERS, VOCAB
+    S = pool * T_MC
+    rows = S * sum(range(P, P + N))            # token rows per pass (every position recomputed every step)
+    ms = stat["ms"]
+    avg_ms = ms / max(1, stat["launches"])
+    hbm = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    if name == "sgemm_tn_kernel":
+        flops = passes * (rows * L * (8 * d * d + 4 * d * F) + N * S * 2 * d * V)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "avg_launch_ms": avg_ms, "peak_source": peak_src,
+                "note": "fp32 CUDA-core GEMM measured against the bf16 tensor peak"}
+    if name == "mc_forward_kernel":
+        flops = passes * pool * flops_per_pool_sample(P, N)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "avg_launch_ms": avg_ms, "peak_source": peak_src}
+    per_row = {"attention_kernel": 4 * d * 4,            # read q,k,v + write out
+               "resid_ln_kernel": 3 * d * 4,             # read x, y + write out
+               "embed_kernel": 4 + d * 4}.get(name)
+    if per_row is None:
+        return {"kernel": name, **hbm, "achieved": None, "frac": None, "traffic": None, "avg_launch_ms": avg_ms,
+                "peak_source": peak_src}
+    mult = {"attention_kernel": L, "resid_ln_kernel": 2 * L, "embed_kernel": 1}[name]
+    ach = passes * rows * mult * per_row / (ms * 1e-3) / 1e9
+    return {"kernel": name, **hbm, "achieved": ach, "frac": ach / peaks["hbm_gbs"], "traffic": None,
+            "avg_launch_ms": avg_ms, "peak_source": peak_src}
+
+
+if __name__ == "__main__":
+    main()

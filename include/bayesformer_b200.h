@@ -233,10 +233,23 @@ size_t bfb200_mc_workspace_bytes(const bfb200_transformer* model, const bfb200_m
 int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc_args* args,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
+ * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */
+int bfb200_step_mean(const float* step_scores, int32_t n_steps, int64_t n_items, float* pool_scores,
+                     void* stream);
+
 /* number of kernel launches issued by this library on the calling thread since
  * the last bfb200_reset_launch_count() (bench.py's gpu_launches). */
 int64_t bfb200_launch_count(void);
 void bfb200_reset_launch_count(void);
+
+/*
+ * Per-kernel device timing for bench.py's roofline leg (no reference counterpart).  Between
+ * _begin and _end every kernel launch of the calling thread is followed by a CUDA event on its stream;
+ * _end synchronises and writes {"kernel_name": {"launches": n, "ms": total}, ...} into json_out.
+ */
+int bfb200_profile_begin(void* stream);
+int bfb200_profile_end(char* json_out, size_t json_bytes);
 
 #ifdef __cplusplus
 }

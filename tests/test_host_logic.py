@@ -1,0 +1,152 @@
+"""CPU-side tests: C-ABI library loads and exports every declared symbol, host mirrors of the reference's
+tokenizer / batch layout reproduce its known answers, bench inputs match the tokenizer, and the product
+refuses to run the scoring path without CUDA (no CPU fallback)."""
+
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from bayesformer_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "bayesformer_b200.h")).read()
+    declared = set(re.findall(r"\b(bfb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.bfb200_abi_version() == _lib.ABI_VERSION
+    # argument validation happens before any device work
+    assert lib.bfb200_compute_uncertainty(None, 4, 3, 7, None, None) == _lib.ERR_INVALID_ARG
+    assert b"Unknown mode" in lib.bfb200_last_error()
+    assert lib.bfb200_topk_workspace_bytes(1_000_000, 200) > 0
+
+
+def test_struct_layouts_match_header_sizes():
+    import ctypes as C
+
+    from bayesformer_b200 import _lib
+
+    # 6 int32 + float + uint32 (32 B) + 14 pointers (112 B) + float + int32 (8 B)
+    assert C.sizeof(_lib.Transformer) == 152
+    assert C.sizeof(_lib.Masks) == 24
+    assert C.sizeof(_lib.McArgs) == 8 + 8 + 4 * 5 + 4 + 8 + 24 + 8 * 5
+
+
+def test_no_cpu_path():
+    from bayesformer_b200.libs import active_learning as al
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    m = MyTransformer(114, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval()
+    prompts = torch.zeros(4, 3, dtype=torch.int64)
+    for fn in (al.greedy_uncertainty, al.sampling_uncertainty, al.dropout_uncertainty):
+        with pytest.raises(RuntimeError, match="no CPU"):
+            fn(m, prompts, 5, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        al.compute_uncertainty(torch.rand(3, 4), "max")
+    with pytest.raises(ValueError):
+        al.compute_uncertainty(torch.rand(3, 4), "nope")
+    with pytest.raises(ValueError):
+        al.select_samples_from_tokens(m, prompts, 5, "cpu", 2, compute="nope")
+    assert al.create_new_train_set([("a", "b")], [("c", "d"), ("e", "f")], [1]) == [("a", "b"), ("e", "f")]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from bayesformer_b200 import _lib
+
+    monkeypatch.setenv("BAYESFORMER_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_module_contract_matches_reference():
+    """state_dict names / parameter count of active_learning.ipynb cells 12-13 (50,178) and autograd."""
+    import copy
+
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    m = MyTransformer(114, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True)
+    assert sum(p.numel() for p in m.parameters()) == 50178
+    z = H.load("c2_transformer.npz")
+    names = {k[3:] for k in z.files if k.startswith("sd.")} | {"pos_enc.pe"}
+    assert set(m.state_dict().keys()) == names
+    m2 = copy.deepcopy(m)
+    out = m2(torch.randint(0, 114, (5, 3)))
+    out.sum().backward()
+    assert m2.embedding.weight.grad is not None and out.shape == (5, 3, 114)
+
+
+def test_module_forward_matches_reference_outputs():
+    """The autograd nn.Module stack (training path) reproduces the reference's stored greedy log-probs."""
+    z = H.load("c2_transformer.npz")
+    model = H.build_model(H.state_dict_from(z), None, False)
+    with torch.no_grad():
+        out = model(torch.from_numpy(z["prompts"]))
+    np.testing.assert_allclose(out[-1].numpy(), z["greedy.logp"][0], rtol=2e-5, atol=2e-5)
+
+
+def test_tokenizer_and_get_batch_known_answers():
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import CharacterLevelTokenizer, ReversedPairingTokenizer
+
+    rp, ch = ReversedPairingTokenizer(), CharacterLevelTokenizer()
+    assert rp.ntokens == 114 and ch.ntokens == 14
+    assert rp.encode("21+352=") == [12, 25, 3, 111]          # SURVEY §4 known answers
+    assert rp.encode("440+420=") == [0, 42, 44, 111]
+    assert rp.encode("007+003=") == [73, 111]
+    assert rp.encode("1560") == [100, 106, 105, 101]
+    X, Y, P, A, _, _ = preprocessing.get_batch([("440+420=", "860"), ("007+003=", "10"), ("937+623=", "1560")], rp, 0, 3)
+    assert X.t().tolist() == [[0, 42, 44, 111], [112, 112, 73, 111], [73, 32, 96, 111]]
+    assert Y.t().tolist() == [[100, 106, 108, 113, 112], [100, 101, 113, 112, 112], [100, 106, 105, 101, 113]]
+    assert (P, A) == (4, 4) and X.dtype == torch.int64
+    js = json.load(open(os.path.join(H.GOLDEN, "tokenizer.json")))
+    for c in js["cases"]:
+        assert rp.encode(c["prompt"]) == c["rp_prompt"] and rp.encode(c["answer"]) == c["rp_answer"]
+        assert rp.decode(c["rp_prompt"] + c["rp_answer"]) == c["rp_decode_full"]
+        assert ch.encode(c["prompt"]) == c["ch_prompt"] and ch.encode(c["answer"]) == c["ch_answer"]
+    batch = [tuple(b) for b in js["batch"]]
+    Xb, Yb, Pb, Ab, _, _ = preprocessing.get_batch(batch, rp, 0, len(batch))
+    assert Xb.tolist() == js["rp_batch"]["X"] and Yb.tolist() == js["rp_batch"]["Y"]
+    assert (Pb, Ab) == (js["rp_batch"]["P"], js["rp_batch"]["A"])
+    assert rp.vocabulary.vocab == js["rp_vocab"] and ch.vocab == js["ch_vocab"]
+    assert rp.decode([112, 112, 73, 111, 100, 101, 113, 112]) == js["decode_padded"]
+
+
+def test_bench_synthetic_prompts_equal_tokenizer_output():
+    import bench
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    n = 3000
+    got = bench.synthetic_addition_prompts(n, seed=7)
+    rng = np.random.RandomState(7)
+    digits = rng.randint(0, 10, size=(n, 2, 3))
+    pool = [("".join(map(str, d[0])) + "+" + "".join(map(str, d[1])) + "=", "0") for d in digits]
+    X, _, P, _, _, _ = preprocessing.get_batch(pool, ReversedPairingTokenizer(), 0, n)
+    assert P == 4 and np.array_equal(got, X.numpy())
+    assert bench.flops_per_pool_sample(4, 5) == pytest.approx(44.36e6, rel=1e-3)
+
+
+def test_shard_bounds_cover_pool():
+    from bayesformer_b200 import sharding
+
+    for n, g in ((1_000_000, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [sharding.shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(10, 2, 2)
+    assert sharding.local_candidates(200, 50) == 50 and sharding.local_candidates(200, 5000) == 200
