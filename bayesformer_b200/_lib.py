@@ -11,13 +11,13 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID_ARG, ERR_NOT_DEVICE_PTR, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 
 MODE = {"max": 0, "margin": 1, "entropy": 2}
 SCHEME = {"greedy": 0, "sampling": 1, "dropout": 2}
-COMPUTE = {"fp32": 0, "bf16": 1}
+COMPUTE = {"fp32": 0, "fp16": 1}
 
 SITE_EMBED = 1 << 0
 SITE_LAYER_OUT = 1 << 1
@@ -56,6 +56,7 @@ class Transformer(C.Structure):
         ("head_b", C.c_void_p),
         ("ln_eps", C.c_float),
         ("compute", C.c_int32),
+        ("fused_image", C.c_void_p),
     ]
 
 
@@ -115,6 +116,8 @@ _SIGNATURES = {
     ),
     "bfb200_mc_workspace_bytes": (C.c_size_t, [C.POINTER(Transformer), C.POINTER(McArgs), C.c_int64]),
     "bfb200_mc_score_transformer": (C.c_int, [C.POINTER(Transformer), C.POINTER(McArgs), _P, C.c_size_t, _P]),
+    "bfb200_fused_image_bytes": (C.c_size_t, [C.POINTER(Transformer)]),
+    "bfb200_fused_pack": (C.c_int, [C.POINTER(Transformer), _P, C.c_size_t, _P]),
     "bfb200_step_mean": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "bfb200_launch_count": (C.c_int64, []),
     "bfb200_reset_launch_count": (None, []),

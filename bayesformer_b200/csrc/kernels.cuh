@@ -26,4 +26,13 @@ int launch_reduce_draws(const float* seq_scores, int64_t n_items_chunk, int n_dr
 int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, float* pool_scores,
                      cudaStream_t st);
 
+
+// fused MC-forward kernel (mc_fused.cu)
+bool fused_supported(const bfb200_transformer& m);
+size_t fused_image_bytes(const bfb200_transformer& m);
+int fused_pack(const bfb200_transformer& m, void* image, size_t bytes, cudaStream_t st);
+int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, int32_t* tokens_out, int tok_stride,
+                            int64_t n_seq, int len, int scheme, int mode, float temperature, const MaskSource& ms,
+                            const int32_t* forced, float* seq_scores, float* logp_out, cudaStream_t st);
+
 }  // namespace bfb

@@ -1,0 +1,752 @@
+// Fused MC-forward kernel for the notebook-default model class (d_model = 64, 8 heads of 8, F <= 64,
+// V <= 128, sequences of at most 16 tokens): ONE kernel runs the whole forward pass of a decode step —
+// embedding + MC dropout + positional encoding, every TransformerBlock (QKV / W_out / FFN contractions on
+// tcgen05 tensor cores with fp16 operands and fp32 TMEM accumulators, causal attention, both
+// residual + LayerNorm pairs, the always-on dropout sites), the last-position vocabulary head, log-softmax,
+// the per-draw uncertainty score and the next token — with every activation resident on chip.
+//
+// Layout.  A CTA holds the complete fp16 weight image (pre-swizzled by fused_pack_kernel, fetched with 1-D
+// bulk TMA copies) in shared memory and runs two independent 128-thread groups.  A group owns a tile of
+// floor(128 / len) whole sequences = up to 128 token rows:
+//   * row phases    — thread = token row: reads its fp32 accumulator row from TMEM (tcgen05.ld 32x32b), does
+//                     bias / ReLU / residual / LayerNorm / dropout in registers, writes the next operand row as
+//                     fp16 into the 128-byte-swizzled K-major tile the next tcgen05.mma consumes;
+//   * pair phase    — thread = (sequence, head): causal softmax(QK^T / sqrt(dh)) V over <= 16 keys from the
+//                     fp16 Q/K/V tiles (a head's 8 values are exactly one 16-byte swizzle chunk);
+//   * score phase   — 4 or 8 threads per sequence: log-softmax over the vocabulary, probabilities, max /
+//                     margin / entropy, greedy arg-max or inverse-CDF sample.
+// The residual stream x stays in fp32 in 64 TMEM columns of the group.  HBM traffic per sequence and step:
+// len token ids in, one score and one token out.
+//
+// Reference arithmetic: src/model/transformer.py:349-375 (forward), :211-234 (block), :37-65 (head),
+// :151-170 (FFN); src/libs/active_learning.py:62-68 / :103-112 / :146-152 (per-step scoring).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace bfb {
+
+namespace {
+
+constexpr int FD = 64;          // d_model
+constexpr int FH = 8;           // heads
+constexpr int FDH = 8;          // head width
+constexpr int FROWS = 128;      // token rows per group tile (UMMA M)
+constexpr int FGROUPS = 2;      // independent 128-thread groups per CTA
+constexpr int FMAXLEN = 16;     // longest sequence the fused path takes
+constexpr int FMAXV = 128;
+constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
+constexpr int PARAMS_PER_LAYER = 6 * 64;      // ln1_w, ln1_b, b1, b2, ln2_w, ln2_b (floats)
+
+struct FusedLayout {
+  uint32_t fp;            // F rounded up to 16
+  uint32_t vp;            // V rounded up to 16
+  uint32_t layer_bytes;   // matrices of one layer
+  uint32_t off_out, off_w1, off_w2;  // inside a layer (qkv at 0)
+  uint32_t off_head;      // absolute
+  uint32_t off_params;    // absolute
+  uint32_t image_bytes;   // multiple of 1024
+};
+
+__host__ __device__ inline FusedLayout fused_layout(int L, int F, int V) {
+  FusedLayout lay;
+  lay.fp = (uint32_t)((F + 15) / 16 * 16);
+  lay.vp = (uint32_t)((V + 15) / 16 * 16);
+  lay.off_out = 3 * FD * 128;
+  lay.off_w1 = lay.off_out + FD * 128;
+  lay.off_w2 = lay.off_w1 + lay.fp * 128;
+  lay.layer_bytes = lay.off_w2 + FD * 128;
+  lay.off_head = (uint32_t)L * lay.layer_bytes;
+  lay.off_params = lay.off_head + lay.vp * 128;
+  const uint32_t n_param_floats = (uint32_t)L * PARAMS_PER_LAYER + FMAXV + FMAXLEN * FD;
+  lay.image_bytes = (lay.off_params + n_param_floats * 4 + 1023u) & ~1023u;
+  return lay;
+}
+
+constexpr size_t kFusedStaticSlack = 2048;  // alignment slack + static __shared__ of the kernel
+
+inline size_t fused_smem_bytes(const FusedLayout& lay) {
+  return 1024 + (size_t)lay.image_bytes + (size_t)FGROUPS * 3 * TILE_BYTES;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight image: fp16 matrices in the swizzled K-major layout + fp32 vectors
+// ------------------------------------------------------------------------------------------
+__global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t* __restrict__ image) {
+  const int L = m.n_layers, F = m.d_ff, V = m.ntoken;
+  const int per_layer = 3 * FD * FD + FD * FD + F * FD + FD * F;
+  const int n_mat = L * per_layer + V * FD;
+  const int n_par = L * PARAMS_PER_LAYER + FMAXV + FMAXLEN * FD;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mat + n_par; i += gridDim.x * blockDim.x) {
+    if (i < n_mat) {
+      float w;
+      uint32_t base, n, k;
+      if (i < L * per_layer) {
+        const int l = i / per_layer;
+        int j = i - l * per_layer;
+        base = (uint32_t)l * lay.layer_bytes;
+        if (j < 3 * FD * FD) {                       // W_qkv (3d, d)
+          n = j / FD; k = j % FD; w = m.w_qkv[(size_t)l * 3 * FD * FD + j];
+        } else if ((j -= 3 * FD * FD) < FD * FD) {   // W_out (d, d)
+          n = j / FD; k = j % FD; w = m.w_out[(size_t)l * FD * FD + j]; base += lay.off_out;
+        } else if ((j -= FD * FD) < F * FD) {        // FFN W1 (F, d)
+          n = j / FD; k = j % FD; w = m.ff1_w[(size_t)l * F * FD + j]; base += lay.off_w1;
+        } else {                                     // FFN W2 (d, F): K = F
+          j -= F * FD;
+          n = j / F; k = j % F; w = m.ff2_w[(size_t)l * FD * F + j]; base += lay.off_w2;
+        }
+      } else {                                       // vocabulary head (V, d)
+        const int j = i - L * per_layer;
+        n = j / FD; k = j % FD; w = m.head_w[j]; base = lay.off_head;
+      }
+      const uint32_t off = base + umma::sw128_offset(n, k >> 3) + (k & 7u) * 2u;
+      *reinterpret_cast<__half*>(image + off) = __float2half_rn(fminf(fmaxf(w, -65504.f), 65504.f));
+    } else {
+      const int j = i - n_mat;
+      float v = 0.f;
+      if (j < L * PARAMS_PER_LAYER) {
+        const int l = j / PARAMS_PER_LAYER, q = j % PARAMS_PER_LAYER, which = q >> 6, c = q & 63;
+        switch (which) {
+          case 0: v = m.ln1_w[l * FD + c]; break;
+          case 1: v = m.ln1_b[l * FD + c]; break;
+          case 2: v = c < F ? m.ff1_b[l * F + c] : 0.f; break;
+          case 3: v = m.ff2_b[l * FD + c]; break;
+          case 4: v = m.ln2_w[l * FD + c]; break;
+          default: v = m.ln2_b[l * FD + c]; break;
+        }
+      } else if (j < L * PARAMS_PER_LAYER + FMAXV) {
+        const int c = j - L * PARAMS_PER_LAYER;
+        v = c < V ? m.head_b[c] : 0.f;
+      } else {
+        const int q = j - L * PARAMS_PER_LAYER - FMAXV;  // pe[pos][c], pos < FMAXLEN
+        const int pos = q >> 6;
+        v = pos < m.pe_len ? m.pe[(size_t)pos * FD + (q & 63)] : 0.f;
+      }
+      reinterpret_cast<float*>(image + lay.off_params)[j] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+struct FusedArgs {
+  const uint8_t* image;
+  const float* embedding;      // (V, 64) fp32
+  FusedLayout lay;
+  int n_layers, d_ff, vocab;
+  uint32_t site_flags;
+  float ln_eps;
+  // this launch
+  int len;                     // tokens per sequence in this step
+  int spt;                     // sequences per tile = 128 / len
+  int tps;                     // score-phase threads per sequence (4 or 8)
+  int64_t n_seq;               // sequences in the chunk
+  int64_t n_tiles;
+  const int32_t* tokens;       // (n_seq, tok_stride)
+  int32_t* tokens_out;         // same buffer (token appended at column len) or nullptr
+  int tok_stride;
+  int scheme, mode;
+  float temperature;
+  const int32_t* forced;       // (n_seq) or nullptr
+  float* seq_scores;           // (n_seq)
+  float* logp_out;             // (n_seq, V) or nullptr
+  MaskSource ms;
+};
+
+// per-row addressing of the mask source, hoisted out of the feature loops
+struct RowRng {
+  uint32_t item, draw;
+  int64_t seq_abs;  // bits mode: seq_base + s
+};
+
+__device__ __forceinline__ RowRng make_row_rng(const MaskSource& m, int64_t s) {
+  RowRng r;
+  r.item = (uint32_t)(uint64_t)(m.item_base + s / m.n_draws);
+  r.draw = m.draw_base + (uint32_t)(s % m.n_draws);
+  r.seq_abs = m.seq_base + s;
+  return r;
+}
+
+// keep bits of features [8*f8, 8*f8 + 8) of (row, site): bit j = feature 8*f8 + j
+__device__ __forceinline__ uint32_t keep8(const MaskSource& m, const RowRng& rr, uint32_t pos, uint32_t site,
+                                          uint32_t f8) {
+  if (m.bits != nullptr) {
+    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + rr.seq_abs) * m.max_len + pos;
+    const uint32_t w = m.bits[row * m.words + (f8 >> 2)];
+    return (w >> ((f8 & 3u) * 8u)) & 0xFFu;
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 2; ++q) {
+    const uint4 r = philox4x32_10(make_uint4(rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (2 * f8 + q)), m.key);
+    const uint32_t k4 = (r.x >= m.threshold ? 1u : 0u) | (r.y >= m.threshold ? 2u : 0u) |
+                        (r.z >= m.threshold ? 4u : 0u) | (r.w >= m.threshold ? 8u : 0u);
+    out |= k4 << (4 * q);
+  }
+  return out;
+}
+
+// v[0..63] = keep ? v * scale : 0 for one row
+__device__ __forceinline__ void drop_row(float (&v)[FD], const MaskSource& m, const RowRng& rr, uint32_t pos,
+                                         uint32_t site) {
+#pragma unroll
+  for (uint32_t f8 = 0; f8 < 8; ++f8) {
+    const uint32_t k = keep8(m, rr, pos, site, f8);
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) v[8 * f8 + j] = ((k >> j) & 1u) ? v[8 * f8 + j] * m.scale : 0.f;
+  }
+}
+
+__device__ __forceinline__ void store_row_f16(uint8_t* tile, uint32_t row, const float (&v)[FD]) {
+#pragma unroll
+  for (uint32_t c = 0; c < 8; ++c) {
+    uint4 w;
+    w.x = umma::pack_f16x2(v[8 * c + 0], v[8 * c + 1]);
+    w.y = umma::pack_f16x2(v[8 * c + 2], v[8 * c + 3]);
+    w.z = umma::pack_f16x2(v[8 * c + 4], v[8 * c + 5]);
+    w.w = umma::pack_f16x2(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(tile + umma::sw128_offset(row, c)) = w;
+  }
+}
+
+__device__ __forceinline__ void tmem_load_row64(uint32_t taddr, float (&v)[FD]) {
+  uint32_t a[32], b[32];
+  umma::tmem_ld32(taddr, a);
+  umma::tmem_ld32(taddr + 32, b);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(a[i]);
+    v[32 + i] = __uint_as_float(b[i]);
+  }
+}
+
+__device__ __forceinline__ void tmem_store_row64(uint32_t taddr, const float (&v)[FD]) {
+  uint32_t a[32], b[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    a[i] = __float_as_uint(v[i]);
+    b[i] = __float_as_uint(v[32 + i]);
+  }
+  umma::tmem_st32(taddr, a);
+  umma::tmem_st32(taddr + 32, b);
+  umma::tmem_st_wait();
+}
+
+// LayerNorm of one row held in registers (biased variance, eps inside the sqrt: nn.LayerNorm)
+__device__ __forceinline__ void layer_norm_row(float (&v)[FD], const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < FD; ++i) s += v[i];
+  const float mean = s * (1.0f / FD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < FD; ++i) {
+    const float c = v[i] - mean;
+    q = fmaf(c, c, q);
+  }
+  const float rstd = 1.0f / sqrtf(q * (1.0f / FD) + eps);
+#pragma unroll
+  for (int i = 0; i < FD; ++i) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+}
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
+  const float2 a = umma::unpack_f16x2(w.x), b = umma::unpack_f16x2(w.y);
+  const float2 c = umma::unpack_f16x2(w.z), d = umma::unpack_f16x2(w.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// reductions over an aligned group of `n` (power of two <= 32) lanes
+__device__ __forceinline__ float sub_max(float v, int n) {
+  for (int o = n >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sub_sum(float v, int n) {
+  for (int o = n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int MAXLEN>
+__global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const FusedArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_image;
+  __shared__ uint64_t bar_group[FGROUPS];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x;
+  const int g = tid >> 7, gt = tid & 127, gw = gt >> 5;
+  const FusedLayout lay = a.lay;
+  uint8_t* img = smem;
+  uint8_t* B0 = smem + lay.image_bytes + (uint32_t)g * 3u * TILE_BYTES;
+  uint8_t* B1 = B0 + TILE_BYTES;
+  uint8_t* B2 = B1 + TILE_BYTES;
+  const float* params = reinterpret_cast<const float*>(img + lay.off_params);
+
+  if (tid < 32) {
+    umma::tmem_alloc(&tmem_slot, 512);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar_image, 1);
+    umma::mbar_init(&bar_group[0], 1);
+    umma::mbar_init(&bar_group[1], 1);
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  if (tid == 0) {
+    umma::mbar_expect_tx(&bar_image, lay.image_bytes);
+    for (uint32_t off = 0; off < lay.image_bytes; off += 16384u) {
+      const uint32_t n = lay.image_bytes - off < 16384u ? lay.image_bytes - off : 16384u;
+      umma::bulk_g2s(img + off, a.image + off, n, &bar_image);
+    }
+  }
+  umma::mbar_wait(&bar_image, 0);
+
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t lane_base = (uint32_t)(gw * 32) << 16;
+  const uint32_t tX = tmem_base + (uint32_t)g * 256u + lane_base;  // residual stream, 64 columns
+  const uint32_t tW = tX + 64u;                                     // accumulators, 192 columns
+  const uint32_t tW_mma = tmem_base + (uint32_t)g * 256u + 64u;     // same, lane field 0 for the MMA
+  uint64_t* bar = &bar_group[g];
+  uint32_t phase = 0;
+  const int bar_id = 1 + g;
+
+  const int len = a.len, spt = a.spt;
+  const int seq_l = gt / len, pos = gt - seq_l * len;
+  const float sqrt_d = sqrtf((float)FD), sqrt_dh = sqrtf((float)FDH);
+  const uint32_t fl = a.site_flags;
+  const MaskSource& ms = a.ms;
+
+  const uint32_t descA0 = umma::smem_u32(B0), descA1 = umma::smem_u32(B1);
+  const uint32_t img_u32 = umma::smem_u32(img);
+
+  // one GEMM phase: operand rows are in shared memory -> accumulators in TMEM columns [tW, tW + N)
+  auto gemm = [&](uint32_t a_addr, uint32_t b_addr, int N, int k_steps) {
+    umma::fence_async_smem();
+    umma::tc_fence_before_sync();
+    umma::group_sync(bar_id, FROWS);
+    if (gt == 0) {
+      umma::tc_fence_after_sync();
+      const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
+      const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
+      for (int k = 0; k < k_steps; ++k) umma::mma_bf16_ss(tW_mma, da + 2 * k, db + 2 * k, idesc, k > 0);
+      umma::mma_commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::tc_fence_after_sync();
+  };
+
+  for (int64_t tile = (int64_t)blockIdx.x * FGROUPS + g; tile < a.n_tiles; tile += (int64_t)gridDim.x * FGROUPS) {
+    const int64_t s0 = tile * spt;
+    const int nseq = (int)((a.n_seq - s0) < spt ? (a.n_seq - s0) : spt);
+    const bool row_valid = seq_l < nseq;
+    const int64_t s = s0 + (row_valid ? seq_l : 0);
+    const RowRng rr = make_row_rng(ms, s);
+
+    // ---- embedding + dropout E + sqrt(d) scale + positional encoding (transformer.py:355-362) ----
+    {
+      float x[FD];
+      if (row_valid) {
+        const int tok = a.tokens[s * a.tok_stride + pos];
+        const float4* e = reinterpret_cast<const float4*>(a.embedding + (size_t)tok * FD);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 v = __ldg(e + i);
+          x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+        if (fl & BFB200_SITE_EMBED) drop_row(x, ms, rr, (uint32_t)pos, 0u);
+        const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD;
+#pragma unroll
+        for (int i = 0; i < FD; ++i) x[i] = x[i] * sqrt_d + pe[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < FD; ++i) x[i] = 0.f;
+      }
+      tmem_store_row64(tX, x);
+      store_row_f16(B0, gt, x);
+    }
+
+    for (int l = 0; l < a.n_layers; ++l) {
+      const uint32_t wl = img_u32 + (uint32_t)l * lay.layer_bytes;
+      const float* pl = params + l * PARAMS_PER_LAYER;
+      const uint32_t sb = 1u + BFB200_SITES_PER_LAYER * (uint32_t)l;
+
+      // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
+      gemm(descA0, wl, 3 * FD, 4);
+      {
+        float v[FD];
+        tmem_load_row64(tW + 64, v);       // K
+        store_row_f16(B1, gt, v);
+        tmem_load_row64(tW + 128, v);      // V
+        store_row_f16(B2, gt, v);
+        tmem_load_row64(tW, v);            // Q
+        store_row_f16(B0, gt, v);         // x (fp16) is dead once the product has completed
+      }
+      umma::tc_fence_before_sync();
+      umma::group_sync(bar_id, FROWS);
+
+      // ---- causal attention, thread = (sequence, head) (transformer.py:58-65) ----
+      for (int p = gt; p < nseq * FH; p += FROWS) {
+        const int sl = p >> 3, h = p & 7;
+        const uint32_t row0 = (uint32_t)(sl * len);
+        // K / V of this (sequence, head): unpacked once for short sequences, kept packed (4 registers per key)
+        // and unpacked on use for the 16-token variant
+        constexpr bool kUnpacked = MAXLEN <= 8;
+        float kf[kUnpacked ? MAXLEN : 1][8], vf[kUnpacked ? MAXLEN : 1][8];
+        uint4 kp[kUnpacked ? 1 : MAXLEN], vp[kUnpacked ? 1 : MAXLEN];
+#pragma unroll
+        for (int j = 0; j < MAXLEN; ++j) {
+          if (j < len) {
+            const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j, h));
+            const uint4 vw = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j, h));
+            if constexpr (kUnpacked) {
+              unpack8(kw, kf[j]);
+              unpack8(vw, vf[j]);
+            } else {
+              kp[j] = kw;
+              vp[j] = vw;
+            }
+          }
+        }
+        const RowRng prr = make_row_rng(ms, s0 + sl);
+#pragma unroll
+        for (int t = 0; t < MAXLEN; ++t) {
+          if (t < len) {
+            uint8_t* qptr = B0 + umma::sw128_offset(row0 + t, h);
+            float q[8];
+            unpack8(*reinterpret_cast<const uint4*>(qptr), q);
+            float sc[MAXLEN];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j <= t; ++j) {
+              float d = 0.f;
+              float kj[8];
+              if constexpr (kUnpacked) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) kj[c] = kf[j][c];
+              } else {
+                unpack8(kp[j], kj);
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) d = fmaf(q[c], kj[c], d);
+              d = d / sqrt_dh;
+              sc[j] = d;
+              mx = fmaxf(mx, d);
+            }
+            float z = 0.f;
+#pragma unroll
+            for (int j = 0; j <= t; ++j) {
+              sc[j] = expf(sc[j] - mx);
+              z += sc[j];
+            }
+            float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j <= t; ++j) {
+              const float pj = sc[j] / z;
+              float vj[8];
+              if constexpr (kUnpacked) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) vj[c] = vf[j][c];
+              } else {
+                unpack8(vp[j], vj);
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, vj[c], o[c]);
+            }
+            if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
+              const uint32_t k = keep8(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)h);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
+            }
+            uint4 w;
+            w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
+            w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(qptr) = w;
+          }
+        }
+      }
+
+      // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
+      gemm(descA0, wl + lay.off_out, FD, 4);
+      {
+        float v[FD], x[FD];
+        tmem_load_row64(tW, v);
+        if (fl & BFB200_SITE_ATTN_RESID) drop_row(v, ms, rr, (uint32_t)pos, sb + 1u);
+        tmem_load_row64(tX, x);
+#pragma unroll
+        for (int i = 0; i < FD; ++i) v[i] += x[i];
+        layer_norm_row(v, pl, pl + 64, a.ln_eps);
+        if (fl & BFB200_SITE_FFN_IN) drop_row(v, ms, rr, (uint32_t)pos, sb + 2u);
+        store_row_f16(B0, gt, v);
+      }
+
+      // ---- FFN: Linear(d -> F) + bias + ReLU (transformer.py:151-155) ----
+      gemm(descA0, wl + lay.off_w1, (int)lay.fp, 4);
+      {
+        const float* b1 = pl + 128;
+        for (uint32_t c0 = 0; c0 < lay.fp; c0 += 16) {
+          uint32_t r[16];
+          umma::tmem_ld16(tW + c0, r);
+          umma::tmem_ld_wait();
+          uint4 w0, w1;
+          float hcol[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hcol[i] = fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
+          w0.x = umma::pack_f16x2(hcol[0], hcol[1]); w0.y = umma::pack_f16x2(hcol[2], hcol[3]);
+          w0.z = umma::pack_f16x2(hcol[4], hcol[5]); w0.w = umma::pack_f16x2(hcol[6], hcol[7]);
+          w1.x = umma::pack_f16x2(hcol[8], hcol[9]); w1.y = umma::pack_f16x2(hcol[10], hcol[11]);
+          w1.z = umma::pack_f16x2(hcol[12], hcol[13]); w1.w = umma::pack_f16x2(hcol[14], hcol[15]);
+          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(gt, c0 >> 3)) = w0;
+          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(gt, (c0 >> 3) + 1)) = w1;
+        }
+      }
+
+      // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
+      gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+      {
+        float v[FD], x[FD];
+        tmem_load_row64(tW, v);
+        const float* b2 = pl + 192;
+#pragma unroll
+        for (int i = 0; i < FD; ++i) v[i] += b2[i];
+        if (fl & BFB200_SITE_FFN_RESID) drop_row(v, ms, rr, (uint32_t)pos, sb + 3u);
+        tmem_load_row64(tX, x);
+#pragma unroll
+        for (int i = 0; i < FD; ++i) v[i] += x[i];
+        layer_norm_row(v, pl + 256, pl + 320, a.ln_eps);
+        if (fl & BFB200_SITE_LAYER_OUT) drop_row(v, ms, rr, (uint32_t)pos, sb + 0u);   // transformer.py:370
+        if (l + 1 < a.n_layers) tmem_store_row64(tX, v);
+        store_row_f16(B0, gt, v);
+      }
+    }
+
+    // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
+    gemm(descA0, img_u32 + lay.off_head, (int)lay.vp, 4);
+    const int stage_stride = (int)lay.vp + a.tps;
+    float* stage = reinterpret_cast<float*>(B1);  // B1 + B2: 32 KB
+    {
+      const float* hb = params + a.n_layers * PARAMS_PER_LAYER;
+      const bool is_last = row_valid && pos == len - 1;
+      for (uint32_t c0 = 0; c0 < lay.vp; c0 += 16) {
+        uint32_t r[16];
+        umma::tmem_ld16(tW + c0, r);
+        umma::tmem_ld_wait();
+        if (is_last) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) stage[seq_l * stage_stride + c0 + i] = __uint_as_float(r[i]) + hb[c0 + i];
+        }
+      }
+    }
+    umma::tc_fence_before_sync();
+    umma::group_sync(bar_id, FROWS);
+
+    // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
+    {
+      const int tps = a.tps, V = a.vocab;
+      const int sl = gt / tps, sub = gt - sl * tps;
+      constexpr int NPT = FMAXV / 4;  // classes per thread at tps = 4
+      const bool active = sl < nseq;
+      const float* row = stage + (active ? sl : 0) * stage_stride;
+      float lg[NPT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = sub + j * tps;
+        lg[j] = c < V ? row[c] : -INFINITY;
+        mx = fmaxf(mx, lg[j]);
+      }
+      mx = sub_max(mx, tps);
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) z += (sub + j * tps) < V ? expf(lg[j] - mx) : 0.f;
+      const float lse = logf(sub_sum(z, tps));
+      const int64_t sq = s0 + (active ? sl : 0);
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = sub + j * tps;
+        if (c < V) {
+          lg[j] = (lg[j] - mx) - lse;  // log-probabilities
+          if (a.logp_out != nullptr && active) a.logp_out[sq * V + c] = lg[j];
+          if (lg[j] > best) { best = lg[j]; best_i = c; }
+        }
+      }
+      for (int o = tps >> 1; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+      }
+      // probs = softmax(log-probs [/ temperature]) (active_learning.py:67, :104-105, :147)
+      float pr[NPT];
+      float pm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        pr[j] = a.scheme == BFB200_SCHEME_SAMPLING ? lg[j] / a.temperature : lg[j];
+        if ((sub + j * tps) < V) pm = fmaxf(pm, pr[j]);
+      }
+      pm = sub_max(pm, tps);
+      float pz = 0.f;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        pr[j] = (sub + j * tps) < V ? expf(pr[j] - pm) : 0.f;
+        pz += pr[j];
+      }
+      pz = sub_sum(pz, tps);
+      float p1 = -INFINITY, ent = 0.f;
+      int p1_i = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = sub + j * tps;
+        pr[j] = pr[j] / pz;
+        if (c < V) {
+          if (pr[j] > p1) { p1 = pr[j]; p1_i = c; }
+          ent += pr[j] * logf(pr[j] + 1e-10f);
+        }
+      }
+      for (int o = tps >> 1; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, p1, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, p1_i, o);
+        if (ob > p1 || (ob == p1 && oi < p1_i)) { p1 = ob; p1_i = oi; }
+      }
+      float p2 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = sub + j * tps;
+        if (c < V && c != p1_i) p2 = fmaxf(p2, pr[j]);
+      }
+      p2 = sub_max(p2, tps);
+      ent = -sub_sum(ent, tps);
+
+      int token = best_i;
+      if (a.scheme == BFB200_SCHEME_SAMPLING) {
+        // inverse CDF in class order from one Philox word (the library's documented sampling rule)
+        const RowRng srr = make_row_rng(ms, sq);
+        const uint4 rnd = philox4x32_10(
+            make_uint4(srr.item, srr.draw, ms.step << 16, BFB200_SITE_SAMPLING_TOKEN << 16), ms.key);
+        const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float running = 0.f;
+        int first = V - 1;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+          float c = pr[j];
+          for (int o = 1; o < tps; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, c, o, tps);
+            if (sub >= o) c += up;
+          }
+          c += running;
+          const int cls = sub + j * tps;
+          if (c > u && cls < V && cls < first) first = cls;
+          running = __shfl_sync(0xffffffffu, c, tps - 1, tps);
+        }
+        for (int o = tps >> 1; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        token = first;
+      }
+      if (active && sub == 0) {
+        a.seq_scores[sq] = a.mode == BFB200_MODE_MAX ? p1 : (a.mode == BFB200_MODE_MARGIN ? p1 - p2 : ent);
+        if (a.forced != nullptr) token = a.forced[sq];
+        if (a.tokens_out != nullptr && len < a.tok_stride) a.tokens_out[sq * a.tok_stride + len] = token;
+      }
+    }
+    // the staging rows are rewritten only after the next tile's first product: barriers in between order it
+  }
+
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+bool fused_supported(const bfb200_transformer& m) {
+  if (m.d_model != FD || m.n_heads != FH || m.n_layers < 1) return false;
+  if (m.d_ff < 1 || m.d_ff > 64 || m.ntoken < 2 || m.ntoken > FMAXV) return false;
+  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
+  return fused_smem_bytes(lay) + kFusedStaticSlack <= 227 * 1024;
+}
+
+size_t fused_image_bytes(const bfb200_transformer& m) {
+  return fused_supported(m) ? fused_layout(m.n_layers, m.d_ff, m.ntoken).image_bytes : 0;
+}
+
+int fused_pack(const bfb200_transformer& m, void* image, size_t bytes, cudaStream_t st) {
+  BFB_REQUIRE(fused_supported(m), BFB200_ERR_UNSUPPORTED, "model shape is outside the fused kernel's class");
+  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
+  BFB_REQUIRE(bytes >= lay.image_bytes, BFB200_ERR_WORKSPACE, "fused image buffer too small: %zu < %u", bytes,
+              lay.image_bytes);
+  cudaError_t e = cudaMemsetAsync(image, 0, lay.image_bytes, st);
+  BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+  fused_pack_kernel<<<64, 256, 0, st>>>(m, lay, (uint8_t*)image);
+  BFB_LAUNCH_CHECK("fused_pack_kernel", st);
+  return BFB200_OK;
+}
+
+int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, int32_t* tokens_out, int tok_stride,
+                            int64_t n_seq, int len, int scheme, int mode, float temperature, const MaskSource& ms,
+                            const int32_t* forced, float* seq_scores, float* logp_out, cudaStream_t st) {
+  BFB_REQUIRE(m.fused_image != nullptr, BFB200_ERR_INVALID_ARG, "compute=f16 needs model.fused_image (bfb200_fused_pack)");
+  BFB_REQUIRE(len >= 1 && len <= FMAXLEN, BFB200_ERR_UNSUPPORTED, "fused kernel takes sequences of 1..%d tokens (got %d)",
+              FMAXLEN, len);
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.image = (const uint8_t*)m.fused_image;
+  a.embedding = m.embedding;
+  a.lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
+  a.n_layers = m.n_layers; a.d_ff = m.d_ff; a.vocab = m.ntoken;
+  a.site_flags = m.site_flags;
+  a.ln_eps = m.ln_eps;
+  a.len = len;
+  a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 4 threads
+  a.tps = (FROWS / a.spt) >= 8 ? 8 : 4;
+  a.n_seq = n_seq;
+  a.n_tiles = (n_seq + a.spt - 1) / a.spt;
+  a.tokens = tokens; a.tokens_out = tokens_out; a.tok_stride = tok_stride;
+  a.scheme = scheme; a.mode = mode; a.temperature = temperature;
+  a.forced = forced; a.seq_scores = seq_scores; a.logp_out = logp_out;
+  a.ms = ms;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const size_t smem = fused_smem_bytes(a.lay);
+  int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  if (len <= 8) {
+    cudaFuncSetAttribute(mc_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mc_forward_kernel<8><<<(int)grid, FGROUPS * FROWS, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(mc_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mc_forward_kernel<16><<<(int)grid, FGROUPS * FROWS, smem, st>>>(a);
+  }
+  BFB_LAUNCH_CHECK("mc_forward_kernel", st);
+  return BFB200_OK;
+}
+
+}  // namespace bfb
+
+extern "C" size_t bfb200_fused_image_bytes(const bfb200_transformer* model) {
+  return model == nullptr ? 0 : bfb::fused_image_bytes(*model);
+}
+
+extern "C" int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream) {
+  using namespace bfb;
+  BFB_REQUIRE(model != nullptr, BFB200_ERR_INVALID_ARG, "model is NULL");
+  BFB_DEV(image);
+  BFB_DEV(model->embedding); BFB_DEV(model->pe); BFB_DEV(model->head_w); BFB_DEV(model->head_b);
+  BFB_DEV(model->w_qkv); BFB_DEV(model->w_out); BFB_DEV(model->ln1_w); BFB_DEV(model->ln1_b); BFB_DEV(model->ff1_w);
+  BFB_DEV(model->ff1_b); BFB_DEV(model->ff2_w); BFB_DEV(model->ff2_b); BFB_DEV(model->ln2_w); BFB_DEV(model->ln2_b);
+  return fused_pack(*model, image, image_bytes, (cudaStream_t)stream);
+}

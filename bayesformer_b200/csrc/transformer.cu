@@ -21,7 +21,11 @@ struct Workspace {
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // bytes for n_seq sequences of at most max_len tokens; full_logits: logits for every row
+static bool use_fused(const bfb200_transformer& m) { return m.compute == BFB200_COMPUTE_F16; }
+
 static size_t workspace_bytes(const bfb200_transformer& m, int64_t n_seq, int max_len, bool full_logits) {
+  if (use_fused(m) && !full_logits)  // fused path: activations never leave the chip
+    return 256 + align256((size_t)n_seq * max_len * sizeof(int32_t)) + align256((size_t)n_seq * sizeof(float));
   const size_t R = (size_t)n_seq * max_len;
   const size_t d = m.d_model, F = m.d_ff, V = m.ntoken;
   size_t b = 256;
@@ -41,6 +45,11 @@ static Workspace carve(void* base, const bfb200_transformer& m, int64_t n_seq, i
   Workspace w;
   auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return q; };
   w.tokens = (int32_t*)take((size_t)n_seq * max_len * sizeof(int32_t));
+  if (use_fused(m) && !full_logits) {
+    w.seq_scores = (float*)take((size_t)n_seq * sizeof(float));
+    w.x = w.att = w.y = w.x1 = w.qkv = w.h = w.logits = nullptr;
+    return w;
+  }
   w.x = (float*)take(R * d * sizeof(float));
   w.att = (float*)take(R * d * sizeof(float));
   w.y = (float*)take(R * d * sizeof(float));
@@ -59,10 +68,14 @@ static int validate_model(const bfb200_transformer* m) {
   BFB_REQUIRE(m->d_model % m->n_heads == 0, BFB200_ERR_INVALID_ARG, "d_model must be divisible by n_heads");
   BFB_REQUIRE((m->d_model & 3) == 0 && (m->d_ff & 3) == 0, BFB200_ERR_UNSUPPORTED,
               "d_model (%d) and dim_feedforward (%d) must be multiples of 4", m->d_model, m->d_ff);
-  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_BF16,
+  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_F16,
               BFB200_ERR_INVALID_ARG, "unknown compute type %d", m->compute);
-  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32, BFB200_ERR_UNSUPPORTED,
-              "compute=bf16 is not available in this build");
+  if (m->compute == BFB200_COMPUTE_F16) {
+    BFB_REQUIRE(fused_supported(*m), BFB200_ERR_UNSUPPORTED,
+                "compute=f16 is served by the fused kernel only: d_model 64, 8 heads, F <= 64, V <= 128 "
+                "(got d=%d H=%d F=%d V=%d L=%d)", m->d_model, m->n_heads, m->d_ff, m->ntoken, m->n_layers);
+    BFB_DEV(m->fused_image);
+  }
   if (m->site_flags != 0)
     BFB_REQUIRE(m->p_drop >= 0.f && m->p_drop < 1.f, BFB200_ERR_INVALID_ARG, "p_drop %f outside [0, 1)", m->p_drop);
   BFB_DEV(m->embedding); BFB_DEV(m->pe); BFB_DEV(m->head_w); BFB_DEV(m->head_b);
@@ -139,6 +152,8 @@ extern "C" int bfb200_transformer_forward(const bfb200_transformer* model, const
                                           int64_t index_base, float* logp_out, void* workspace,
                                           size_t workspace_bytes_, void* stream) {
   BFB_CALL(validate_model(model));
+  BFB_REQUIRE(model->compute == BFB200_COMPUTE_FP32, BFB200_ERR_UNSUPPORTED,
+              "bfb200_transformer_forward (all-position log-probs) runs with compute=fp32");
   BFB_REQUIRE(len >= 0 && batch >= 0, BFB200_ERR_INVALID_ARG, "bad shape (%d, %lld)", len, (long long)batch);
   if (len == 0 || batch == 0) return BFB200_OK;
   BFB_DEV(src);
@@ -225,6 +240,10 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
     BFB_REQUIRE(a.masks.max_len >= P + N - 1, BFB200_ERR_INVALID_ARG, "masks.max_len %d < P + N - 1 = %d",
                 a.masks.max_len, P + N - 1);
   const int64_t S_total = a.n_items * T;
+  const bool fused = use_fused(m);
+  if (fused)
+    BFB_REQUIRE(P + N - 1 <= 16, BFB200_ERR_UNSUPPORTED,
+                "compute=f16 (fused kernel) takes sequences of at most 16 tokens; P + N - 1 = %d", P + N - 1);
 
   for (int64_t item0 = 0; item0 < a.n_items; item0 += chunk) {
     const int64_t items = (a.n_items - item0 < chunk) ? a.n_items - item0 : chunk;
@@ -240,13 +259,18 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
       ms.n_draws = (uint32_t)T;
       ms.draw_base = 0;
       ms.item_base = a.index_base + item0;
-      BFB_CALL(forward_chunk(m, ws, S, len, max_len, ms, st));
-      // vocabulary head on the last position only (active_learning.py:62, :103, :146)
-      BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, S, m.ntoken, m.d_model, len, len - 1, 0, st));
       const int32_t* forced = a.forced_tokens != nullptr ? a.forced_tokens + (int64_t)step * S_total + item0 * T : nullptr;
       float* logp = a.logp_out != nullptr ? a.logp_out + ((int64_t)step * S_total + item0 * T) * m.ntoken : nullptr;
-      BFB_CALL(launch_score_step(ws.logits, S, m.ntoken, a.scheme, a.mode, a.temperature, ms, forced, ws.tokens,
-                                 max_len, len, ws.seq_scores, logp, st));
+      if (fused) {
+        BFB_CALL(launch_mc_forward_fused(m, ws.tokens, ws.tokens, max_len, S, len, a.scheme, a.mode, a.temperature,
+                                         ms, forced, ws.seq_scores, logp, st));
+      } else {
+        BFB_CALL(forward_chunk(m, ws, S, len, max_len, ms, st));
+        // vocabulary head on the last position only (active_learning.py:62, :103, :146)
+        BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, S, m.ntoken, m.d_model, len, len - 1, 0, st));
+        BFB_CALL(launch_score_step(ws.logits, S, m.ntoken, a.scheme, a.mode, a.temperature, ms, forced, ws.tokens,
+                                   max_len, len, ws.seq_scores, logp, st));
+      }
       BFB_CALL(launch_reduce_draws(ws.seq_scores, items, T, a.step_scores + (int64_t)step * a.n_items + item0, st));
     }
     if (a.tokens_out != nullptr) {

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -86,15 +87,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N x 16.
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+// Instruction descriptor of kind::f16: 16-bit operands (format 0 = F16, 1 = BF16) -> fp32, both operands
+// K-major, shape M x N x 16.
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+__host__ __device__ constexpr uint32_t instr_desc_16bit(int M, int N, uint32_t fmt) {
   return (1u << 4)                      // [4,6)   accumulator format: F32
-         | (1u << 7)                    // [7,10)  A format: BF16
-         | (1u << 10)                   // [10,13) B format: BF16
+         | (fmt << 7)                   // [7,10)  A format
+         | (fmt << 10)                  // [10,13) B format
          | (0u << 15) | (0u << 16)      // A, B K-major
          | ((uint32_t)(N >> 3) << 17)   // [17,23) N >> 3
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) { return instr_desc_16bit(M, N, kFmtBF16); }
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) { return instr_desc_16bit(M, N, kFmtF16); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -171,6 +176,15 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
+}
+// fp16 with saturation to +-65504 (an overflowing activation must not become inf inside the tensor core)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t packed) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&packed));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }

@@ -276,12 +276,29 @@ class PackedTransformer:
             w_qkv=_ptr(self.w_qkv), w_out=_ptr(self.w_out), ln1_w=_ptr(self.ln1_w), ln1_b=_ptr(self.ln1_b),
             ff1_w=_ptr(self.ff1_w), ff1_b=_ptr(self.ff1_b), ff2_w=_ptr(self.ff2_w), ff2_b=_ptr(self.ff2_b),
             ln2_w=_ptr(self.ln2_w), ln2_b=_ptr(self.ln2_b), head_w=self.head_w.data_ptr(),
-            head_b=self.head_b.data_ptr(), ln_eps=float(eps), compute=_lib.COMPUTE[compute])
+            head_b=self.head_b.data_ptr(), ln_eps=float(eps), compute=_lib.COMPUTE[compute], fused_image=None)
         self.ntoken = module.ntoken
         self.d_model = d
         self.n_layers = L
         self.compute = compute
         self._workspace: torch.Tensor | None = None
+        self.fused_image: torch.Tensor | None = None
+        if compute == "fp16":
+            lib = _lib.load()
+            nbytes = lib.bfb200_fused_image_bytes(C.byref(self.desc))
+            if nbytes == 0:
+                raise NotImplementedError(
+                    "compute='fp16' is served by the fused tcgen05 kernel only (d_model 64, 8 heads, "
+                    f"dim_feedforward <= 64, ntoken <= 128); got d={d} H={H} F={F} V={module.ntoken} L={L}")
+            self.fused_image = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.desc.fused_image = self.fused_image.data_ptr()
+            with torch.cuda.device(device):
+                _lib.check(lib.bfb200_fused_pack(C.byref(self.desc), self.fused_image.data_ptr(), nbytes,
+                                                 _stream_ptr(device)))
+
+    def fused_capable(self) -> bool:
+        """True when this model's shape is in the fused tcgen05 kernel's class (compute='fp16')."""
+        return _lib.load().bfb200_fused_image_bytes(C.byref(self.desc)) > 0
 
     def workspace(self, nbytes: int) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() < nbytes:
@@ -339,18 +356,39 @@ _PACKS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 def _param_signature(module, device) -> tuple:
-    return (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + (
-        getattr(module, "bayes", False), getattr(module, "bayes_dropout", None))
+    return (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + site_flags_of(module)
 
 
 def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransformer:
-    """Cached PackedTransformer of `module` for `device` (rebuilt after any in-place weight update)."""
-    sig = _param_signature(module, device) + (compute,)
-    cache = _PACKS.get(module)
-    if cache is None or cache[0] != sig:
-        cache = (sig, PackedTransformer(module, device, compute))
-        _PACKS[module] = cache
-    return cache[1]
+    """Cached PackedTransformer of `module` for `device` and `compute` (rebuilt after any in-place weight
+    update or change of the dropout configuration)."""
+    sig = _param_signature(module, device)
+    per_module = _PACKS.get(module)
+    if per_module is None:
+        per_module = {}
+        _PACKS[module] = per_module
+    entry = per_module.get(compute)
+    if entry is None or entry[0] != sig:
+        entry = (sig, PackedTransformer(module, device, compute))
+        per_module[compute] = entry
+    return entry[1]
+
+
+FUSED_MAX_LEN = 16  # longest sequence (P + N - 1) the fused fp16 kernel takes
+
+
+def scoring_pack(module, device: torch.device, prompt_len: int, new_tokens: int, compute: str = "auto") -> PackedTransformer:
+    """Pack used by the MC-scoring loop.  compute='auto' picks the fused fp16 tensor-core kernel whenever the
+    model and sequence lengths are in its class (the reference notebooks' configuration) and the exact fp32
+    CUDA path otherwise; 'fp32' / 'fp16' force one (fp16 raises NotImplementedError outside the class)."""
+    if compute not in ("auto", "fp32", "fp16"):
+        raise ValueError(f"unknown compute {compute!r}")
+    if compute == "auto":
+        base = packed(module, device, "fp32")
+        if base.fused_capable() and prompt_len + new_tokens - 1 <= FUSED_MAX_LEN and len(module.layers) >= 1:
+            return packed(module, device, "fp16")
+        return base
+    return packed(module, device, compute)
 
 
 def transformer_forward(pack: PackedTransformer, src: torch.Tensor, seed: int | None = None, draw: int | None = None,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BFB200_ABI_VERSION 1
+#define BFB200_ABI_VERSION 2
 
 enum {
   BFB200_OK = 0,
@@ -48,8 +48,13 @@ enum { BFB200_SCHEME_GREEDY = 0, BFB200_SCHEME_SAMPLING = 1, BFB200_SCHEME_DROPO
 /* arithmetic of the contractions */
 enum {
   BFB200_COMPUTE_FP32 = 0, /* fp32 CUDA-core FMA everywhere (1e-3 parity class) */
-  BFB200_COMPUTE_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate,
-                              fp32 softmax / LayerNorm statistics (1e-2 parity class) */
+  BFB200_COMPUTE_F16 = 1   /* 16-bit operands on tcgen05 tensor cores (kind::f16), fp32 accumulate in TMEM, fp32
+                              residual stream / softmax / LayerNorm statistics: the north star's 1e-2 parity
+                              class.  Operands are IEEE fp16 (saturating): bf16's 8-bit mantissa moves the
+                              trained model's mid-range probabilities by up to 5 %, fp16 keeps them within
+                              1 % (measured).  Served by the
+                              fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 16
+                              (the reference notebooks' model); other shapes return BFB200_ERR_UNSUPPORTED */
 };
 
 /* always-on dropout sites of src/model/transformer.py (bit set = site live) */
@@ -106,6 +111,8 @@ typedef struct bfb200_transformer {
   const float* head_b;    /* [dev] (V) */
   float ln_eps;           /* 1e-5 (nn.LayerNorm default) */
   int32_t compute;        /* BFB200_COMPUTE_* */
+  const void* fused_image; /* [dev] fp16 weight image written by bfb200_fused_pack, or NULL; needed by
+                              compute = BFB200_COMPUTE_F16 (see bfb200_fused_image_bytes) */
 } bfb200_transformer;
 
 /*
@@ -232,6 +239,15 @@ size_t bfb200_mc_workspace_bytes(const bfb200_transformer* model, const bfb200_m
                                  int64_t items_per_chunk);
 int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc_args* args,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Weight image of the fused MC-forward kernel (compute = BFB200_COMPUTE_F16): every nn.Linear weight of
+ * src/model/transformer.py as fp16 in the 128-byte-swizzled K-major shared-memory layout tcgen05.mma reads,
+ * followed by the fp32 LayerNorm / bias vectors and the first 16 rows of `pe`.  _bytes returns 0 when the
+ * model's shape is outside the fused kernel's class.  Re-pack after every weight update.
+ */
+size_t bfb200_fused_image_bytes(const bfb200_transformer* model);
+int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream);
 
 /* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
  * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */

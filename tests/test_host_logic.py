@@ -38,8 +38,8 @@ def test_struct_layouts_match_header_sizes():
 
     from bayesformer_b200 import _lib
 
-    # 6 int32 + float + uint32 (32 B) + 14 pointers (112 B) + float + int32 (8 B)
-    assert C.sizeof(_lib.Transformer) == 152
+    # 6 int32 + float + uint32 (32 B) + 14 pointers (112 B) + float + int32 (8 B) + 1 pointer
+    assert C.sizeof(_lib.Transformer) == 160
     assert C.sizeof(_lib.Masks) == 24
     assert C.sizeof(_lib.McArgs) == 8 + 8 + 4 * 5 + 4 + 8 + 24 + 8 * 5
 
