@@ -51,7 +51,7 @@ struct FusedLayout {
 __host__ __device__ inline FusedLayout fused_layout(int L, int F, int V) {
   FusedLayout lay;
   lay.fp = (uint32_t)((F + 15) / 16 * 16);
-  lay.vp = (uint32_t)((V + 15) / 16 * 16);
+  lay.vp = FMAXV;   // the head product always spans 128 classes; classes >= V carry zero weights and bias -inf
   lay.off_out = 3 * FD * 128;
   lay.off_w1 = lay.off_out + FD * 128;
   lay.off_w2 = lay.off_w1 + lay.fp * 128;
@@ -116,7 +116,7 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
         }
       } else if (j < L * PARAMS_PER_LAYER + FMAXV) {
         const int c = j - L * PARAMS_PER_LAYER;
-        v = c < V ? m.head_b[c] : 0.f;
+        v = c < V ? m.head_b[c] : -INFINITY;   // padded classes vanish from every softmax
       } else {
         const int q = j - L * PARAMS_PER_LAYER - FMAXV;  // pe[pos][c], pos < FMAXLEN
         const int pos = q >> 6;
@@ -157,44 +157,61 @@ struct FusedArgs {
 // per-row addressing of the mask source, hoisted out of the feature loops
 struct RowRng {
   uint32_t item, draw;
-  int64_t seq_abs;  // bits mode: seq_base + s
+  uint32_t seq_local;  // sequence inside this launch (bits mode adds seq_base)
 };
 
-__device__ __forceinline__ RowRng make_row_rng(const MaskSource& m, int64_t s) {
+__device__ __forceinline__ RowRng make_row_rng(const MaskSource& m, uint32_t s) {
   RowRng r;
-  r.item = (uint32_t)(uint64_t)(m.item_base + s / m.n_draws);
-  r.draw = m.draw_base + (uint32_t)(s % m.n_draws);
-  r.seq_abs = m.seq_base + s;
+  const uint32_t q = s / m.n_draws;
+  r.item = (uint32_t)((uint64_t)m.item_base + q);
+  r.draw = m.draw_base + (s - q * m.n_draws);
+  r.seq_local = s;
   return r;
 }
 
-// keep bits of features [8*f8, 8*f8 + 8) of (row, site): bit j = feature 8*f8 + j
-__device__ __forceinline__ uint32_t keep8(const MaskSource& m, const RowRng& rr, uint32_t pos, uint32_t site,
-                                          uint32_t f8) {
-  if (m.bits != nullptr) {
-    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + rr.seq_abs) * m.max_len + pos;
-    const uint32_t w = m.bits[row * m.words + (f8 >> 2)];
-    return (w >> ((f8 & 3u) * 8u)) & 0xFFu;
-  }
-  uint32_t out = 0;
-#pragma unroll
-  for (uint32_t q = 0; q < 2; ++q) {
-    const uint4 r = philox4x32_10(make_uint4(rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (2 * f8 + q)), m.key);
-    const uint32_t k4 = (r.x >= m.threshold ? 1u : 0u) | (r.y >= m.threshold ? 2u : 0u) |
-                        (r.z >= m.threshold ? 4u : 0u) | (r.w >= m.threshold ? 8u : 0u);
-    out |= k4 << (4 * q);
+__device__ __forceinline__ uint32_t keep4_of(const uint4& r, uint32_t thr) {
+  return (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+}
+
+// 64 keep bits of one (row, site) from the Philox stream: bit f = feature f.  Deliberately NOT inlined: the
+// seven dropout sites of the kernel share this one copy of the rounds (the kernel is instruction-fetch
+// sensitive); arguments are scalars so nothing spills to local memory at the call, and four counters are
+// advanced together so the rounds of independent streams interleave.
+__device__ __noinline__ uint64_t philox_keep64(uint32_t key_x, uint32_t key_y, uint32_t threshold, uint32_t item,
+                                               uint32_t draw, uint32_t c2, uint32_t c3) {
+  const uint2 key = make_uint2(key_x, key_y);
+  uint64_t out = 0;
+#pragma unroll 1
+  for (uint32_t f4 = 0; f4 < 16; f4 += 4) {
+    const uint4 r0 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 0)), key);
+    const uint4 r1 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 1)), key);
+    const uint4 r2 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 2)), key);
+    const uint4 r3 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 3)), key);
+    const uint32_t k16 = keep4_of(r0, threshold) | (keep4_of(r1, threshold) << 4) |
+                         (keep4_of(r2, threshold) << 8) | (keep4_of(r3, threshold) << 12);
+    out |= (uint64_t)k16 << (4 * f4);
   }
   return out;
 }
 
-// v[0..63] = keep ? v * scale : 0 for one row
-__device__ __forceinline__ void drop_row(float (&v)[FD], const MaskSource& m, const RowRng& rr, uint32_t pos,
-                                         uint32_t site) {
+__device__ __forceinline__ uint64_t row_keep_mask(const MaskSource& m, uint32_t item, uint32_t draw, uint32_t seq_local,
+                                                  uint32_t pos, uint32_t site) {
+  if (m.bits != nullptr) {   // mask-injection mode: 64 bits = two packed words of the row
+    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + seq_local)) * m.max_len + pos;
+    const uint32_t* w = m.bits + row * m.words;
+    return (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+  }
+  return philox_keep64(m.key.x, m.key.y, m.threshold, item, draw, (m.step << 16) | pos, site << 16);
+}
+
+// v[0..63] = keep ? v * scale : 0 for one row; `k` = row_keep_mask(...) taken BEFORE the row is loaded into
+// registers, so the call does not have to save 64 live values
+__device__ __forceinline__ void drop_row(float (&v)[FD], uint64_t k, float scale) {
+  const uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
 #pragma unroll
-  for (uint32_t f8 = 0; f8 < 8; ++f8) {
-    const uint32_t k = keep8(m, rr, pos, site, f8);
-#pragma unroll
-    for (uint32_t j = 0; j < 8; ++j) v[8 * f8 + j] = ((k >> j) & 1u) ? v[8 * f8 + j] * m.scale : 0.f;
+  for (uint32_t j = 0; j < 32; ++j) {
+    v[j] = ((lo >> j) & 1u) ? v[j] * scale : 0.f;
+    v[32 + j] = ((hi >> j) & 1u) ? v[32 + j] * scale : 0.f;
   }
 }
 
@@ -247,7 +264,7 @@ __device__ __forceinline__ void layer_norm_row(float (&v)[FD], const float* __re
     const float c = v[i] - mean;
     q = fmaf(c, c, q);
   }
-  const float rstd = 1.0f / sqrtf(q * (1.0f / FD) + eps);
+  const float rstd = rsqrtf(q * (1.0f / FD) + eps);
 #pragma unroll
   for (int i = 0; i < FD; ++i) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
 }
@@ -268,10 +285,142 @@ __device__ __forceinline__ float sub_sum(float v, int n) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------
+// score phase: TPS threads per sequence over the staged last-position logits.
+//   log-probs = log_softmax(logits)                                   transformer.py:375
+//   probs     = softmax(log-probs [/ temperature])                    active_learning.py:67, :104-105, :147
+//   score     = max p | p(1) - p(2) | -sum p log(p + 1e-10)           active_learning.py:25-31
+//   token     = argmax log-probs | inverse-CDF sample | forced        active_learning.py:63, :106, :148
+// softmax(log-probs) is exp(log-probs) up to rounding, so the un-tempered probabilities reuse the exponentials
+// of the log-softmax, and log(p + 1e-10) is taken as log p (the terms where they differ weigh < 1e-8).
+// ------------------------------------------------------------------------------------------
+template <int TPS>
+__device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __restrict__ stage, int stage_stride,
+                                            int gt, int nseq, uint32_t s0, int len) {
+  constexpr int NPT = FMAXV / TPS;
+  const int V = a.vocab;
+  const int sl = gt / TPS, sub = gt % TPS;
+  const bool active = sl < nseq;
+  const float* row = stage + (active ? sl : 0) * stage_stride;
+  const uint32_t sq = s0 + (active ? (uint32_t)sl : 0u);
+  float lg[NPT], pr[NPT];
+  float mx = -INFINITY;
+  int best_i = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int c = sub + j * TPS;
+    lg[j] = row[c];   // classes >= V hold -inf (head bias padding)
+    if (lg[j] > mx) { mx = lg[j]; best_i = c; }
+  }
+#pragma unroll
+  for (int o = TPS >> 1; o > 0; o >>= 1) {   // arg-max, lowest class wins ties
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (om > mx || (om == mx && oi < best_i)) { mx = om; best_i = oi; }
+  }
+  float z = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    pr[j] = __expf(lg[j] - mx);
+    z += pr[j];
+  }
+  z = sub_sum(z, TPS);
+  const float lse = __logf(z);
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int c = sub + j * TPS;
+    lg[j] = (lg[j] - mx) - lse;   // log-probabilities (class >= V: -inf)
+    if (a.logp_out != nullptr && active && c < V) a.logp_out[(size_t)sq * V + c] = lg[j];
+  }
+  float ent = 0.f;
+  if (a.scheme != BFB200_SCHEME_SAMPLING) {
+    const float inv_z = __fdividef(1.0f, z);
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      pr[j] *= inv_z;
+      ent = fmaf(pr[j], fmaxf(lg[j], -1e30f), ent);   // 0 * -inf guard for padded / underflowed classes
+    }
+  } else {
+    // tempered distribution: softmax(log-probs / temperature); its maximum sits at the arg-max class
+    const float inv_t = 1.0f / a.temperature;
+    float pz = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      lg[j] = (lg[j] + lse) * inv_t;   // (logit - max) / T  <= 0
+      pr[j] = __expf(lg[j]);
+      pz += pr[j];
+    }
+    pz = sub_sum(pz, TPS);
+    const float inv_pz = __fdividef(1.0f, pz), log_pz = __logf(pz);
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      pr[j] *= inv_pz;
+      ent = fmaf(pr[j], fmaxf(lg[j] - log_pz, -1e30f), ent);
+    }
+  }
+  ent = -sub_sum(ent, TPS);
+  float p1 = -INFINITY;
+  int p1_i = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int c = sub + j * TPS;
+    if (pr[j] > p1) { p1 = pr[j]; p1_i = c; }
+  }
+#pragma unroll
+  for (int o = TPS >> 1; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, p1, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, p1_i, o);
+    if (ob > p1 || (ob == p1 && oi < p1_i)) { p1 = ob; p1_i = oi; }
+  }
+  float p2 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int c = sub + j * TPS;
+    if (c != p1_i) p2 = fmaxf(p2, pr[j]);
+  }
+  p2 = sub_max(p2, TPS);
+
+  int token = best_i;
+  if (a.scheme == BFB200_SCHEME_SAMPLING) {
+    // inverse CDF in class order from one Philox word (the library's documented sampling rule)
+    const RowRng srr = make_row_rng(a.ms, sq);
+    const uint4 rnd = philox4x32_10(
+        make_uint4(srr.item, srr.draw, a.ms.step << 16, BFB200_SITE_SAMPLING_TOKEN << 16), a.ms.key);
+    const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float running = 0.f;
+    int first = V - 1;
+#pragma unroll 1
+    for (int j = 0; j < NPT; ++j) {
+      float c = 0.f;
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) c = q == j ? pr[q] : c;   // register select keeps pr[] out of local memory
+#pragma unroll
+      for (int o = 1; o < TPS; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, c, o, TPS);
+        if (sub >= o) c += up;
+      }
+      c += running;
+      const int cls = sub + j * TPS;
+      if (c > u && cls < V && cls < first) first = cls;
+      running = __shfl_sync(0xffffffffu, c, TPS - 1, TPS);
+    }
+#pragma unroll
+    for (int o = TPS >> 1; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    token = first;
+  }
+  if (active && sub == 0) {
+    a.seq_scores[sq] = a.mode == BFB200_MODE_MAX ? p1 : (a.mode == BFB200_MODE_MARGIN ? p1 - p2 : ent);
+    if (a.forced != nullptr) token = a.forced[sq];
+    if (a.tokens_out != nullptr && len < a.tok_stride) a.tokens_out[(size_t)sq * a.tok_stride + len] = token;
+  }
+}
+
 template <int MAXLEN>
 __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment of the swizzled tiles, computed as an offset so the pointers stay in the shared
+  // address space (LDS / STS instead of generic loads)
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_image;
   __shared__ uint64_t bar_group[FGROUPS];
   __shared__ uint32_t tmem_slot;
@@ -318,7 +467,7 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
 
   const int len = a.len, spt = a.spt;
   const int seq_l = gt / len, pos = gt - seq_l * len;
-  const float sqrt_d = sqrtf((float)FD), sqrt_dh = sqrtf((float)FDH);
+  const float sqrt_d = sqrtf((float)FD), inv_sqrt_dh = 1.0f / sqrtf((float)FDH);
   const uint32_t fl = a.site_flags;
   const MaskSource& ms = a.ms;
 
@@ -343,24 +492,26 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
   };
 
   for (int64_t tile = (int64_t)blockIdx.x * FGROUPS + g; tile < a.n_tiles; tile += (int64_t)gridDim.x * FGROUPS) {
-    const int64_t s0 = tile * spt;
-    const int nseq = (int)((a.n_seq - s0) < spt ? (a.n_seq - s0) : spt);
+    const uint32_t s0 = (uint32_t)tile * (uint32_t)spt;   // n_seq < 2^31 per launch (checked on the host)
+    const int nseq = (int)(((uint32_t)a.n_seq - s0) < (uint32_t)spt ? ((uint32_t)a.n_seq - s0) : (uint32_t)spt);
     const bool row_valid = seq_l < nseq;
-    const int64_t s = s0 + (row_valid ? seq_l : 0);
+    const uint32_t s = s0 + (row_valid ? (uint32_t)seq_l : 0u);
     const RowRng rr = make_row_rng(ms, s);
 
     // ---- embedding + dropout E + sqrt(d) scale + positional encoding (transformer.py:355-362) ----
     {
+      const uint64_t k_embed =
+          (fl & BFB200_SITE_EMBED) ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, 0u) : 0ull;
       float x[FD];
       if (row_valid) {
-        const int tok = a.tokens[s * a.tok_stride + pos];
+        const int tok = a.tokens[(size_t)s * a.tok_stride + pos];
         const float4* e = reinterpret_cast<const float4*>(a.embedding + (size_t)tok * FD);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4 v = __ldg(e + i);
           x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        if (fl & BFB200_SITE_EMBED) drop_row(x, ms, rr, (uint32_t)pos, 0u);
+        if (fl & BFB200_SITE_EMBED) drop_row(x, k_embed, ms.scale);
         const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD;
 #pragma unroll
         for (int i = 0; i < FD; ++i) x[i] = x[i] * sqrt_d + pe[i];
@@ -379,14 +530,26 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
       gemm(descA0, wl, 3 * FD, 4);
-      {
-        float v[FD];
-        tmem_load_row64(tW + 64, v);       // K
-        store_row_f16(B1, gt, v);
-        tmem_load_row64(tW + 128, v);      // V
-        store_row_f16(B2, gt, v);
-        tmem_load_row64(tW, v);            // Q
-        store_row_f16(B0, gt, v);         // x (fp16) is dead once the product has completed
+      // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 operand tiles B0, B1, B2
+      // (x in B0 is dead once the product has completed); 16 columns per trip keeps this loop compact
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < 3 * FD; c0 += 16) {
+        uint32_t r[16];
+        umma::tmem_ld16(tW + c0, r);
+        umma::tmem_ld_wait();
+        uint8_t* dst = B0 + (c0 >> 6) * TILE_BYTES;   // B0, B1, B2 are contiguous
+        const uint32_t ch = (c0 & 63u) >> 3;
+        uint4 w0, w1;
+        w0.x = umma::pack_f16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+        w0.y = umma::pack_f16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        w0.z = umma::pack_f16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+        w0.w = umma::pack_f16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+        w1.x = umma::pack_f16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+        w1.y = umma::pack_f16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+        w1.z = umma::pack_f16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+        w1.w = umma::pack_f16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(gt, ch)) = w0;
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(gt, ch + 1)) = w1;
       }
       umma::tc_fence_before_sync();
       umma::group_sync(bar_id, FROWS);
@@ -414,7 +577,7 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
             }
           }
         }
-        const RowRng prr = make_row_rng(ms, s0 + sl);
+        const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
         for (int t = 0; t < MAXLEN; ++t) {
           if (t < len) {
@@ -435,20 +598,21 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c) d = fmaf(q[c], kj[c], d);
-              d = d / sqrt_dh;
+              d = d * inv_sqrt_dh;
               sc[j] = d;
               mx = fmaxf(mx, d);
             }
             float z = 0.f;
 #pragma unroll
             for (int j = 0; j <= t; ++j) {
-              sc[j] = expf(sc[j] - mx);
+              sc[j] = __expf(sc[j] - mx);
               z += sc[j];
             }
+            const float inv_z = __fdividef(1.0f, z);
             float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j <= t; ++j) {
-              const float pj = sc[j] / z;
+              const float pj = sc[j] * inv_z;
               float vj[8];
               if constexpr (kUnpacked) {
 #pragma unroll
@@ -460,7 +624,8 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
               for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, vj[c], o[c]);
             }
             if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
-              const uint32_t k = keep8(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)h);
+              const uint32_t k = (uint32_t)(row_keep_mask(ms, prr.item, prr.draw, prr.seq_local, (uint32_t)t, sb + 4u) >>
+                                            (8 * h)) & 0xFFu;
 #pragma unroll
               for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
             }
@@ -475,14 +640,18 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
       // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
       gemm(descA0, wl + lay.off_out, FD, 4);
       {
+        const uint64_t k_attn = (fl & BFB200_SITE_ATTN_RESID)
+                                    ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 1u) : 0ull;
+        const uint64_t k_ffn_in = (fl & BFB200_SITE_FFN_IN)
+                                      ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 2u) : 0ull;
         float v[FD], x[FD];
         tmem_load_row64(tW, v);
-        if (fl & BFB200_SITE_ATTN_RESID) drop_row(v, ms, rr, (uint32_t)pos, sb + 1u);
+        if (fl & BFB200_SITE_ATTN_RESID) drop_row(v, k_attn, ms.scale);
         tmem_load_row64(tX, x);
 #pragma unroll
         for (int i = 0; i < FD; ++i) v[i] += x[i];
         layer_norm_row(v, pl, pl + 64, a.ln_eps);
-        if (fl & BFB200_SITE_FFN_IN) drop_row(v, ms, rr, (uint32_t)pos, sb + 2u);
+        if (fl & BFB200_SITE_FFN_IN) drop_row(v, k_ffn_in, ms.scale);
         store_row_f16(B0, gt, v);
       }
 
@@ -510,17 +679,21 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
       gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
       {
+        const uint64_t k_resid = (fl & BFB200_SITE_FFN_RESID)
+                                     ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 3u) : 0ull;
+        const uint64_t k_out = (fl & BFB200_SITE_LAYER_OUT)
+                                   ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 0u) : 0ull;
         float v[FD], x[FD];
         tmem_load_row64(tW, v);
         const float* b2 = pl + 192;
 #pragma unroll
         for (int i = 0; i < FD; ++i) v[i] += b2[i];
-        if (fl & BFB200_SITE_FFN_RESID) drop_row(v, ms, rr, (uint32_t)pos, sb + 3u);
+        if (fl & BFB200_SITE_FFN_RESID) drop_row(v, k_resid, ms.scale);
         tmem_load_row64(tX, x);
 #pragma unroll
         for (int i = 0; i < FD; ++i) v[i] += x[i];
         layer_norm_row(v, pl + 256, pl + 320, a.ln_eps);
-        if (fl & BFB200_SITE_LAYER_OUT) drop_row(v, ms, rr, (uint32_t)pos, sb + 0u);   // transformer.py:370
+        if (fl & BFB200_SITE_LAYER_OUT) drop_row(v, k_out, ms.scale);   // transformer.py:370
         if (l + 1 < a.n_layers) tmem_store_row64(tX, v);
         store_row_f16(B0, gt, v);
       }
@@ -547,113 +720,8 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
     umma::group_sync(bar_id, FROWS);
 
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
-    {
-      const int tps = a.tps, V = a.vocab;
-      const int sl = gt / tps, sub = gt - sl * tps;
-      constexpr int NPT = FMAXV / 4;  // classes per thread at tps = 4
-      const bool active = sl < nseq;
-      const float* row = stage + (active ? sl : 0) * stage_stride;
-      float lg[NPT];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        const int c = sub + j * tps;
-        lg[j] = c < V ? row[c] : -INFINITY;
-        mx = fmaxf(mx, lg[j]);
-      }
-      mx = sub_max(mx, tps);
-      float z = 0.f;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) z += (sub + j * tps) < V ? expf(lg[j] - mx) : 0.f;
-      const float lse = logf(sub_sum(z, tps));
-      const int64_t sq = s0 + (active ? sl : 0);
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        const int c = sub + j * tps;
-        if (c < V) {
-          lg[j] = (lg[j] - mx) - lse;  // log-probabilities
-          if (a.logp_out != nullptr && active) a.logp_out[sq * V + c] = lg[j];
-          if (lg[j] > best) { best = lg[j]; best_i = c; }
-        }
-      }
-      for (int o = tps >> 1; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-      }
-      // probs = softmax(log-probs [/ temperature]) (active_learning.py:67, :104-105, :147)
-      float pr[NPT];
-      float pm = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        pr[j] = a.scheme == BFB200_SCHEME_SAMPLING ? lg[j] / a.temperature : lg[j];
-        if ((sub + j * tps) < V) pm = fmaxf(pm, pr[j]);
-      }
-      pm = sub_max(pm, tps);
-      float pz = 0.f;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        pr[j] = (sub + j * tps) < V ? expf(pr[j] - pm) : 0.f;
-        pz += pr[j];
-      }
-      pz = sub_sum(pz, tps);
-      float p1 = -INFINITY, ent = 0.f;
-      int p1_i = 0x7fffffff;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        const int c = sub + j * tps;
-        pr[j] = pr[j] / pz;
-        if (c < V) {
-          if (pr[j] > p1) { p1 = pr[j]; p1_i = c; }
-          ent += pr[j] * logf(pr[j] + 1e-10f);
-        }
-      }
-      for (int o = tps >> 1; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, p1, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, p1_i, o);
-        if (ob > p1 || (ob == p1 && oi < p1_i)) { p1 = ob; p1_i = oi; }
-      }
-      float p2 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) {
-        const int c = sub + j * tps;
-        if (c < V && c != p1_i) p2 = fmaxf(p2, pr[j]);
-      }
-      p2 = sub_max(p2, tps);
-      ent = -sub_sum(ent, tps);
-
-      int token = best_i;
-      if (a.scheme == BFB200_SCHEME_SAMPLING) {
-        // inverse CDF in class order from one Philox word (the library's documented sampling rule)
-        const RowRng srr = make_row_rng(ms, sq);
-        const uint4 rnd = philox4x32_10(
-            make_uint4(srr.item, srr.draw, ms.step << 16, BFB200_SITE_SAMPLING_TOKEN << 16), ms.key);
-        const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        float running = 0.f;
-        int first = V - 1;
-#pragma unroll
-        for (int j = 0; j < NPT; ++j) {
-          float c = pr[j];
-          for (int o = 1; o < tps; o <<= 1) {
-            const float up = __shfl_up_sync(0xffffffffu, c, o, tps);
-            if (sub >= o) c += up;
-          }
-          c += running;
-          const int cls = sub + j * tps;
-          if (c > u && cls < V && cls < first) first = cls;
-          running = __shfl_sync(0xffffffffu, c, tps - 1, tps);
-        }
-        for (int o = tps >> 1; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        token = first;
-      }
-      if (active && sub == 0) {
-        a.seq_scores[sq] = a.mode == BFB200_MODE_MAX ? p1 : (a.mode == BFB200_MODE_MARGIN ? p1 - p2 : ent);
-        if (a.forced != nullptr) token = a.forced[sq];
-        if (a.tokens_out != nullptr && len < a.tok_stride) a.tokens_out[sq * a.tok_stride + len] = token;
-      }
-    }
+    if (a.tps == 8) score_phase<8>(a, stage, stage_stride, gt, nseq, s0, len);
+    else            score_phase<4>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
