@@ -356,7 +356,7 @@ def main() -> None:
             "frac": value / world * flops_per_pool_sample(P, N) / 1e12 / peaks["bf16_tflops_sustained"]},
     }
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (rank 0 of a multi-rank job skips it)
             line["cpu_baseline"] = {k: v for k, v in
                                     time_cpu_port(model, prompts_np, N, 2000, 2, 1).items() if k != "seconds_per_pass"}
         print(json.dumps(line), flush=True)
