@@ -32,7 +32,9 @@ constexpr int FD = 64;          // d_model
 constexpr int FH = 8;           // heads
 constexpr int FDH = 8;          // head width
 constexpr int FROWS = 128;      // token rows per group tile (UMMA M)
-constexpr int FGROUPS = 2;      // independent 128-thread groups per CTA
+constexpr int FGROUPS = 2;      // independent groups per CTA, one tile of 128 token rows each
+constexpr int FGROUP_THREADS = 256;   // two threads per token row (32 features each)
+constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
 constexpr int FMAXLEN = 16;     // longest sequence the fused path takes
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
@@ -190,6 +192,25 @@ __device__ __noinline__ uint64_t philox_keep64(uint32_t key_x, uint32_t key_y, u
     const uint32_t k16 = keep4_of(r0, threshold) | (keep4_of(r1, threshold) << 4) |
                          (keep4_of(r2, threshold) << 8) | (keep4_of(r3, threshold) << 12);
     out |= (uint64_t)k16 << (4 * f4);
+  }
+  return out;
+}
+
+// 32 keep bits: features [4 * (c3 & 0xFFFF), ... + 32) of the (row, site) encoded in (c2, c3); same stream as
+// philox_keep64, eight counters, four advanced together
+__device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, uint32_t threshold, uint32_t item,
+                                               uint32_t draw, uint32_t c2, uint32_t c3) {
+  const uint2 key = make_uint2(key_x, key_y);
+  uint32_t out = 0;
+#pragma unroll 1
+  for (uint32_t f4 = 0; f4 < 8; f4 += 4) {
+    const uint4 r0 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 0), key);
+    const uint4 r1 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 1), key);
+    const uint4 r2 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 2), key);
+    const uint4 r3 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 3), key);
+    const uint32_t k16 = keep4_of(r0, threshold) | (keep4_of(r1, threshold) << 4) |
+                         (keep4_of(r2, threshold) << 8) | (keep4_of(r3, threshold) << 12);
+    out |= k16 << (4 * f4);
   }
   return out;
 }
@@ -415,8 +436,84 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// half-row helpers: a token row's 64 features are split between two threads (features [32h, 32h + 32))
+// ------------------------------------------------------------------------------------------
+constexpr int HW = FD / 2;   // features per thread
+
+__device__ __forceinline__ void drop_half(float (&v)[HW], uint32_t k, float scale) {
+#pragma unroll
+  for (uint32_t j = 0; j < HW; ++j) v[j] = ((k >> j) & 1u) ? v[j] * scale : 0.f;
+}
+
+// 32 keep bits (features [32h, 32h + 32)) of one (row, site)
+__device__ __forceinline__ uint32_t half_keep_mask(const MaskSource& m, const RowRng& rr, uint32_t pos, uint32_t site,
+                                                   uint32_t h) {
+  if (m.bits != nullptr) {
+    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + rr.seq_local)) * m.max_len + pos;
+    return m.bits[row * m.words + h];
+  }
+  return philox_keep32(m.key.x, m.key.y, m.threshold, rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (8u * h));
+}
+
+__device__ __forceinline__ void store_half_f16(uint8_t* tile, uint32_t row, uint32_t h, const float (&v)[HW]) {
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c) {
+    uint4 w;
+    w.x = umma::pack_f16x2(v[8 * c + 0], v[8 * c + 1]);
+    w.y = umma::pack_f16x2(v[8 * c + 2], v[8 * c + 3]);
+    w.z = umma::pack_f16x2(v[8 * c + 4], v[8 * c + 5]);
+    w.w = umma::pack_f16x2(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(tile + umma::sw128_offset(row, 4 * h + c)) = w;
+  }
+}
+
+__device__ __forceinline__ void tmem_load_half(uint32_t taddr, float (&v)[HW]) {
+  uint32_t r[32];
+  umma::tmem_ld32(taddr, r);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < HW; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_store_half(uint32_t taddr, const float (&v)[HW]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < HW; ++i) r[i] = __float_as_uint(v[i]);
+  umma::tmem_st32(taddr, r);
+  umma::tmem_st_wait();
+}
+
+// LayerNorm over a 64-feature row held as two 32-feature halves in two threads (biased variance, eps inside the
+// sqrt: nn.LayerNorm).  Each half computes its mean and centred sum of squares exactly, the pair exchanges them
+// through `red` and combines with the parallel-variance formula (n_a = n_b = 32):
+//   mean = (m_a + m_b) / 2,  M2 = M2_a + M2_b + 16 (m_a - m_b)^2
+__device__ __forceinline__ void layer_norm_half(float (&v)[HW], float2* __restrict__ red, int row, int h, int bar_id,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HW; ++i) s += v[i];
+  const float m_own = s * (1.0f / HW);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < HW; ++i) {
+    const float c = v[i] - m_own;
+    q = fmaf(c, c, q);
+  }
+  red[h * FROWS + row] = make_float2(m_own, q);
+  umma::group_sync(bar_id, 2 * FROWS);
+  const float2 other = red[(h ^ 1) * FROWS + row];
+  const float dm = m_own - other.x;
+  const float mean = 0.5f * (m_own + other.x);
+  const float var = (q + other.y + 16.0f * dm * dm) * (1.0f / FD);
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int i = 0; i < HW; ++i) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+}
+
 template <int MAXLEN>
-__global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment of the swizzled tiles, computed as an offset so the pointers stay in the shared
   // address space (LDS / STS instead of generic loads)
@@ -424,15 +521,19 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
   __shared__ uint64_t bar_image;
   __shared__ uint64_t bar_group[FGROUPS];
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 ln_red[FGROUPS][2 * FROWS];
 
   const int tid = threadIdx.x;
-  const int g = tid >> 7, gt = tid & 127, gw = gt >> 5;
+  const int g = tid / FGROUP_THREADS, gt = tid % FGROUP_THREADS;   // group, thread in group
+  const int h = gt >> 7, row = gt & 127;                           // feature half, token row
+  const int gw = row >> 5;                                         // TMEM lane quarter (= CTA warp % 4)
   const FusedLayout lay = a.lay;
   uint8_t* img = smem;
   uint8_t* B0 = smem + lay.image_bytes + (uint32_t)g * 3u * TILE_BYTES;
   uint8_t* B1 = B0 + TILE_BYTES;
   uint8_t* B2 = B1 + TILE_BYTES;
   const float* params = reinterpret_cast<const float*>(img + lay.off_params);
+  float2* red = ln_red[g];
 
   if (tid < 32) {
     umma::tmem_alloc(&tmem_slot, 512);
@@ -458,15 +559,15 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
 
   const uint32_t tmem_base = tmem_slot;
   const uint32_t lane_base = (uint32_t)(gw * 32) << 16;
-  const uint32_t tX = tmem_base + (uint32_t)g * 256u + lane_base;  // residual stream, 64 columns
-  const uint32_t tW = tX + 64u;                                     // accumulators, 192 columns
-  const uint32_t tW_mma = tmem_base + (uint32_t)g * 256u + 64u;     // same, lane field 0 for the MMA
+  const uint32_t tX = tmem_base + (uint32_t)g * 256u + lane_base + (uint32_t)h * HW;  // residual stream (this half)
+  const uint32_t tW = tmem_base + (uint32_t)g * 256u + lane_base + 64u;               // accumulators, 192 columns
+  const uint32_t tW_mma = tmem_base + (uint32_t)g * 256u + 64u;                       // same, lane field 0
   uint64_t* bar = &bar_group[g];
   uint32_t phase = 0;
   const int bar_id = 1 + g;
 
   const int len = a.len, spt = a.spt;
-  const int seq_l = gt / len, pos = gt - seq_l * len;
+  const int seq_l = row / len, pos = row - seq_l * len;
   const float sqrt_d = sqrtf((float)FD), inv_sqrt_dh = 1.0f / sqrtf((float)FDH);
   const uint32_t fl = a.site_flags;
   const MaskSource& ms = a.ms;
@@ -478,7 +579,7 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
   auto gemm = [&](uint32_t a_addr, uint32_t b_addr, int N, int k_steps) {
     umma::fence_async_smem();
     umma::tc_fence_before_sync();
-    umma::group_sync(bar_id, FROWS);
+    umma::group_sync(bar_id, FGROUP_THREADS);
     if (gt == 0) {
       umma::tc_fence_after_sync();
       const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
@@ -500,27 +601,26 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
 
     // ---- embedding + dropout E + sqrt(d) scale + positional encoding (transformer.py:355-362) ----
     {
-      const uint64_t k_embed =
-          (fl & BFB200_SITE_EMBED) ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, 0u) : 0ull;
-      float x[FD];
+      const uint32_t k_embed = (fl & BFB200_SITE_EMBED) ? half_keep_mask(ms, rr, (uint32_t)pos, 0u, (uint32_t)h) : 0u;
+      float x[HW];
       if (row_valid) {
         const int tok = a.tokens[(size_t)s * a.tok_stride + pos];
-        const float4* e = reinterpret_cast<const float4*>(a.embedding + (size_t)tok * FD);
+        const float4* e = reinterpret_cast<const float4*>(a.embedding + (size_t)tok * FD + h * HW);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < HW / 4; ++i) {
           const float4 v = __ldg(e + i);
           x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        if (fl & BFB200_SITE_EMBED) drop_row(x, k_embed, ms.scale);
-        const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD;
+        if (fl & BFB200_SITE_EMBED) drop_half(x, k_embed, ms.scale);
+        const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD + h * HW;
 #pragma unroll
-        for (int i = 0; i < FD; ++i) x[i] = x[i] * sqrt_d + pe[i];
+        for (int i = 0; i < HW; ++i) x[i] = x[i] * sqrt_d + pe[i];
       } else {
 #pragma unroll
-        for (int i = 0; i < FD; ++i) x[i] = 0.f;
+        for (int i = 0; i < HW; ++i) x[i] = 0.f;
       }
-      tmem_store_row64(tX, x);
-      store_row_f16(B0, gt, x);
+      tmem_store_half(tX, x);
+      store_half_f16(B0, row, h, x);
     }
 
     for (int l = 0; l < a.n_layers; ++l) {
@@ -531,9 +631,9 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
       gemm(descA0, wl, 3 * FD, 4);
       // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 operand tiles B0, B1, B2
-      // (x in B0 is dead once the product has completed); 16 columns per trip keeps this loop compact
+      // (x in B0 is dead once the product has completed); each half copies 96 columns, 16 per trip
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < 3 * FD; c0 += 16) {
+      for (uint32_t c0 = 96u * h; c0 < 96u * h + 96u; c0 += 16) {
         uint32_t r[16];
         umma::tmem_ld16(tW + c0, r);
         umma::tmem_ld_wait();
@@ -548,91 +648,85 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
         w1.y = umma::pack_f16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
         w1.z = umma::pack_f16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
         w1.w = umma::pack_f16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(gt, ch)) = w0;
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(gt, ch + 1)) = w1;
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch)) = w0;
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch + 1)) = w1;
       }
       umma::tc_fence_before_sync();
-      umma::group_sync(bar_id, FROWS);
+      umma::group_sync(bar_id, FGROUP_THREADS);
 
-      // ---- causal attention, thread = (sequence, head) (transformer.py:58-65) ----
-      for (int p = gt; p < nseq * FH; p += FROWS) {
-        const int sl = p >> 3, h = p & 7;
-        const uint32_t row0 = (uint32_t)(sl * len);
-        // K / V of this (sequence, head): unpacked once for short sequences, kept packed (4 registers per key)
-        // and unpacked on use for the 16-token variant
-        constexpr bool kUnpacked = MAXLEN <= 8;
-        float kf[kUnpacked ? MAXLEN : 1][8], vf[kUnpacked ? MAXLEN : 1][8];
-        uint4 kp[kUnpacked ? 1 : MAXLEN], vp[kUnpacked ? 1 : MAXLEN];
+      // ---- causal attention (transformer.py:58-65): work item = (sequence, head[, query parity]) ----
+      {
+        const int npairs = nseq * FH;
+        const int nsplit = npairs * 2 <= FGROUP_THREADS ? 2 : 1;   // few pairs: two threads share one, by query parity
+        for (int it = gt; it < npairs * nsplit; it += FGROUP_THREADS) {
+          const int p = nsplit == 2 ? it >> 1 : it;
+          const int qpar = nsplit == 2 ? (it & 1) : -1;
+          const int sl = p >> 3, hd = p & 7;
+          const uint32_t row0 = (uint32_t)(sl * len);
+          // K unpacked once for short sequences; the 16-token variant keeps K packed too (4 registers per key)
+          constexpr bool kUnpackK = false;   // at 128 registers per thread even 8 unpacked keys spill
+          float kf[kUnpackK ? MAXLEN : 1][8];
+          uint4 kp[kUnpackK ? 1 : MAXLEN], vp[MAXLEN];
 #pragma unroll
-        for (int j = 0; j < MAXLEN; ++j) {
-          if (j < len) {
-            const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j, h));
-            const uint4 vw = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j, h));
-            if constexpr (kUnpacked) {
-              unpack8(kw, kf[j]);
-              unpack8(vw, vf[j]);
-            } else {
-              kp[j] = kw;
-              vp[j] = vw;
+          for (int j = 0; j < MAXLEN; ++j) {
+            if (j < len) {
+              const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j, hd));
+              if constexpr (kUnpackK) unpack8(kw, kf[j]);
+              else kp[j] = kw;
+              vp[j] = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j, hd));
             }
           }
-        }
-        const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
+          const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
-        for (int t = 0; t < MAXLEN; ++t) {
-          if (t < len) {
-            uint8_t* qptr = B0 + umma::sw128_offset(row0 + t, h);
-            float q[8];
-            unpack8(*reinterpret_cast<const uint4*>(qptr), q);
-            float sc[MAXLEN];
-            float mx = -INFINITY;
+          for (int t = 0; t < MAXLEN; ++t) {
+            if (t < len && (qpar < 0 || (t & 1) == qpar)) {
+              uint8_t* qptr = B0 + umma::sw128_offset(row0 + t, hd);
+              float q[8];
+              unpack8(*reinterpret_cast<const uint4*>(qptr), q);
+              float sc[MAXLEN];
+              float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j <= t; ++j) {
-              float d = 0.f;
-              float kj[8];
-              if constexpr (kUnpacked) {
+              for (int j = 0; j <= t; ++j) {
+                float d = 0.f;
+                float kj[8];
+                if constexpr (kUnpackK) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) kj[c] = kf[j][c];
-              } else {
-                unpack8(kp[j], kj);
+                  for (int c = 0; c < 8; ++c) kj[c] = kf[j][c];
+                } else {
+                  unpack8(kp[j], kj);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d = fmaf(q[c], kj[c], d);
+                d = d * inv_sqrt_dh;
+                sc[j] = d;
+                mx = fmaxf(mx, d);
               }
+              float z = 0.f;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) d = fmaf(q[c], kj[c], d);
-              d = d * inv_sqrt_dh;
-              sc[j] = d;
-              mx = fmaxf(mx, d);
-            }
-            float z = 0.f;
+              for (int j = 0; j <= t; ++j) {
+                sc[j] = __expf(sc[j] - mx);
+                z += sc[j];
+              }
+              const float inv_z = __fdividef(1.0f, z);
+              float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j <= t; ++j) {
-              sc[j] = __expf(sc[j] - mx);
-              z += sc[j];
-            }
-            const float inv_z = __fdividef(1.0f, z);
-            float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j <= t; ++j) {
-              const float pj = sc[j] * inv_z;
-              float vj[8];
-              if constexpr (kUnpacked) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) vj[c] = vf[j][c];
-              } else {
+              for (int j = 0; j <= t; ++j) {
+                const float pj = sc[j] * inv_z;
+                float vj[8];
                 unpack8(vp[j], vj);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, vj[c], o[c]);
               }
+              if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
+                const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, vj[c], o[c]);
+                for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
+              }
+              uint4 w;
+              w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
+              w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(qptr) = w;
             }
-            if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
-              const uint32_t k = (uint32_t)(row_keep_mask(ms, prr.item, prr.draw, prr.seq_local, (uint32_t)t, sb + 4u) >>
-                                            (8 * h)) & 0xFFu;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
-            }
-            uint4 w;
-            w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
-            w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(qptr) = w;
           }
         }
       }
@@ -640,73 +734,67 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
       // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
       gemm(descA0, wl + lay.off_out, FD, 4);
       {
-        const uint64_t k_attn = (fl & BFB200_SITE_ATTN_RESID)
-                                    ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 1u) : 0ull;
-        const uint64_t k_ffn_in = (fl & BFB200_SITE_FFN_IN)
-                                      ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 2u) : 0ull;
-        float v[FD], x[FD];
-        tmem_load_row64(tW, v);
-        if (fl & BFB200_SITE_ATTN_RESID) drop_row(v, k_attn, ms.scale);
-        tmem_load_row64(tX, x);
+        const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
+        const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
+        float v[HW], x[HW];
+        tmem_load_half(tW + h * HW, v);
+        if (fl & BFB200_SITE_ATTN_RESID) drop_half(v, k_attn, ms.scale);
+        tmem_load_half(tX, x);
 #pragma unroll
-        for (int i = 0; i < FD; ++i) v[i] += x[i];
-        layer_norm_row(v, pl, pl + 64, a.ln_eps);
-        if (fl & BFB200_SITE_FFN_IN) drop_row(v, k_ffn_in, ms.scale);
-        store_row_f16(B0, gt, v);
+        for (int i = 0; i < HW; ++i) v[i] += x[i];
+        layer_norm_half(v, red, row, h, bar_id, pl + h * HW, pl + 64 + h * HW, a.ln_eps);
+        if (fl & BFB200_SITE_FFN_IN) drop_half(v, k_ffn_in, ms.scale);
+        store_half_f16(B0, row, h, v);
       }
 
-      // ---- FFN: Linear(d -> F) + bias + ReLU (transformer.py:151-155) ----
+      // ---- FFN: Linear(d -> F) + bias + ReLU (transformer.py:151-155); each half takes fp / 2 columns ----
       gemm(descA0, wl + lay.off_w1, (int)lay.fp, 4);
       {
         const float* b1 = pl + 128;
-        for (uint32_t c0 = 0; c0 < lay.fp; c0 += 16) {
-          uint32_t r[16];
-          umma::tmem_ld16(tW + c0, r);
+        const uint32_t half_cols = lay.fp >> 1;   // multiple of 8
+        for (uint32_t c0 = half_cols * h; c0 < half_cols * (h + 1); c0 += 8) {
+          uint32_t r[8];
+          umma::tmem_ld8(tW + c0, r);
           umma::tmem_ld_wait();
-          uint4 w0, w1;
-          float hcol[16];
+          float hc[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) hcol[i] = fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
-          w0.x = umma::pack_f16x2(hcol[0], hcol[1]); w0.y = umma::pack_f16x2(hcol[2], hcol[3]);
-          w0.z = umma::pack_f16x2(hcol[4], hcol[5]); w0.w = umma::pack_f16x2(hcol[6], hcol[7]);
-          w1.x = umma::pack_f16x2(hcol[8], hcol[9]); w1.y = umma::pack_f16x2(hcol[10], hcol[11]);
-          w1.z = umma::pack_f16x2(hcol[12], hcol[13]); w1.w = umma::pack_f16x2(hcol[14], hcol[15]);
-          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(gt, c0 >> 3)) = w0;
-          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(gt, (c0 >> 3) + 1)) = w1;
+          for (int i = 0; i < 8; ++i) hc[i] = fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
+          uint4 w;
+          w.x = umma::pack_f16x2(hc[0], hc[1]); w.y = umma::pack_f16x2(hc[2], hc[3]);
+          w.z = umma::pack_f16x2(hc[4], hc[5]); w.w = umma::pack_f16x2(hc[6], hc[7]);
+          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(row, c0 >> 3)) = w;
         }
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
       gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
       {
-        const uint64_t k_resid = (fl & BFB200_SITE_FFN_RESID)
-                                     ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 3u) : 0ull;
-        const uint64_t k_out = (fl & BFB200_SITE_LAYER_OUT)
-                                   ? row_keep_mask(ms, rr.item, rr.draw, rr.seq_local, (uint32_t)pos, sb + 0u) : 0ull;
-        float v[FD], x[FD];
-        tmem_load_row64(tW, v);
-        const float* b2 = pl + 192;
+        const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
+        const uint32_t k_out = (fl & BFB200_SITE_LAYER_OUT) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
+        float v[HW], x[HW];
+        tmem_load_half(tW + h * HW, v);
+        const float* b2 = pl + 192 + h * HW;
 #pragma unroll
-        for (int i = 0; i < FD; ++i) v[i] += b2[i];
-        if (fl & BFB200_SITE_FFN_RESID) drop_row(v, k_resid, ms.scale);
-        tmem_load_row64(tX, x);
+        for (int i = 0; i < HW; ++i) v[i] += b2[i];
+        if (fl & BFB200_SITE_FFN_RESID) drop_half(v, k_resid, ms.scale);
+        tmem_load_half(tX, x);
 #pragma unroll
-        for (int i = 0; i < FD; ++i) v[i] += x[i];
-        layer_norm_row(v, pl + 256, pl + 320, a.ln_eps);
-        if (fl & BFB200_SITE_LAYER_OUT) drop_row(v, k_out, ms.scale);   // transformer.py:370
-        if (l + 1 < a.n_layers) tmem_store_row64(tX, v);
-        store_row_f16(B0, gt, v);
+        for (int i = 0; i < HW; ++i) v[i] += x[i];
+        layer_norm_half(v, red, row, h, bar_id, pl + 256 + h * HW, pl + 320 + h * HW, a.ln_eps);
+        if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);   // transformer.py:370
+        if (l + 1 < a.n_layers) tmem_store_half(tX, v);
+        store_half_f16(B0, row, h, v);
       }
     }
 
     // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
-    gemm(descA0, img_u32 + lay.off_head, (int)lay.vp, 4);
-    const int stage_stride = (int)lay.vp + a.tps;
-    float* stage = reinterpret_cast<float*>(B1);  // B1 + B2: 32 KB
+    gemm(descA0, img_u32 + lay.off_head, FMAXV, 4);
+    const int stage_stride = FMAXV + a.tps;
+    float* stage = reinterpret_cast<float*>(B1);  // B1 + B2: 32 KB (K / V / FFN hidden are dead)
     {
       const float* hb = params + a.n_layers * PARAMS_PER_LAYER;
       const bool is_last = row_valid && pos == len - 1;
-      for (uint32_t c0 = 0; c0 < lay.vp; c0 += 16) {
+      for (uint32_t c0 = 64u * h; c0 < 64u * h + 64u; c0 += 16) {
         uint32_t r[16];
         umma::tmem_ld16(tW + c0, r);
         umma::tmem_ld_wait();
@@ -717,11 +805,11 @@ __global__ void __launch_bounds__(FGROUPS * FROWS, 1) mc_forward_kernel(const Fu
       }
     }
     umma::tc_fence_before_sync();
-    umma::group_sync(bar_id, FROWS);
+    umma::group_sync(bar_id, FGROUP_THREADS);
 
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
-    if (a.tps == 8) score_phase<8>(a, stage, stage_stride, gt, nseq, s0, len);
-    else            score_phase<4>(a, stage, stage_stride, gt, nseq, s0, len);
+    if (a.tps == 16) score_phase<16>(a, stage, stage_stride, gt, nseq, s0, len);
+    else             score_phase<8>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
@@ -773,8 +861,8 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   a.site_flags = m.site_flags;
   a.ln_eps = m.ln_eps;
   a.len = len;
-  a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 4 threads
-  a.tps = (FROWS / a.spt) >= 8 ? 8 : 4;
+  a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 8 threads
+  a.tps = (FGROUP_THREADS / a.spt) >= 16 ? 16 : 8;
   a.n_seq = n_seq;
   a.n_tiles = (n_seq + a.spt - 1) / a.spt;
   a.tokens = tokens; a.tokens_out = tokens_out; a.tok_stride = tok_stride;
@@ -794,10 +882,10 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   if (grid < 1) grid = 1;
   if (len <= 8) {
     cudaFuncSetAttribute(mc_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mc_forward_kernel<8><<<(int)grid, FGROUPS * FROWS, smem, st>>>(a);
+    mc_forward_kernel<8><<<(int)grid, FTHREADS, smem, st>>>(a);
   } else {
     cudaFuncSetAttribute(mc_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mc_forward_kernel<16><<<(int)grid, FGROUPS * FROWS, smem, st>>>(a);
+    mc_forward_kernel<16><<<(int)grid, FTHREADS, smem, st>>>(a);
   }
   BFB_LAUNCH_CHECK("mc_forward_kernel", st);
   return BFB200_OK;
