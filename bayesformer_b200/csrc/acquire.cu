@@ -5,6 +5,7 @@
 // one warp owns one pool item, lanes stride over the class dimension so every global
 // load is a coalesced 128-byte line, reductions stay in registers / warp shuffles.
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace bfb {
 
@@ -13,11 +14,12 @@ namespace bfb {
 // ---------------------------------------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(256) compute_uncertainty_kernel(const float* __restrict__ probs,
-                                                                  int64_t n_rows, int n_classes,
-                                                                  int mode, float* __restrict__ out) {
+                                                                  int64_t row_begin, int64_t n_rows,
+                                                                  int n_classes, int mode,
+                                                                  float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows;
+  for (int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows;
        row += warps_total) {
     const float* src = probs + row * n_classes;
     float p[NPL];
@@ -39,14 +41,14 @@ __global__ void __launch_bounds__(256) compute_uncertainty_kernel(const float* _
 // ---------------------------------------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(256) acquire_kernel(const float* __restrict__ x, int is_logp,
-                                                      int n_draws, int64_t n_items, int n_classes,
-                                                      float* __restrict__ mean_p,
+                                                      int n_draws, int64_t item_begin, int64_t n_items,
+                                                      int n_classes, float* __restrict__ mean_p,
                                                       float* __restrict__ score_of_mean,
                                                       float* __restrict__ mean_of_scores) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t draw_stride = n_items * (int64_t)n_classes;
-  for (int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items;
+  for (int64_t item = item_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items;
        item += warps_total) {
     const float* src = x + item * n_classes;
     float acc[NPL];
@@ -106,6 +108,157 @@ __global__ void __launch_bounds__(256) acquire_kernel(const float* __restrict__ 
       mean_of_scores[item] = a0 / inv_t;
       mean_of_scores[n_items + item] = a1 / inv_t;
       mean_of_scores[2 * n_items + item] = a2 / inv_t;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// HBM-streaming acquisition kernel for n_classes <= 128 (SURVEY 8d "Acquisition kernel standalone").
+// A tile of 128 consecutive items of one draw is a contiguous byte range of x, so it is fetched by ONE 1-D bulk
+// TMA copy (cp.async.bulk -> shared memory, completion on an mbarrier) into a ring of stages; the copy engine
+// keeps HBM busy while the 128 threads each reduce their own item from shared memory (thread = item: no
+// shuffles, 32 items per warp instruction).  A thread walks its row starting at a thread-dependent rotation when
+// n_classes is even, which makes the stride-C shared-memory reads conflict-free for every C.
+// Draws are visited in index order and divided by T at the end, as the reference's `uncertainties += ...` loop.
+// ---------------------------------------------------------------------------
+constexpr int AQ_ROWS = 128;
+
+template <bool IS_LOGP, bool WANT_MEAN_P>
+__global__ void __launch_bounds__(AQ_ROWS) acquire_tma_kernel(const float* __restrict__ x, int n_draws,
+                                                               int64_t n_items, int64_t n_tiles, int n_classes,
+                                                               int n_stages, uint32_t need,  // bit0 max, 1 margin, 2 entropy
+                                                               float* __restrict__ mean_p,
+                                                               float* __restrict__ score_of_mean,
+                                                               float* __restrict__ mean_of_scores,
+                                                               float* __restrict__ single_out, int single_mode) {
+  extern __shared__ __align__(128) uint8_t aq_smem[];
+  __shared__ uint64_t full_bar[4];
+  const int C = n_classes;
+  const uint32_t tile_bytes = (uint32_t)AQ_ROWS * C * 4u;
+  float* stage_base = reinterpret_cast<float*>(aq_smem);
+  float* acc_tile = WANT_MEAN_P ? stage_base + (size_t)n_stages * AQ_ROWS * C : nullptr;
+  const int tid = threadIdx.x;
+  const int64_t draw_stride = n_items * (int64_t)C;
+
+  if (tid == 0) {
+    for (int i = 0; i < n_stages; ++i) umma::mbar_init(&full_bar[i], 1);
+    umma::fence_mbar_init();
+  }
+  __syncthreads();
+
+  // flattened sequence of (tile, draw) loads of this CTA; load k goes to stage k % n_stages
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t n_loads = my_tiles * n_draws;
+  auto issue = [&](int64_t k) {
+    const int64_t tile = blockIdx.x + (k / n_draws) * gridDim.x;
+    const int t = (int)(k % n_draws);
+    const int st = (int)(k % n_stages);
+    umma::mbar_expect_tx(&full_bar[st], tile_bytes);
+    umma::bulk_g2s(stage_base + (size_t)st * AQ_ROWS * C, x + t * draw_stride + tile * AQ_ROWS * (int64_t)C, tile_bytes,
+                   &full_bar[st]);
+  };
+  if (tid == 0)
+    for (int64_t k = 0; k < n_stages && k < n_loads; ++k) issue(k);
+
+  const int rot = (C & 1) ? 0 : tid % C;   // even C: start column differs per thread -> no bank conflicts
+  auto col = [&](int j) { const int c = rot + j; return c >= C ? c - C : c; };
+  const float inv_t = 1.0f / (float)n_draws;
+  int64_t k = 0;
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    const int64_t item = tile * AQ_ROWS + tid;
+    float a_max = 0.f, a_margin = 0.f, a_ent = 0.f;
+    float* acc = WANT_MEAN_P ? acc_tile + tid * C : nullptr;
+    for (int t = 0; t < n_draws; ++t, ++k) {
+      const int st = (int)(k % n_stages);
+      umma::mbar_wait(&full_bar[st], (uint32_t)((k / n_stages) & 1));
+      float* row = stage_base + (size_t)st * AQ_ROWS * C + tid * C;
+      // The row is walked in rotated order with a warp-uniform trip count; the column is derived from the loop
+      // counter (no serial dependency between iterations).
+      float b1 = -INFINITY, b2 = -INFINITY, ent = 0.f;
+      if (IS_LOGP) {
+        // probs = softmax(log-probs), as dropout_uncertainty does (active_learning.py:147):
+        // e = exp(l - max), z = sum e, p = e / z.  The scores are taken on e and rescaled, and the entropy uses
+        // log p = (l - max) - log z exactly (log(p + 1e-10) differs from it only where p < 1e-8).
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int j = 0; j < C; ++j) mx = fmaxf(mx, row[col(j)]);
+        float z = 0.f, el = 0.f;
+        auto body = [&](int c) {
+          const float d = row[c] - mx;
+          const float e = __expf(d);
+          z += e;
+          if (need & 4u) el = fmaf(e, fmaxf(d, -1e30f), el);
+          if (need & 3u) {
+            b2 = fmaxf(b2, fminf(b1, e));
+            b1 = fmaxf(b1, e);
+          }
+          if (WANT_MEAN_P) row[c] = e;
+        };
+#pragma unroll 4
+        for (int j = 0; j < C; ++j) body(col(j));
+        const float inv_z = 1.0f / z;
+        b1 *= inv_z;
+        b2 *= inv_z;
+        ent = el * inv_z - __logf(z);   // sum p log p
+        if (WANT_MEAN_P) {
+          auto accum = [&](int c) { acc[c] = t == 0 ? row[c] * inv_z : fmaf(row[c], inv_z, acc[c]); };
+#pragma unroll 4
+          for (int j = 0; j < C; ++j) accum(col(j));
+        }
+      } else {
+        auto body = [&](int c) {
+          const float p = row[c];
+          if (need & 3u) {
+            b2 = fmaxf(b2, fminf(b1, p));
+            b1 = fmaxf(b1, p);
+          }
+          if (need & 4u) ent = fmaf(p, __logf(p + 1e-10f), ent);
+          if (WANT_MEAN_P) acc[c] = t == 0 ? p : acc[c] + p;
+        };
+#pragma unroll 4
+        for (int j = 0; j < C; ++j) body(col(j));
+      }
+      a_max += b1;
+      a_margin += b1 - b2;
+      a_ent -= ent;
+      // this stage is consumed: refill it with the load n_stages ahead (generic-proxy accesses of the stage are
+      // ordered before the copy engine's overwrite)
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0 && k + n_stages < n_loads) issue(k + n_stages);
+    }
+    if (mean_of_scores != nullptr) {
+      if (need & 1u) mean_of_scores[item] = a_max * inv_t;
+      if (need & 2u) mean_of_scores[n_items + item] = a_margin * inv_t;
+      if (need & 4u) mean_of_scores[2 * n_items + item] = a_ent * inv_t;
+    }
+    if (single_out != nullptr)
+      single_out[item] = (single_mode == BFB200_MODE_MAX ? a_max : single_mode == BFB200_MODE_MARGIN ? a_margin : a_ent) * inv_t;
+    if (WANT_MEAN_P) {
+      float b1 = -INFINITY, b2 = -INFINITY, ent = 0.f;
+      auto fin = [&](int c) {
+        const float p = acc[c] * inv_t;
+        acc[c] = p;
+        b2 = fmaxf(b2, fminf(b1, p));
+        b1 = fmaxf(b1, p);
+        ent = fmaf(p, __logf(p + 1e-10f), ent);
+      };
+#pragma unroll 4
+      for (int j = 0; j < C; ++j) fin(col(j));
+      if (score_of_mean != nullptr) {
+        score_of_mean[item] = b1;
+        score_of_mean[n_items + item] = b1 - b2;
+        score_of_mean[2 * n_items + item] = -ent;
+      }
+      __syncthreads();
+      if (mean_p != nullptr) {   // the tile of predictive means is contiguous in mean_p: coalesced 128-bit stores
+        float4* dst = reinterpret_cast<float4*>(mean_p + tile * AQ_ROWS * (int64_t)C);
+        const float4* src = reinterpret_cast<const float4*>(acc_tile);
+        for (int i = tid; i < AQ_ROWS * C / 4; i += AQ_ROWS) dst[i] = src[i];
+      }
+      __syncthreads();
     }
   }
 }
@@ -280,6 +433,53 @@ static int grid_for(int64_t work_items, int per_block, int blocks_per_sm = 8) {
   return (int)(need < cap ? need : cap);
 }
 
+
+// number of SMs of the current device
+static int aq_sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+
+// Launch the TMA-staged kernel on the full 128-item tiles of x; returns the number of items it covered (0 when
+// the shape or alignment is outside its class, in which case the warp-per-item kernels take everything).
+static int64_t launch_acquire_tma(const float* x, int is_logp, int n_draws, int64_t n_items, int n_classes,
+                                  uint32_t need, float* mean_p, float* score_of_mean, float* mean_of_scores,
+                                  float* single_out, int single_mode, cudaStream_t st, int* rc) {
+  *rc = BFB200_OK;
+  const int64_t n_tiles = n_items / AQ_ROWS;
+  if (n_tiles == 0 || n_classes > 128) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return 0;
+  if (n_draws > 1 && ((n_items * (int64_t)n_classes) & 3) != 0) return 0;   // every draw's tile 16-byte aligned
+  const bool want_mean = mean_p != nullptr || score_of_mean != nullptr;
+  if (want_mean && mean_p != nullptr && (reinterpret_cast<uintptr_t>(mean_p) & 15u) != 0) return 0;
+  const size_t tile_bytes = (size_t)AQ_ROWS * n_classes * sizeof(float);
+  int n_stages = (int)((200 * 1024 - (want_mean ? tile_bytes : 0)) / tile_bytes);
+  if (n_stages > 4) n_stages = 4;
+  if (n_stages < 2) return 0;
+  const size_t smem = tile_bytes * (n_stages + (want_mean ? 1 : 0));
+  int64_t grid = n_tiles < aq_sm_count() ? n_tiles : aq_sm_count();
+#define AQ_LAUNCH(LOGP, MEAN)                                                                              \
+  do {                                                                                                     \
+    cudaFuncSetAttribute(acquire_tma_kernel<LOGP, MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    acquire_tma_kernel<LOGP, MEAN><<<(int)grid, AQ_ROWS, smem, st>>>(x, n_draws, n_items, n_tiles, n_classes,   \
+                                                                     n_stages, need, mean_p, score_of_mean,  \
+                                                                     mean_of_scores, single_out, single_mode); \
+  } while (0)
+  if (is_logp) { if (want_mean) AQ_LAUNCH(true, true); else AQ_LAUNCH(true, false); }
+  else         { if (want_mean) AQ_LAUNCH(false, true); else AQ_LAUNCH(false, false); }
+#undef AQ_LAUNCH
+  count_launch("acquire_tma_kernel", st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of acquire_tma_kernel failed: %s", cudaGetErrorString(e));
+    *rc = BFB200_ERR_CUDA;
+    return 0;
+  }
+  return n_tiles * AQ_ROWS;
+}
+
 }  // namespace bfb
 
 using namespace bfb;
@@ -295,8 +495,14 @@ extern "C" int bfb200_compute_uncertainty(const float* probs, int64_t n_rows, in
   BFB_DEV(probs);
   BFB_DEV(out);
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(n_rows, 8);
-#define LAUNCH_CU(NPL) compute_uncertainty_kernel<NPL><<<grid, 256, 0, st>>>(probs, n_rows, n_classes, mode, out)
+  int rc = BFB200_OK;
+  const uint32_t need = mode == BFB200_MODE_ENTROPY ? 4u : 3u;
+  const int64_t row_begin = launch_acquire_tma(probs, 0, 1, n_rows, n_classes, need, nullptr, nullptr, nullptr, out, mode,
+                                               st, &rc);
+  if (rc != BFB200_OK) return rc;
+  if (row_begin == n_rows) return BFB200_OK;
+  const int grid = grid_for(n_rows - row_begin, 8);
+#define LAUNCH_CU(NPL) compute_uncertainty_kernel<NPL><<<grid, 256, 0, st>>>(probs, row_begin, n_rows, n_classes, mode, out)
   if (n_classes <= 32) LAUNCH_CU(1);
   else if (n_classes <= 64) LAUNCH_CU(2);
   else if (n_classes <= 128) LAUNCH_CU(4);
@@ -319,8 +525,13 @@ extern "C" int bfb200_acquire(const float* x, int32_t is_logp, int32_t n_draws, 
   BFB_DEV_OPT(score_of_mean);
   BFB_DEV_OPT(mean_of_scores);
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(n_items, 8);
-#define LAUNCH_AQ(NPL) acquire_kernel<NPL><<<grid, 256, 0, st>>>(x, is_logp, n_draws, n_items, n_classes, mean_p, score_of_mean, mean_of_scores)
+  int rc = BFB200_OK;
+  const int64_t item_begin = launch_acquire_tma(x, is_logp, n_draws, n_items, n_classes, mean_of_scores != nullptr ? 7u : 0u,
+                                                mean_p, score_of_mean, mean_of_scores, nullptr, 0, st, &rc);
+  if (rc != BFB200_OK) return rc;
+  if (item_begin == n_items) return BFB200_OK;
+  const int grid = grid_for(n_items - item_begin, 8);
+#define LAUNCH_AQ(NPL) acquire_kernel<NPL><<<grid, 256, 0, st>>>(x, is_logp, n_draws, item_begin, n_items, n_classes, mean_p, score_of_mean, mean_of_scores)
   if (n_classes <= 32) LAUNCH_AQ(1);
   else if (n_classes <= 64) LAUNCH_AQ(2);
   else if (n_classes <= 128) LAUNCH_AQ(4);

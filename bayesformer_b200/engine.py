@@ -71,24 +71,26 @@ def compute_uncertainty(probs: torch.Tensor, mode: str = "max") -> torch.Tensor:
 
 @dataclass
 class Acquisition:
-    mean_p: torch.Tensor          # (B, C)
-    score_of_mean: torch.Tensor   # (3, B): max, margin, entropy of the predictive mean
+    mean_p: torch.Tensor | None          # (B, C)
+    score_of_mean: torch.Tensor | None   # (3, B): max, margin, entropy of the predictive mean
     mean_of_scores: torch.Tensor  # (3, B): mean over draws of the per-draw scores
 
 
-def acquire(x: torch.Tensor, is_logp: bool = False) -> Acquisition:
-    """Reduce MC outputs x (T, B, C) to predictive mean + all three scores in one pass."""
+def acquire(x: torch.Tensor, is_logp: bool = False, want_mean_p: bool = True) -> Acquisition:
+    """Reduce MC outputs x (T, B, C) to predictive mean + all three scores in one pass.  With
+    `want_mean_p=False` only the mean-of-scores (what dropout_uncertainty accumulates) is produced and the
+    predictive-mean outputs are None."""
     _require_cuda(x, "x")
     if x.dim() != 3:
         raise ValueError("acquire expects (draws, items, classes)")
     x = _f32c(x)
     T, B, Cn = x.shape
-    mean_p = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
-    som = torch.empty(3, B, dtype=torch.float32, device=x.device)
+    mean_p = torch.empty(B, Cn, dtype=torch.float32, device=x.device) if want_mean_p else None
+    som = torch.empty(3, B, dtype=torch.float32, device=x.device) if want_mean_p else None
     mos = torch.empty(3, B, dtype=torch.float32, device=x.device)
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        _lib.check(lib.bfb200_acquire(x.data_ptr(), int(is_logp), T, B, Cn, mean_p.data_ptr(), som.data_ptr(),
+        _lib.check(lib.bfb200_acquire(x.data_ptr(), int(is_logp), T, B, Cn, _ptr(mean_p), _ptr(som),
                                       mos.data_ptr(), _stream_ptr(x.device)))
     return Acquisition(mean_p, som, mos)
 

@@ -220,6 +220,7 @@ def main() -> None:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--pool", type=int, default=POOL_PER_GPU, help="pool items per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the stand-alone kernel measurements")
     ap.add_argument("--compute", default="auto", choices=["auto", "fp16", "fp32"],
                     help="auto/fp16: fused tcgen05 kernel (fp16 operands, fp32 accumulate); fp32: exact layered CUDA path")
     args = ap.parse_args()
@@ -355,6 +356,11 @@ def main() -> None:
             "peak_tflops": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
             "frac": value / world * flops_per_pool_sample(P, N) / 1e12 / peaks["bf16_tflops_sustained"]},
     }
+    if rank == 0 and world == 1 and not args.no_aux:
+        try:
+            line["aux_kernels"] = aux_kernel_benchmarks(dev, peaks, peak_src)
+        except Exception as exc:  # the headline must never be lost to an auxiliary measurement
+            line["aux_kernels"] = {"error": repr(exc)}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (rank 0 of a multi-rank job skips it)
             line["cpu_baseline"] = {k: v for k, v in
@@ -363,6 +369,62 @@ def main() -> None:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
+    """Stand-alone measurements of the other kernels on the path (rank 0, N = 1): the acquisition reduction and
+    compute_uncertainty against the HBM roofline, top-k, and the toy-classifier MC kernel (SURVEY C2i:
+    MLP(2, 50, 1, dropout 0.5), T = 20, 100 k moons points).  CUDA events, 3 warm-ups, mean of 10; every input is
+    far larger than the 126 MB L2 except where noted."""
+    from bayesformer_b200 import engine
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    hbm = peaks["hbm_gbs"]
+    T, B, C = 20, 400_000, 114
+    x = torch.log_softmax(torch.randn(T, B, C, device=dev), dim=-1)          # 3.6 GB of per-draw log-probs
+    for label, want_mean, extra in (("acquire[mean-of-scores]", False, 3), ("acquire[+predictive mean]", True, C + 6)):
+        ms = timed(lambda: engine.acquire(x, is_logp=True, want_mean_p=want_mean))
+        bytes_alg = T * B * C * 4 + B * extra * 4
+        out[label] = {"shape": [T, B, C], "ms": ms, "bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": hbm,
+                      "unit": "GB/s", "frac": bytes_alg / ms / 1e6 / hbm, "peak_source": peak_src,
+                      "algorithmic_bytes": bytes_alg, "item_steps_per_s": B / (ms * 1e-3)}
+    probs = torch.softmax(x[0].repeat(8, 1), dim=-1)                          # (3.2 M, 114) = 1.46 GB
+    for mode in ("max", "margin", "entropy"):
+        ms = timed(lambda: engine.compute_uncertainty(probs, mode))
+        b = probs.numel() * 4 + probs.shape[0] * 4
+        out[f"compute_uncertainty[{mode}]"] = {"shape": list(probs.shape), "ms": ms, "bound": "hbm",
+                                               "achieved": b / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                               "frac": b / ms / 1e6 / hbm, "peak_source": peak_src}
+    del x, probs
+    scores = torch.randn(1_000_000, device=dev)
+    ms = timed(lambda: engine.topk_keys(scores, K_TOP))
+    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident, latency bound (3 launches)"}
+    # toy classifier, SURVEY C2i
+    from bayesformer_b200.model.bayesian_classification import MLP
+    torch.manual_seed(SEED)
+    mlp = MLP(2, 50, 1, dropout=True, dropout_rate=0.5).to(dev).eval()
+    for n in (100_000, 10_000_000):
+        pts = torch.randn(n, 2, device=dev)
+        with torch.no_grad():
+            ms = timed(lambda: mlp.mc_predict(pts, nsamples=T_MC, return_scores=True))
+        out[f"mlp_mc_kernel[{n}]"] = {"items": n, "T_mc": T_MC, "ms": ms, "items_per_s": n / (ms * 1e-3),
+                                      "bernoulli_draws_per_s": n * T_MC * 50 / (ms * 1e-3),
+                                      "hbm_gbs": n * 12 / ms / 1e6,
+                                      "note": "ALU/RNG bound by construction: 12 B of HBM, 1,000 Bernoulli draws and "
+                                              "1,100 FMA per item (SURVEY 8d)"}
+    return out
 
 
 def kernel_roofline(name: str, stat: dict, passes: int, pool: int, P: int, N: int, peaks: dict, peak_src: str) -> dict:

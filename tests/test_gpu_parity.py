@@ -76,7 +76,10 @@ def test_compute_uncertainty_edge_cases(engine, dev):
 
 
 @pytest.mark.parametrize("is_logp", [False, True])
-@pytest.mark.parametrize("shape", [(20, 100, 114), (1, 7, 2), (50, 33, 67), (3, 5, 300)])
+@pytest.mark.parametrize("shape", [(20, 100, 114), (1, 7, 2), (50, 33, 67), (3, 5, 300),
+                                   # >= 128 items: TMA-staged kernel on the full tiles + warp-per-item tail
+                                   (20, 1000, 114), (5, 132, 67), (7, 300, 2), (3, 256, 128), (4, 384, 33), (2, 130, 114),
+                                   (3, 129, 67)])
 def test_acquire_matches_oracle(engine, dev, is_logp, shape):
     g = torch.Generator().manual_seed(sum(shape))
     logits = torch.randn(*shape, generator=g) * 2.0
