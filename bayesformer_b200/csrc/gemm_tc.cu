@@ -1,0 +1,289 @@
+// MC-batched tensor-core linear layer: C[M, N] = A[M, K] * W[N, K]^T (+ bias) (ReLU)
+// nn.Linear of src/model/transformer.py (:33-35 Q/K/V, :100 W_out, :152-154 FFN, :336 vocabulary head) over the
+// R = B * T_mc * len token rows of a chunk, for models outside the fused kernel's class (d_model 512, F 2048 ...).
+//
+// sm_100a design (the canonical Blackwell GEMM): persistent CTAs, 192 threads in three roles
+//   warp 0      one lane issues 2-D TMA loads (cp.async.bulk.tensor, 128-byte swizzle) of the 128 x 64 A tile and
+//               the BN x 64 W tile into a 4-stage shared-memory ring, completion on `full` mbarriers;
+//   warp 1      one lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN, K = 16 x 4 per stage) into one of
+//               two TMEM accumulator stages; tcgen05.commit releases the ring slot (`empty`) and, after the last
+//               K block, hands the accumulator to the epilogue (`acc_full`);
+//   warps 2-5   epilogue: thread = accumulator row; tcgen05.ld 32 columns at a time, + bias, ReLU, convert, 16-byte
+//               global stores (16-bit and/or fp32 outputs), then `acc_empty` so the MMA warp can reuse the stage.
+// Operands are 16-bit (fp16 or bf16, instruction-descriptor format bit), accumulation fp32.  M / N / K tails are
+// zero-filled by TMA and masked in the epilogue.  Tiles are walked N-fastest so an A row block stays in L2 while
+// all of its N tiles are produced.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace bfb {
+
+namespace {
+
+constexpr int GM = 128;       // tile rows (UMMA M)
+constexpr int GK = 64;        // K per stage: one 128-byte swizzle row of 16-bit elements
+constexpr int GSTAGES = 4;
+constexpr int GACC = 2;       // TMEM accumulator stages
+constexpr int GTHREADS = 192;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(umma::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+struct GemmArgs {
+  int64_t M;
+  int N, K;
+  const float* bias;       // (N) or nullptr
+  void* out16;             // (M, N) 16-bit or nullptr
+  float* out32;            // (M, N) fp32 or nullptr
+  int relu;
+  uint32_t fmt;            // umma::kFmtF16 / kFmtBF16
+  int64_t ldc;             // output row pitch in elements (= N)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_w,
+                                                              const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr uint32_t A_BYTES = GM * GK * 2, W_BYTES = BN * GK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles_m = (g.M + GM - 1) / GM;
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int64_t n_tiles = tiles_m * tiles_n;
+  const int k_blocks = (g.K + GK - 1) / GK;
+
+  if (warp == 0) {
+    umma::tmem_alloc(&tmem_slot, GACC * BN);   // 256 or 512 columns: a power of two
+    umma::tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < GSTAGES; ++i) {
+      umma::mbar_init(&full_bar[i], 1);
+      umma::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < GACC; ++i) {
+      umma::mbar_init(&acc_full[i], 1);
+      umma::mbar_init(&acc_empty[i], 4);   // one arrival per epilogue warp
+    }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t mb = tile / tiles_n;
+        const int nb = (int)(tile - mb * tiles_n);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          umma::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          umma::mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(sa, &map_a, kb * GK, (int)(mb * GM), &full_bar[s]);
+          tma_load_2d(sa + A_BYTES, &map_w, kb * GK, nb * BN, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma::instr_desc_16bit(GM, BN, g.fmt);
+      uint32_t it = 0, tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+        umma::mbar_wait(&acc_empty[as], aph ^ 1u);   // epilogue has drained this accumulator stage
+        umma::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          umma::mbar_wait(&full_bar[s], ph);
+          umma::tc_fence_after_sync();
+          const uint32_t sa = umma::smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma::smem_desc_sw128(sa), dw = umma::smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GK / 16; ++k) umma::mma_bf16_ss(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
+          umma::mma_commit(&empty_bar[s]);          // ring slot free once these MMAs have read it
+        }
+        umma::mma_commit(&acc_full[as]);            // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 -> TMEM lane quarters 2, 3, 0, 1 =====
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t tcount = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int64_t mb = tile / tiles_n;
+      const int nb = (int)(tile - mb * tiles_n);
+      const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+      umma::mbar_wait(&acc_full[as], aph);
+      umma::tc_fence_after_sync();
+      const int64_t row = mb * GM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        umma::tmem_ld32(tmem_base + lane_base + as * BN + c0, r);
+        umma::tmem_ld_wait();
+        const int n0 = nb * BN + c0;
+        if (n0 >= g.N) continue;   // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]);
+          if (g.bias != nullptr && n0 + i < g.N) x += __ldg(g.bias + n0 + i);
+          if (g.relu) x = fmaxf(x, 0.f);
+          v[i] = x;
+        }
+        if (row_ok) {
+          const bool full = n0 + 32 <= g.N && (g.ldc & 7) == 0;
+          if (g.out32 != nullptr) {
+            float* dst = g.out32 + row * g.ldc + n0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+              for (int i = 0; i < 32 && n0 + i < g.N; ++i) dst[i] = v[i];
+            }
+          }
+          if (g.out16 != nullptr) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(g.out16) + row * g.ldc + n0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 w;
+                if (g.fmt == umma::kFmtF16) {
+                  w.x = umma::pack_f16x2(v[i], v[i + 1]); w.y = umma::pack_f16x2(v[i + 2], v[i + 3]);
+                  w.z = umma::pack_f16x2(v[i + 4], v[i + 5]); w.w = umma::pack_f16x2(v[i + 6], v[i + 7]);
+                } else {
+                  w.x = umma::pack_bf16x2(v[i], v[i + 1]); w.y = umma::pack_bf16x2(v[i + 2], v[i + 3]);
+                  w.z = umma::pack_bf16x2(v[i + 4], v[i + 5]); w.w = umma::pack_bf16x2(v[i + 6], v[i + 7]);
+                }
+                *reinterpret_cast<uint4*>(dst + i) = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && n0 + i < g.N; ++i) {
+                const uint32_t w = g.fmt == umma::kFmtF16 ? umma::pack_f16x2(v[i], 0.f) : umma::pack_bf16x2(v[i], 0.f);
+                dst[i] = (uint16_t)(w & 0xFFFFu);
+              }
+            }
+          }
+        }
+      }
+      umma::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, GACC * BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// host: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D map over a (rows, K) 16-bit matrix with row pitch `pitch_elems`; box = 64 x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t pitch_elems, int box_rows, uint32_t fmt) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  BFB_REQUIRE(fn != nullptr, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, fmt == umma::kFmtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BFB_REQUIRE(r == CUDA_SUCCESS, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for rows=%lld K=%d pitch=%lld",
+              (int)r, (long long)rows, K, (long long)pitch_elems);
+  return BFB200_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32, int64_t M,
+                   int N, int K, int relu, uint32_t fmt, cudaStream_t st) {
+  if (M == 0 || N == 0) return BFB200_OK;
+  BFB_REQUIRE((K & 7) == 0 && (a_pitch & 7) == 0, BFB200_ERR_UNSUPPORTED,
+              "tensor-core GEMM needs K (%d) and the A row pitch (%lld) to be multiples of 8", K, (long long)a_pitch);
+  BFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0,
+              BFB200_ERR_INVALID_ARG, "GEMM operands must be 16-byte aligned");
+  const int BN = N > 128 ? 256 : 128;
+  CUtensorMap map_a, map_w;
+  BFB_CALL(make_map(&map_a, A, M, K, a_pitch, GM, fmt));
+  BFB_CALL(make_map(&map_w, W, N, K, K, BN, fmt));
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = N;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int64_t n_tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  const size_t smem = 1024 + (size_t)GSTAGES * (GM * GK * 2 + BN * GK * 2);
+  if (BN == 256) {
+    cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_tc_kernel<256><<<grid, GTHREADS, smem, st>>>(map_a, map_w, g);
+  } else {
+    cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_tc_kernel<128><<<grid, GTHREADS, smem, st>>>(map_a, map_w, g);
+  }
+  BFB_LAUNCH_CHECK("gemm_tc_kernel", st);
+  return BFB200_OK;
+}
+
+}  // namespace bfb
+
+// C[M, N] = A[M, K] W[N, K]^T (+ bias)(ReLU); A, W 16-bit (fmt 0 = fp16, 1 = bf16) device pointers, A rows `a_pitch`
+// elements apart; out16 (same format) and/or out32 (fp32), either may be NULL.
+extern "C" int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16,
+                                float* out32, int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream) {
+  using namespace bfb;
+  BFB_REQUIRE(M >= 0 && N >= 1 && K >= 8, BFB200_ERR_INVALID_ARG, "bad GEMM shape (%lld, %d, %d)", (long long)M, N, K);
+  BFB_REQUIRE(fmt == 0 || fmt == 1, BFB200_ERR_INVALID_ARG, "fmt must be 0 (fp16) or 1 (bf16)");
+  BFB_REQUIRE(out16 != nullptr || out32 != nullptr, BFB200_ERR_INVALID_ARG, "no output requested");
+  if (M == 0) return BFB200_OK;
+  BFB_DEV(A); BFB_DEV(W);
+  BFB_DEV_OPT(bias); BFB_DEV_OPT(out16); BFB_DEV_OPT(out32);
+  return launch_gemm_tc(A, a_pitch, W, bias, out16, out32, M, N, K, relu, (uint32_t)fmt, (cudaStream_t)stream);
+}

@@ -147,6 +147,35 @@ def topk(scores: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
     return unpack_keys(topk_keys(scores, k))
 
 
+def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False,
+              out_dtype: torch.dtype | None = None, a_pitch: int | None = None, rows: int | None = None) -> torch.Tensor:
+    """`a @ w.T (+ bias) (ReLU)` on the tcgen05 tensor cores (bfb200_linear_tc).  a (M, K) and w (N, K) are fp16 or
+    bf16 CUDA tensors of the same dtype; the result is `out_dtype` (the operand dtype by default, or torch.float32).
+    `a_pitch` / `rows` address M = rows rows of K elements that are `a_pitch` elements apart starting at a's first
+    element (used to evaluate the vocabulary head on last positions only)."""
+    _require_cuda(a, "a")
+    if a.dtype not in (torch.float16, torch.bfloat16) or w.dtype != a.dtype:
+        raise TypeError("linear_tc takes fp16 or bf16 operands of one dtype")
+    w = w.contiguous()
+    N, K = w.shape
+    if a_pitch is None:
+        a = a.contiguous()
+        M, a_pitch = a.shape[0], K
+    else:
+        M = int(rows)
+    out_dtype = out_dtype or a.dtype
+    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    fmt = 0 if a.dtype == torch.float16 else 1
+    b = None if bias is None else _f32c(bias).to(a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.bfb200_linear_tc(a.data_ptr(), a_pitch, w.data_ptr(), _ptr(b),
+                                        out.data_ptr() if out_dtype != torch.float32 else None,
+                                        out.data_ptr() if out_dtype == torch.float32 else None,
+                                        M, N, K, int(relu), fmt, _stream_ptr(a.device)))
+    return out
+
+
 def step_mean(step_scores: torch.Tensor) -> torch.Tensor:
     """`torch.mean(uncertainties, dim=0)` of select_samples (reference active_learning.py:209): (N, B) -> (B,)."""
     _require_cuda(step_scores, "step_scores")

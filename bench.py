@@ -411,6 +411,20 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
     scores = torch.randn(1_000_000, device=dev)
     ms = timed(lambda: engine.topk_keys(scores, K_TOP))
     out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident, latency bound (3 launches)"}
+    # MC-batched tensor-core GEMMs at the scaled configuration's shapes (d = 512, F = 2048; one chunk of
+    # 256 sequences x 256 tokens = 65,536 token rows), against the measured dense bf16 matmul peak
+    tc_peak = peaks["bf16_tflops"]
+    R = 65536
+    for name, n, k_, relu in (("qkv", 1536, 512, False), ("w_out", 512, 512, False), ("ffn1", 2048, 512, True),
+                              ("ffn2", 512, 2048, False)):
+        a = (torch.randn(R, k_, device=dev) * 0.5).half()
+        w = (torch.randn(n, k_, device=dev) * 0.05).half()
+        b = torch.randn(n, device=dev)
+        ms = timed(lambda: engine.linear_tc(a, w, b, relu))
+        tf = 2.0 * R * n * k_ / (ms * 1e-3) / 1e12
+        out[f"gemm_tc[{name} {R}x{n}x{k_}]"] = {"ms": ms, "bound": "tensor", "achieved": tf, "peak": tc_peak,
+                                                 "unit": "TFLOP/s", "frac": tf / tc_peak, "peak_source": peak_src + " (burst)"}
+        del a, w
     # toy classifier, SURVEY C2i
     from bayesformer_b200.model.bayesian_classification import MLP
     torch.manual_seed(SEED)

@@ -249,6 +249,16 @@ int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc
 size_t bfb200_fused_image_bytes(const bfb200_transformer* model);
 int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream);
 
+/*
+ * MC-batched tensor-core linear layer, nn.Linear of src/model/transformer.py (:33-35, :100, :152-154, :336) over the
+ * token rows of a chunk: C[M, N] = A[M, K] W[N, K]^T (+ bias) (ReLU).  A and W are 16-bit [dev] matrices (fmt 0 =
+ * fp16, 1 = bf16), K contiguous, A rows `a_pitch` elements apart (a pitch of len * K with A offset to the last
+ * position evaluates the vocabulary head on last positions only).  out16 (same format) and/or out32 (fp32) receive
+ * the result; either may be NULL.  TMA-fed tcgen05 kernel, fp32 accumulation in TMEM.
+ */
+int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
+                     int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream);
+
 /* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
  * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */
 int bfb200_step_mean(const float* step_scores, int32_t n_steps, int64_t n_items, float* pool_scores,

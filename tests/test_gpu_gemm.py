@@ -1,0 +1,44 @@
+"""TMA-fed tcgen05 GEMM (bfb200_linear_tc) against torch on the same 16-bit operands (fp32 accumulation)."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,relu,bias", [(1000, 1536, 512, False, False), (129, 114, 512, False, True),
+                                             (4096, 2048, 512, True, True), (4096, 512, 2048, False, True),
+                                             (1, 8, 64, False, True), (300, 200, 72, True, False),
+                                             (20000, 512, 512, False, False)])
+def test_linear_tc_matches_torch(dtype, M, N, K, relu, bias):
+    from bayesformer_b200 import engine
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev, dtype)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(dev, dtype)
+    b = torch.randn(N, generator=g).to(dev) if bias else None
+    want = a.float() @ w.float().t()
+    if bias:
+        want = want + b
+    if relu:
+        want = torch.relu(want)
+    got32 = engine.linear_tc(a, w, b, relu, out_dtype=torch.float32)
+    torch.testing.assert_close(got32, want, rtol=1e-4, atol=1e-3)
+    got16 = engine.linear_tc(a, w, b, relu)
+    torch.testing.assert_close(got16.float(), want.to(dtype).float(), rtol=2e-2 if dtype == torch.bfloat16 else 2e-3,
+                               atol=2e-2 if dtype == torch.bfloat16 else 2e-3)
+
+
+def test_linear_tc_strided_rows_pick_last_positions():
+    from bayesformer_b200 import engine
+
+    dev = torch.device("cuda:0")
+    S, L, K, N = 37, 16, 512, 114
+    x = torch.randn(S, L, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) * 0.05).half()
+    last = x[:, -1, :].contiguous()
+    want = last.float() @ w.float().t()
+    got = engine.linear_tc(x.view(-1)[(L - 1) * K:], w, out_dtype=torch.float32, a_pitch=L * K, rows=S)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-3)
