@@ -8,8 +8,10 @@
 //   warp 1      one lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN, K = 16 x 4 per stage) into one of
 //               two TMEM accumulator stages; tcgen05.commit releases the ring slot (`empty`) and, after the last
 //               K block, hands the accumulator to the epilogue (`acc_full`);
-//   warps 2-5   epilogue: thread = accumulator row; tcgen05.ld 32 columns at a time, + bias, ReLU, convert, 16-byte
-//               global stores (16-bit and/or fp32 outputs), then `acc_empty` so the MMA warp can reuse the stage.
+//   warps 2-5   epilogue: thread = accumulator row; tcgen05.ld 32 columns at a time, + bias (staged in shared memory),
+//               ReLU, convert, write a 32-row x 128-byte slab into swizzled shared memory and hand it to a 2-D TMA
+//               store (cp.async.bulk.tensor ... global.shared::cta), double-buffered per warp, so every global
+//               write is a full 128-byte line and M / N tails are clipped by the copy engine; then `acc_empty`.
 // Operands are 16-bit (fp16 or bf16, instruction-descriptor format bit), accumulation fp32.  M / N / K tails are
 // zero-filled by TMA and masked in the epilogue.  Tiles are walked N-fastest so an A row block stays in L2 while
 // all of its N tiles are produced.
@@ -25,7 +27,7 @@ namespace {
 
 constexpr int GM = 128;       // tile rows (UMMA M)
 constexpr int GK = 64;        // K per stage: one 128-byte swizzle row of 16-bit elements
-constexpr int GSTAGES = 4;
+constexpr int GSTAGES_MAX = 4;
 constexpr int GACC = 2;       // TMEM accumulator stages
 constexpr int GTHREADS = 192;
 
@@ -34,6 +36,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(umma::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(umma::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
@@ -50,15 +63,20 @@ struct GemmArgs {
   int64_t ldc;             // output row pitch in elements (= N)
 };
 
-template <int BN>
+template <int BN, int GSTAGES>
 __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_w,
+                                                              const __grid_constant__ CUtensorMap map_c16,
+                                                              const __grid_constant__ CUtensorMap map_c32,
                                                               const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t A_BYTES = GM * GK * 2, W_BYTES = BN * GK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  constexpr uint32_t SLAB_BYTES = 32 * 128;   // 32 rows x 128 bytes, one TMA-store box
+  uint8_t* slabs = smem + GSTAGES * STAGE_BYTES;            // 4 epilogue warps x 2 slabs
   __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
   __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[GACC][BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles_m = (g.M + GM - 1) / GM;
@@ -129,64 +147,83 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ===== epilogue: warps 2..5 -> TMEM lane quarters 2, 3, 0, 1 =====
     const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;   // 0..127 over the epilogue warps
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t tcount = 0;
+    uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * 2u * SLAB_BYTES;
+    uint32_t tcount = 0, slab_i = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int64_t mb = tile / tiles_n;
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+      // bias of this tile's columns -> shared memory (the stage's previous user finished two tiles ago)
+      for (int i = et; i < BN; i += 128) {
+        const int n = nb * BN + i;
+        bias_s[as][i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
       umma::mbar_wait(&acc_full[as], aph);
       umma::tc_fence_after_sync();
-      const int64_t row = mb * GM + q * 32 + lane;
-      const bool row_ok = row < g.M;
+      const int row0 = (int)(mb * GM) + q * 32;         // first row of this warp's slab
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = nb * BN + c0;
+        if (n0 >= g.N) break;   // warp-uniform: the remaining columns are outside the matrix
         uint32_t r[32];
         umma::tmem_ld32(tmem_base + lane_base + as * BN + c0, r);
         umma::tmem_ld_wait();
-        const int n0 = nb * BN + c0;
-        if (n0 >= g.N) continue;   // warp-uniform
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]);
-          if (g.bias != nullptr && n0 + i < g.N) x += __ldg(g.bias + n0 + i);
+          float x = __uint_as_float(r[i]) + bias_s[as][c0 + i];
           if (g.relu) x = fmaxf(x, 0.f);
           v[i] = x;
         }
-        if (row_ok) {
-          const bool full = n0 + 32 <= g.N && (g.ldc & 7) == 0;
-          if (g.out32 != nullptr) {
-            float* dst = g.out32 + row * g.ldc + n0;
-            if (full) {
+        if (g.out32 != nullptr) {
+          uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
+          tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
+          __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              for (int i = 0; i < 32 && n0 + i < g.N; ++i) dst[i] = v[i];
-            }
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(slab + umma::sw128_offset(lane, c)) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          umma::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c32, slab, n0, row0);
+            tma_store_commit();
           }
-          if (g.out16 != nullptr) {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(g.out16) + row * g.ldc + n0;
-            if (full) {
+          ++slab_i;
+        }
+        if (g.out16 != nullptr) {
+          // two 32-column chunks share one 128-byte slab row: even chunk -> bytes [0, 64), odd chunk -> [64, 128)
+          uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
+          const int half = (c0 >> 5) & 1;
+          if (half == 0) {
+            tma_store_wait_read<1>();
+            __syncwarp();
+          }
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 w;
-                if (g.fmt == umma::kFmtF16) {
-                  w.x = umma::pack_f16x2(v[i], v[i + 1]); w.y = umma::pack_f16x2(v[i + 2], v[i + 3]);
-                  w.z = umma::pack_f16x2(v[i + 4], v[i + 5]); w.w = umma::pack_f16x2(v[i + 6], v[i + 7]);
-                } else {
-                  w.x = umma::pack_bf16x2(v[i], v[i + 1]); w.y = umma::pack_bf16x2(v[i + 2], v[i + 3]);
-                  w.z = umma::pack_bf16x2(v[i + 4], v[i + 5]); w.w = umma::pack_bf16x2(v[i + 6], v[i + 7]);
-                }
-                *reinterpret_cast<uint4*>(dst + i) = w;
-              }
+          for (int c = 0; c < 4; ++c) {
+            uint4 w;
+            const int i = 8 * c;
+            if (g.fmt == umma::kFmtF16) {
+              w.x = umma::pack_f16x2(v[i], v[i + 1]); w.y = umma::pack_f16x2(v[i + 2], v[i + 3]);
+              w.z = umma::pack_f16x2(v[i + 4], v[i + 5]); w.w = umma::pack_f16x2(v[i + 6], v[i + 7]);
             } else {
-              for (int i = 0; i < 32 && n0 + i < g.N; ++i) {
-                const uint32_t w = g.fmt == umma::kFmtF16 ? umma::pack_f16x2(v[i], 0.f) : umma::pack_bf16x2(v[i], 0.f);
-                dst[i] = (uint16_t)(w & 0xFFFFu);
-              }
+              w.x = umma::pack_bf16x2(v[i], v[i + 1]); w.y = umma::pack_bf16x2(v[i + 2], v[i + 3]);
+              w.z = umma::pack_bf16x2(v[i + 4], v[i + 5]); w.w = umma::pack_bf16x2(v[i + 6], v[i + 7]);
             }
+            *reinterpret_cast<uint4*>(slab + umma::sw128_offset(lane, 4 * half + c)) = w;
+          }
+          const bool last_chunk = half == 1 || n0 + 32 >= g.N || c0 + 32 >= BN;
+          if (last_chunk) {
+            umma::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c16, slab, n0 - 32 * half, row0);
+              tma_store_commit();
+            }
+            ++slab_i;
           }
         }
       }
@@ -194,6 +231,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    tma_store_wait_read<0>();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
   }
 
   umma::tc_fence_before_sync();
@@ -220,15 +259,19 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2-D map over a (rows, K) 16-bit matrix with row pitch `pitch_elems`; box = 64 x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t pitch_elems, int box_rows, uint32_t fmt) {
+// 2-D map over a (rows, cols) matrix of 16-bit (elem_bytes 2) or fp32 (4) elements with row pitch `pitch_elems`;
+// box = (128 bytes of columns) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t pitch_elems, int box_rows, uint32_t fmt,
+             int elem_bytes = 2) {
   EncodeTiledFn fn = encode_tiled_fn();
   BFB_REQUIRE(fn != nullptr, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, fmt == umma::kFmtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : fmt == umma::kFmtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = fn(map, dt, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BFB_REQUIRE(r == CUDA_SUCCESS, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for rows=%lld K=%d pitch=%lld",
@@ -238,19 +281,31 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t pi
 
 }  // namespace
 
-int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32, int64_t M,
-                   int N, int K, int relu, uint32_t fmt, cudaStream_t st) {
+int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
+                   int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, cudaStream_t st) {
   if (M == 0 || N == 0) return BFB200_OK;
   BFB_REQUIRE((K & 7) == 0 && (a_pitch & 7) == 0, BFB200_ERR_UNSUPPORTED,
               "tensor-core GEMM needs K (%d) and the A row pitch (%lld) to be multiples of 8", K, (long long)a_pitch);
   BFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0,
               BFB200_ERR_INVALID_ARG, "GEMM operands must be 16-byte aligned");
+  BFB_REQUIRE(ldc >= N, BFB200_ERR_INVALID_ARG, "output pitch %lld < N = %d", (long long)ldc, N);
+  BFB_REQUIRE(out16 == nullptr || ((ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 15u) == 0),
+              BFB200_ERR_UNSUPPORTED, "16-bit GEMM output needs a row pitch (%lld) that is a multiple of 8 elements and a "
+              "16-byte aligned buffer", (long long)ldc);
+  BFB_REQUIRE(out32 == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(out32) & 15u) == 0),
+              BFB200_ERR_UNSUPPORTED, "fp32 GEMM output needs a row pitch (%lld) that is a multiple of 4 elements and a "
+              "16-byte aligned buffer", (long long)ldc);
   const int BN = N > 128 ? 256 : 128;
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_c16, map_c32;
   BFB_CALL(make_map(&map_a, A, M, K, a_pitch, GM, fmt));
   BFB_CALL(make_map(&map_w, W, N, K, K, BN, fmt));
+  // outputs: 32-row x 128-byte store boxes; an absent output reuses the other's map (never dereferenced)
+  if (out16 != nullptr) BFB_CALL(make_map(&map_c16, out16, M, N, ldc, 32, fmt, 2));
+  if (out32 != nullptr) BFB_CALL(make_map(&map_c32, out32, M, N, ldc, 32, fmt, 4));
+  if (out16 == nullptr) map_c16 = map_c32;
+  if (out32 == nullptr) map_c32 = map_c16;
   GemmArgs g;
-  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = N;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = ldc;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -260,13 +315,14 @@ int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* b
   }
   const int64_t n_tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  const size_t smem = 1024 + (size_t)GSTAGES * (GM * GK * 2 + BN * GK * 2);
+  const int stages = BN == 256 ? 3 : 4;
+  const size_t smem = 1024 + (size_t)stages * (GM * GK * 2 + BN * GK * 2) + 8 * 32 * 128;
   if (BN == 256) {
-    cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_tc_kernel<256><<<grid, GTHREADS, smem, st>>>(map_a, map_w, g);
+    cudaFuncSetAttribute(gemm_tc_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_tc_kernel<256, 3><<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, g);
   } else {
-    cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_tc_kernel<128><<<grid, GTHREADS, smem, st>>>(map_a, map_w, g);
+    cudaFuncSetAttribute(gemm_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_tc_kernel<128, 4><<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, g);
   }
   BFB_LAUNCH_CHECK("gemm_tc_kernel", st);
   return BFB200_OK;
@@ -275,9 +331,10 @@ int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* b
 }  // namespace bfb
 
 // C[M, N] = A[M, K] W[N, K]^T (+ bias)(ReLU); A, W 16-bit (fmt 0 = fp16, 1 = bf16) device pointers, A rows `a_pitch`
-// elements apart; out16 (same format) and/or out32 (fp32), either may be NULL.
+// elements apart; out16 (same format) and/or out32 (fp32) with row pitch `ldc` elements, either may be NULL.
 extern "C" int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16,
-                                float* out32, int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream) {
+                                float* out32, int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt,
+                                void* stream) {
   using namespace bfb;
   BFB_REQUIRE(M >= 0 && N >= 1 && K >= 8, BFB200_ERR_INVALID_ARG, "bad GEMM shape (%lld, %d, %d)", (long long)M, N, K);
   BFB_REQUIRE(fmt == 0 || fmt == 1, BFB200_ERR_INVALID_ARG, "fmt must be 0 (fp16) or 1 (bf16)");
@@ -285,5 +342,5 @@ extern "C" int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, c
   if (M == 0) return BFB200_OK;
   BFB_DEV(A); BFB_DEV(W);
   BFB_DEV_OPT(bias); BFB_DEV_OPT(out16); BFB_DEV_OPT(out32);
-  return launch_gemm_tc(A, a_pitch, W, bias, out16, out32, M, N, K, relu, (uint32_t)fmt, (cudaStream_t)stream);
+  return launch_gemm_tc(A, a_pitch, W, bias, out16, out32, ldc, M, N, K, relu, (uint32_t)fmt, (cudaStream_t)stream);
 }

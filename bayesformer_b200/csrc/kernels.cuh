@@ -37,7 +37,7 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
 
 
 // TMA-fed tcgen05 GEMM (gemm_tc.cu): C = A W^T (+ bias)(ReLU), 16-bit operands (fmt: umma::kFmtF16 / kFmtBF16)
-int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32, int64_t M,
-                   int N, int K, int relu, uint32_t fmt, cudaStream_t st);
+int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
+                   int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, cudaStream_t st);
 
 }  // namespace bfb

@@ -164,7 +164,9 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None
     else:
         M = int(rows)
     out_dtype = out_dtype or a.dtype
-    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    align = 4 if out_dtype == torch.float32 else 8          # output rows leave through TMA: pitch * size % 16 == 0
+    ldc = (N + align - 1) // align * align
+    out = torch.empty(M, ldc, dtype=out_dtype, device=a.device)
     fmt = 0 if a.dtype == torch.float16 else 1
     b = None if bias is None else _f32c(bias).to(a.device)
     lib = _lib.load()
@@ -172,8 +174,8 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None
         _lib.check(lib.bfb200_linear_tc(a.data_ptr(), a_pitch, w.data_ptr(), _ptr(b),
                                         out.data_ptr() if out_dtype != torch.float32 else None,
                                         out.data_ptr() if out_dtype == torch.float32 else None,
-                                        M, N, K, int(relu), fmt, _stream_ptr(a.device)))
-    return out
+                                        ldc, M, N, K, int(relu), fmt, _stream_ptr(a.device)))
+    return out if ldc == N else out[:, :N]
 
 
 def step_mean(step_scores: torch.Tensor) -> torch.Tensor:

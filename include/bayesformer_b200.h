@@ -254,10 +254,11 @@ int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image
  * token rows of a chunk: C[M, N] = A[M, K] W[N, K]^T (+ bias) (ReLU).  A and W are 16-bit [dev] matrices (fmt 0 =
  * fp16, 1 = bf16), K contiguous, A rows `a_pitch` elements apart (a pitch of len * K with A offset to the last
  * position evaluates the vocabulary head on last positions only).  out16 (same format) and/or out32 (fp32) receive
- * the result; either may be NULL.  TMA-fed tcgen05 kernel, fp32 accumulation in TMEM.
+ * the result with a row pitch of `ldc` >= N elements (ldc * element size a multiple of 16 bytes: results leave the
+ * chip through 2-D TMA stores); either may be NULL.  TMA-fed tcgen05 kernel, fp32 accumulation in TMEM.
  */
 int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
-                     int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream);
+                     int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream);
 
 /* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
  * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */
