@@ -120,6 +120,7 @@ _SIGNATURES = {
     "bfb200_fused_pack": (C.c_int, [C.POINTER(Transformer), _P, C.c_size_t, _P]),
     "bfb200_linear_tc": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
+    "bfb200_attention_tc": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bfb200_step_mean": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "bfb200_launch_count": (C.c_int64, []),
     "bfb200_reset_launch_count": (None, []),

@@ -1,0 +1,290 @@
+// Fused causal attention for heads of width 64 on tcgen05 tensor cores (the scaled configuration: d_model 512,
+// 8 heads, sequences of up to 256 tokens).  Reference arithmetic: src/model/transformer.py:58-65 (per head:
+// softmax(Q K^T / sqrt(dh) + causal mask) V) and :116-124 (optional head-output dropout, concatenation).
+//
+// One CTA (128 threads) per (sequence, head, tile of 128 queries):
+//   1. one thread issues 2-D TMA loads (128-byte swizzle) of the Q tile and of the K rows this tile can attend to,
+//      straight out of the packed (R, 3d) QKV activation; meanwhile all threads read the V rows and write them
+//      TRANSPOSED (dims x keys, K-major) into shared memory, the layout tcgen05.mma wants for the B operand of P V;
+//   2. S = Q K^T: tcgen05.mma M = 128, N = keys (<= 256), K = 64, fp32 accumulator in 256 TMEM columns;
+//   3. softmax, thread = query row: two passes over the row with tcgen05.ld (max, then exp / sum with the causal
+//      mask), the un-normalised probabilities go to shared memory as the 16-bit A operand (swizzled K-major slabs);
+//   4. O = P V: tcgen05.mma M = 128, N = 64, K = keys into 64 more TMEM columns;
+//   5. epilogue: O row / row sum (+ head-output dropout), converted, one 128-byte line per query row to HBM.
+// Q, K, V, P are 16-bit (fp16 or bf16); scores, softmax statistics and both accumulators are fp32.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace bfb {
+
+namespace {
+
+constexpr int AT_DH = 64;
+constexpr int AT_M = 128;        // queries per CTA
+constexpr int AT_MAXKV = 256;    // keys per CTA
+constexpr uint32_t AT_Q_BYTES = AT_M * 128;
+constexpr uint32_t AT_K_BYTES = AT_MAXKV * 128;
+constexpr uint32_t AT_VT_BYTES = (AT_MAXKV / 64) * 64 * 128;   // 4 slabs of 64 dims x 64 keys
+constexpr uint32_t AT_P_BYTES = (AT_MAXKV / 64) * AT_M * 128;  // 4 slabs of 128 rows x 64 keys
+
+__device__ __forceinline__ void at_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(umma::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+struct AttnArgs {
+  const uint16_t* qkv;   // (R, 3d)
+  uint16_t* out;         // (R, d)
+  int64_t n_rows;        // R = n_seq * len
+  int len, d, n_heads, m_tiles;
+  uint32_t fmt;
+  float inv_sqrt_dh;
+  int site;              // head-output dropout site or -1
+  MaskSource ms;
+};
+
+__device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
+  return fmt == umma::kFmtF16 ? umma::pack_f16x2(a, b) : umma::pack_bf16x2(a, b);
+}
+
+__global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                               const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_Q_BYTES;
+  uint8_t* sVT = sK + AT_K_BYTES;
+  uint8_t* sP = sVT + AT_VT_BYTES;
+  __shared__ uint64_t bar_qk, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.x % a.m_tiles;
+  const int h = (blockIdx.x / a.m_tiles) % a.n_heads;
+  const int64_t s = blockIdx.x / (a.m_tiles * a.n_heads);
+  const int m0 = mt * AT_M;
+  const int kv_len = min(a.len, m0 + AT_M);
+  const int kvp = (kv_len + 15) & ~15;
+  const int64_t row_base = s * a.len;
+
+  if (warp == 0) {
+    umma::tmem_alloc(&tmem_slot, 512);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar_qk, 1);
+    umma::mbar_init(&bar_s, 1);
+    umma::mbar_init(&bar_o, 1);
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (tid == 0) {
+    const int k_boxes = (kvp + AT_M - 1) / AT_M;
+    umma::mbar_expect_tx(&bar_qk, AT_Q_BYTES + (uint32_t)k_boxes * AT_M * 128u);
+    at_tma_load_2d(sQ, &map_qkv, h * AT_DH, (int)(row_base + m0), &bar_qk);
+    for (int b = 0; b < k_boxes; ++b)
+      at_tma_load_2d(sK + b * AT_M * 128, &map_qkv, a.d + h * AT_DH, (int)(row_base + b * AT_M), &bar_qk);
+  }
+  // V rows -> V^T (dims x keys) in the swizzled K-major slab layout; rows past the activation end are zeros
+  for (int j = tid; j < kvp; j += AT_M) {
+    const int64_t r = row_base + j;
+    uint4 v[8];
+    if (r < a.n_rows) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.qkv + r * 3 * (int64_t)a.d + 2 * a.d + h * AT_DH);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = make_uint4(0, 0, 0, 0);
+    }
+    uint8_t* slab = sVT + (j >> 6) * (64 * 128);
+    const uint32_t kc = (uint32_t)(j & 63) >> 3, ko = (uint32_t)(j & 7) * 2u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t dim = (uint32_t)(8 * c + e);
+        const uint16_t val = (uint16_t)((w[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
+        *reinterpret_cast<uint16_t*>(slab + umma::sw128_offset(dim, kc) + ko) = val;
+      }
+    }
+  }
+  umma::fence_async_smem();
+  __syncthreads();
+
+  // ---- S = Q K^T ----
+  if (tid == 0) {
+    umma::mbar_wait(&bar_qk, 0);
+    umma::tc_fence_after_sync();
+    const uint64_t dq = umma::smem_desc_sw128(umma::smem_u32(sQ)), dk = umma::smem_desc_sw128(umma::smem_u32(sK));
+    const uint32_t idesc = umma::instr_desc_16bit(AT_M, kvp, a.fmt);
+#pragma unroll
+    for (int k = 0; k < AT_DH / 16; ++k) umma::mma_bf16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
+    umma::mma_commit(&bar_s);
+  }
+  umma::mbar_wait(&bar_s, 0);
+  umma::tc_fence_after_sync();
+
+  // ---- softmax over the keys j <= query position, thread = query row ----
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int tq = m0 + tid;                       // query position inside the sequence
+  const bool q_ok = tq < a.len;
+  const int last_key = q_ok ? tq : -1;           // causal mask (generate_subsequent_mask, transformer.py:275-287)
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < kvp; c0 += 32) {
+    uint32_t r[32];
+    umma::tmem_ld32(tmem_base + lane_base + c0, r);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i <= last_key) mx = fmaxf(mx, __uint_as_float(r[i]));
+  }
+  float sum = 0.f;
+  for (int c0 = 0; c0 < kvp; c0 += 32) {
+    uint32_t r[32];
+    umma::tmem_ld32(tmem_base + lane_base + c0, r);
+    umma::tmem_ld_wait();
+    float e[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      e[i] = (c0 + i <= last_key) ? __expf((__uint_as_float(r[i]) - mx) * a.inv_sqrt_dh) : 0.f;
+      sum += e[i];
+    }
+    uint8_t* slab = sP + (c0 >> 6) * (AT_M * 128);
+    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 w;
+      w.x = at_pack2(e[8 * c], e[8 * c + 1], a.fmt); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], a.fmt);
+      w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], a.fmt); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], a.fmt);
+      *reinterpret_cast<uint4*>(slab + umma::sw128_offset(tid, ch0 + c)) = w;
+    }
+  }
+  umma::fence_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+
+  // ---- O = P V ----
+  if (tid == 0) {
+    umma::tc_fence_after_sync();
+    const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, a.fmt);
+    const uint32_t pP = umma::smem_u32(sP), pV = umma::smem_u32(sVT);
+    for (int ks = 0; ks < kvp / 16; ++ks) {
+      const uint64_t dp = umma::smem_desc_sw128(pP + (ks >> 2) * (AT_M * 128) + (ks & 3) * 32);
+      const uint64_t dv = umma::smem_desc_sw128(pV + (ks >> 2) * (64 * 128) + (ks & 3) * 32);
+      umma::mma_bf16_ss(tmem_base + 256, dp, dv, idesc, ks > 0);
+    }
+    umma::mma_commit(&bar_o);
+  }
+  umma::mbar_wait(&bar_o, 0);
+  umma::tc_fence_after_sync();
+
+  // ---- epilogue ----
+  {
+    uint32_t r0[32], r1[32];
+    umma::tmem_ld32(tmem_base + lane_base + 256, r0);
+    umma::tmem_ld32(tmem_base + lane_base + 288, r1);
+    umma::tmem_ld_wait();
+    if (q_ok) {
+      const float inv = 1.0f / sum;
+      float o[AT_DH];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        o[i] = __uint_as_float(r0[i]) * inv;
+        o[32 + i] = __uint_as_float(r1[i]) * inv;
+      }
+      if (a.site >= 0) {   // transformer.py:116-122
+#pragma unroll
+        for (int f4 = 0; f4 < AT_DH / 4; ++f4) {
+          const uint32_t keep = keep4(a.ms, s, (uint32_t)tq, (uint32_t)a.site, (uint32_t)(h * (AT_DH / 4) + f4));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[4 * f4 + q] = ((keep >> q) & 1u) ? o[4 * f4 + q] * a.ms.scale : 0.f;
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(a.out + (row_base + tq) * (int64_t)a.d + h * AT_DH);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 w;
+        w.x = at_pack2(o[8 * c], o[8 * c + 1], a.fmt); w.y = at_pack2(o[8 * c + 2], o[8 * c + 3], a.fmt);
+        w.z = at_pack2(o[8 * c + 4], o[8 * c + 5], a.fmt); w.w = at_pack2(o[8 * c + 6], o[8 * c + 7], a.fmt);
+        dst[c] = w;
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*AtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, int d, int n_heads, uint32_t fmt,
+                        const MaskSource& ms, int site, cudaStream_t st) {
+  if (n_seq == 0) return BFB200_OK;
+  BFB_REQUIRE(d == n_heads * AT_DH, BFB200_ERR_UNSUPPORTED, "tensor-core attention needs heads of width 64 (d=%d, H=%d)", d,
+              n_heads);
+  BFB_REQUIRE(len >= 1 && len <= AT_MAXKV, BFB200_ERR_UNSUPPORTED, "tensor-core attention takes sequences of 1..%d tokens (got %d)",
+              AT_MAXKV, len);
+  static AtEncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<AtEncodeTiledFn>(p);
+  }
+  BFB_REQUIRE(fn != nullptr, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const int64_t R = n_seq * len;
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {(cuuint64_t)(3 * d), (cuuint64_t)R};
+  const cuuint64_t strides[1] = {(cuuint64_t)(3 * d) * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)AT_DH, (cuuint32_t)AT_M};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(&map, fmt == umma::kFmtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(qkv16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BFB_REQUIRE(r == CUDA_SUCCESS, BFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the QKV activation", (int)r);
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = (const uint16_t*)qkv16; a.out = (uint16_t*)out16; a.n_rows = R;
+  a.len = len; a.d = d; a.n_heads = n_heads; a.m_tiles = (len + AT_M - 1) / AT_M;
+  a.fmt = fmt; a.inv_sqrt_dh = 1.0f / sqrtf((float)AT_DH); a.site = site; a.ms = ms;
+  const int64_t grid = n_seq * n_heads * a.m_tiles;
+  BFB_REQUIRE(grid <= 0x7FFFFFFF, BFB200_ERR_UNSUPPORTED, "too many attention tiles in one launch");
+  const size_t smem = 1024 + AT_Q_BYTES + AT_K_BYTES + AT_VT_BYTES + AT_P_BYTES;
+  cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  attention_tc_kernel<<<(unsigned)grid, AT_M, smem, st>>>(map, a);
+  BFB_LAUNCH_CHECK("attention_tc_kernel", st);
+  return BFB200_OK;
+}
+
+}  // namespace bfb
+
+// causal multi-head attention on a packed 16-bit QKV activation: qkv (n_seq * len, 3 d) -> out (n_seq * len, d);
+// fmt 0 = fp16, 1 = bf16; heads of width 64, len <= 256.
+extern "C" int bfb200_attention_tc(const void* qkv, void* out, int64_t n_seq, int32_t len, int32_t d_model, int32_t n_heads,
+                                   int32_t fmt, void* stream) {
+  using namespace bfb;
+  BFB_REQUIRE(n_seq >= 0 && len >= 1 && d_model >= 1 && n_heads >= 1, BFB200_ERR_INVALID_ARG, "bad attention shape");
+  BFB_REQUIRE(fmt == 0 || fmt == 1, BFB200_ERR_INVALID_ARG, "fmt must be 0 (fp16) or 1 (bf16)");
+  if (n_seq == 0) return BFB200_OK;
+  BFB_DEV(qkv); BFB_DEV(out);
+  MaskSource ms;
+  memset(&ms, 0, sizeof(ms));
+  ms.n_draws = 1;
+  return launch_attention_tc(qkv, out, n_seq, len, d_model, n_heads, (uint32_t)fmt, ms, -1, (cudaStream_t)stream);
+}

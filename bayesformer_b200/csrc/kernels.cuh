@@ -40,4 +40,9 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
 int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
                    int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, cudaStream_t st);
 
+
+// tcgen05 causal attention for heads of width 64 (attention_tc.cu): qkv16 (R, 3d) -> out16 (R, d)
+int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, int d, int n_heads, uint32_t fmt,
+                        const MaskSource& ms, int site, cudaStream_t st);
+
 }  // namespace bfb

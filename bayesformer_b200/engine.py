@@ -178,6 +178,22 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None
     return out if ldc == N else out[:, :N]
 
 
+def attention_tc(qkv: torch.Tensor, n_seq: int, length: int, n_heads: int) -> torch.Tensor:
+    """Causal multi-head attention on the tcgen05 tensor cores (bfb200_attention_tc): qkv (n_seq * length, 3 d) fp16 or
+    bf16 with columns [Q | K | V] -> (n_seq * length, d).  Heads of width 64, length <= 256."""
+    _require_cuda(qkv, "qkv")
+    if qkv.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("attention_tc takes fp16 or bf16")
+    qkv = qkv.contiguous()
+    d = qkv.shape[1] // 3
+    out = torch.empty(qkv.shape[0], d, dtype=qkv.dtype, device=qkv.device)
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.bfb200_attention_tc(qkv.data_ptr(), out.data_ptr(), n_seq, length, d, n_heads,
+                                           0 if qkv.dtype == torch.float16 else 1, _stream_ptr(qkv.device)))
+    return out
+
+
 def step_mean(step_scores: torch.Tensor) -> torch.Tensor:
     """`torch.mean(uncertainties, dim=0)` of select_samples (reference active_learning.py:209): (N, B) -> (B,)."""
     _require_cuda(step_scores, "step_scores")

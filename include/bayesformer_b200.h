@@ -260,6 +260,14 @@ int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image
 int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
                      int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t relu, int32_t fmt, void* stream);
 
+/*
+ * Causal multi-head attention of src/model/transformer.py:58-65, :123-124 on tcgen05 tensor cores, for heads of
+ * width 64 and sequences of at most 256 tokens: qkv (n_seq * len, 3 * d_model) 16-bit [dev] with columns
+ * [Q heads | K heads | V heads] -> out (n_seq * len, d_model) 16-bit [dev] (heads concatenated).  fmt 0 = fp16, 1 = bf16.
+ */
+int bfb200_attention_tc(const void* qkv, void* out, int64_t n_seq, int32_t len, int32_t d_model, int32_t n_heads,
+                        int32_t fmt, void* stream);
+
 /* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
  * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */
 int bfb200_step_mean(const float* step_scores, int32_t n_steps, int64_t n_items, float* pool_scores,

@@ -42,3 +42,27 @@ def test_linear_tc_strided_rows_pick_last_positions():
     want = last.float() @ w.float().t()
     got = engine.linear_tc(x.view(-1)[(L - 1) * K:], w, out_dtype=torch.float32, a_pitch=L * K, rows=S)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_seq,length,heads", [(3, 256, 8), (2, 200, 8), (5, 128, 2), (4, 40, 2), (7, 7, 1), (1, 129, 4),
+                                                (2, 16, 8), (3, 1, 2)])
+def test_attention_tc_matches_torch(dtype, n_seq, length, heads):
+    """Fused causal attention (tcgen05 QK^T and PV) against the reference formula (transformer.py:58-65) evaluated in
+    fp32 on the same 16-bit Q, K, V."""
+    import math
+
+    from bayesformer_b200 import engine
+
+    dev = torch.device("cuda:0")
+    d = heads * 64
+    g = torch.Generator().manual_seed(n_seq * 1000 + length)
+    qkv = (torch.randn(n_seq * length, 3 * d, generator=g) * 0.7).to(dev, dtype)
+    got = engine.attention_tc(qkv, n_seq, length, heads).float()
+    x = qkv.float().view(n_seq, length, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))            # (S, H, L, 64)
+    scores = q @ k.transpose(-1, -2) / math.sqrt(64)
+    scores = scores + torch.triu(torch.full((length, length), float("-inf"), device=dev), diagonal=1)
+    want = (torch.softmax(scores, -1) @ v).permute(0, 2, 1, 3).reshape(n_seq * length, d)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    torch.testing.assert_close(got, want, rtol=tol, atol=tol)
