@@ -11,13 +11,13 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID_ARG, ERR_NOT_DEVICE_PTR, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 
 MODE = {"max": 0, "margin": 1, "entropy": 2}
 SCHEME = {"greedy": 0, "sampling": 1, "dropout": 2}
-COMPUTE = {"fp32": 0, "fp16": 1}
+COMPUTE = {"fp32": 0, "fp16": 1, "bf16": 2}
 
 SITE_EMBED = 1 << 0
 SITE_LAYER_OUT = 1 << 1
@@ -117,6 +117,7 @@ _SIGNATURES = {
     "bfb200_mc_workspace_bytes": (C.c_size_t, [C.POINTER(Transformer), C.POINTER(McArgs), C.c_int64]),
     "bfb200_mc_score_transformer": (C.c_int, [C.POINTER(Transformer), C.POINTER(McArgs), _P, C.c_size_t, _P]),
     "bfb200_fused_image_bytes": (C.c_size_t, [C.POINTER(Transformer)]),
+    "bfb200_compute_path": (C.c_int, [C.POINTER(Transformer)]),
     "bfb200_fused_pack": (C.c_int, [C.POINTER(Transformer), _P, C.c_size_t, _P]),
     "bfb200_linear_tc": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),

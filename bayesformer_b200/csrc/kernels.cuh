@@ -8,19 +8,22 @@ int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t it
                        int n_draws, int prompt_len, int stride, int vocab, int32_t* tokens,
                        cudaStream_t st);
 int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const float* pe, int64_t n_seq,
-                 int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st);
+                 int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st, void* x16 = nullptr,
+                 uint32_t fmt = 0);
 int launch_sgemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
                  int64_t a_row_mul, int64_t a_row_off, int relu, cudaStream_t st);
 int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d, int n_heads,
                      const MaskSource& ms, int site, cudaStream_t st);
 int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,
                     const float* gamma, const float* beta, float eps, const MaskSource& ms,
-                    int branch_site, int out_site, cudaStream_t st);
+                    int branch_site, int out_site, cudaStream_t st, void* out16 = nullptr, uint32_t fmt = 0);
 int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme, int mode,
                       float temperature, const MaskSource& ms, const int32_t* forced, int32_t* tokens,
-                      int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st);
+                      int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st,
+                      int pitch = 0);
 int launch_logsoftmax_seqfirst(const float* logits, int64_t n_seq, int len, int vocab, float* out,
-                               cudaStream_t st);
+                               cudaStream_t st, int pitch = 0);
+int launch_to16(const float* src, void* dst, int64_t n, uint32_t fmt, cudaStream_t st);
 int launch_reduce_draws(const float* seq_scores, int64_t n_items_chunk, int n_draws, float* dst,
                         cudaStream_t st);
 int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, float* pool_scores,

@@ -892,17 +892,3 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
 }
 
 }  // namespace bfb
-
-extern "C" size_t bfb200_fused_image_bytes(const bfb200_transformer* model) {
-  return model == nullptr ? 0 : bfb::fused_image_bytes(*model);
-}
-
-extern "C" int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream) {
-  using namespace bfb;
-  BFB_REQUIRE(model != nullptr, BFB200_ERR_INVALID_ARG, "model is NULL");
-  BFB_DEV(image);
-  BFB_DEV(model->embedding); BFB_DEV(model->pe); BFB_DEV(model->head_w); BFB_DEV(model->head_b);
-  BFB_DEV(model->w_qkv); BFB_DEV(model->w_out); BFB_DEV(model->ln1_w); BFB_DEV(model->ln1_b); BFB_DEV(model->ff1_w);
-  BFB_DEV(model->ff1_b); BFB_DEV(model->ff2_w); BFB_DEV(model->ff2_b); BFB_DEV(model->ln2_w); BFB_DEV(model->ln2_b);
-  return fused_pack(*model, image, image_bytes, (cudaStream_t)stream);
-}

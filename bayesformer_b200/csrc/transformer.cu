@@ -3,6 +3,7 @@
 // Reference control flow: src/libs/active_learning.py:38-155 and :209; src/model/transformer.py:349-375.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace bfb {
 
@@ -16,18 +17,61 @@ struct Workspace {
   float* h;         // (R, F)
   float* logits;    // (S or R, V)
   float* seq_scores;  // (S)
+  // layered tensor-core path: 16-bit operand copies and a second residual buffer
+  uint16_t* x16;    // (R, d)
+  uint16_t* qkv16;  // (R, 3d)
+  uint16_t* att16;  // (R, d) attention output, then LayerNorm1 output
+  uint16_t* h16;    // (R, F)
+  float* x2;        // (R, d) next block input
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // bytes for n_seq sequences of at most max_len tokens; full_logits: logits for every row
-static bool use_fused(const bfb200_transformer& m) { return m.compute == BFB200_COMPUTE_F16; }
+// ---- which path serves a model ---------------------------------------------------------------
+//   fp32            : layered CUDA-core kernels, any shape
+//   f16, fused class: fused MC-forward kernel (mc_fused.cu)
+//   f16 / bf16 else : layered tensor-core path — TMA-fed tcgen05 GEMMs (gemm_tc.cu), tcgen05 attention
+//                     (attention_tc.cu), fp32 residual stream / LayerNorm; heads of width 64, len <= 256
+static bool use_fused(const bfb200_transformer& m) { return m.compute == BFB200_COMPUTE_F16 && fused_supported(m); }
+static bool tc_shape_ok(const bfb200_transformer& m) {
+  return m.n_layers >= 1 && m.d_model == m.n_heads * 64 && (m.d_ff & 7) == 0 && m.d_ff >= 8;
+}
+static bool use_tc(const bfb200_transformer& m) {
+  return (m.compute == BFB200_COMPUTE_F16 && !fused_supported(m)) || m.compute == BFB200_COMPUTE_BF16;
+}
+static uint32_t tc_fmt(const bfb200_transformer& m) {
+  return m.compute == BFB200_COMPUTE_BF16 ? umma::kFmtBF16 : umma::kFmtF16;
+}
+static int logits_pitch(const bfb200_transformer& m) { return use_tc(m) ? (m.ntoken + 3) & ~3 : m.ntoken; }
+
+// 16-bit weight image of the layered tensor-core path: [W_qkv | W_out | FFN W1 | FFN W2 | head], element offsets
+struct TcImage {
+  size_t qkv, out, ff1, ff2, head, elems;
+};
+static TcImage tc_image(const bfb200_transformer& m) {
+  const size_t L = m.n_layers, d = m.d_model, F = m.d_ff, V = m.ntoken;
+  TcImage t;
+  t.qkv = 0;
+  t.out = t.qkv + L * 3 * d * d;
+  t.ff1 = t.out + L * d * d;
+  t.ff2 = t.ff1 + L * F * d;
+  t.head = t.ff2 + L * d * F;
+  t.elems = t.head + V * d;
+  return t;
+}
 
 static size_t workspace_bytes(const bfb200_transformer& m, int64_t n_seq, int max_len, bool full_logits) {
   if (use_fused(m) && !full_logits)  // fused path: activations never leave the chip
     return 256 + align256((size_t)n_seq * max_len * sizeof(int32_t)) + align256((size_t)n_seq * sizeof(float));
   const size_t R = (size_t)n_seq * max_len;
   const size_t d = m.d_model, F = m.d_ff, V = m.ntoken;
+  if (use_tc(m)) {
+    const size_t Vp = (size_t)logits_pitch(m);
+    return 256 + align256((size_t)n_seq * max_len * sizeof(int32_t)) + 3 * align256(R * d * 4) +
+           2 * align256(R * d * 2) + align256(R * 3 * d * 2) + align256(R * F * 2) +
+           align256((full_logits ? R : (size_t)n_seq) * Vp * 4) + align256((size_t)n_seq * 4);
+  }
   size_t b = 256;
   b += align256((size_t)n_seq * max_len * sizeof(int32_t));
   b += 4 * align256(R * d * sizeof(float));
@@ -43,11 +87,26 @@ static Workspace carve(void* base, const bfb200_transformer& m, int64_t n_seq, i
   const size_t d = m.d_model, F = m.d_ff, V = m.ntoken;
   char* p = (char*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   Workspace w;
+  memset(&w, 0, sizeof(w));
   auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return q; };
   w.tokens = (int32_t*)take((size_t)n_seq * max_len * sizeof(int32_t));
   if (use_fused(m) && !full_logits) {
     w.seq_scores = (float*)take((size_t)n_seq * sizeof(float));
     w.x = w.att = w.y = w.x1 = w.qkv = w.h = w.logits = nullptr;
+    return w;
+  }
+  if (use_tc(m)) {
+    const size_t Vp = (size_t)logits_pitch(m);
+    w.x = (float*)take(R * d * 4);
+    w.x2 = (float*)take(R * d * 4);
+    w.y = (float*)take(R * d * 4);
+    w.x16 = (uint16_t*)take(R * d * 2);
+    w.att16 = (uint16_t*)take(R * d * 2);
+    w.qkv16 = (uint16_t*)take(R * 3 * d * 2);
+    w.h16 = (uint16_t*)take(R * F * 2);
+    w.logits = (float*)take((full_logits ? R : (size_t)n_seq) * Vp * 4);
+    w.seq_scores = (float*)take((size_t)n_seq * 4);
+    w.att = w.x1 = w.qkv = w.h = nullptr;
     return w;
   }
   w.x = (float*)take(R * d * sizeof(float));
@@ -68,12 +127,13 @@ static int validate_model(const bfb200_transformer* m) {
   BFB_REQUIRE(m->d_model % m->n_heads == 0, BFB200_ERR_INVALID_ARG, "d_model must be divisible by n_heads");
   BFB_REQUIRE((m->d_model & 3) == 0 && (m->d_ff & 3) == 0, BFB200_ERR_UNSUPPORTED,
               "d_model (%d) and dim_feedforward (%d) must be multiples of 4", m->d_model, m->d_ff);
-  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_F16,
+  BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_F16 || m->compute == BFB200_COMPUTE_BF16,
               BFB200_ERR_INVALID_ARG, "unknown compute type %d", m->compute);
-  if (m->compute == BFB200_COMPUTE_F16) {
-    BFB_REQUIRE(fused_supported(*m), BFB200_ERR_UNSUPPORTED,
-                "compute=f16 is served by the fused kernel only: d_model 64, 8 heads, F <= 64, V <= 128 "
-                "(got d=%d H=%d F=%d V=%d L=%d)", m->d_model, m->n_heads, m->d_ff, m->ntoken, m->n_layers);
+  if (m->compute != BFB200_COMPUTE_FP32) {
+    BFB_REQUIRE(use_fused(*m) || tc_shape_ok(*m), BFB200_ERR_UNSUPPORTED,
+                "16-bit tensor-core compute serves (a) f16: d_model 64, 8 heads, F <= 64, V <= 128 (fused kernel) and "
+                "(b) f16 / bf16: heads of width 64, F %% 8 == 0 (layered tensor-core path); got d=%d H=%d F=%d V=%d L=%d",
+                m->d_model, m->n_heads, m->d_ff, m->ntoken, m->n_layers);
     BFB_DEV(m->fused_image);
   }
   if (m->site_flags != 0)
@@ -137,9 +197,84 @@ static int forward_chunk(const bfb200_transformer& m, Workspace& ws, int64_t S, 
   return BFB200_OK;
 }
 
+// One forward pass of the layered tensor-core path; leaves the last block's output in ws.x (fp32) and ws.x16.
+static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t S, int len, int tok_stride,
+                            const MaskSource& ms, cudaStream_t st) {
+  const int d = m.d_model, F = m.d_ff;
+  const int64_t R = S * len;
+  const uint32_t fl = m.site_flags, fmt = tc_fmt(m);
+  const TcImage img = tc_image(m);
+  const uint16_t* w16 = (const uint16_t*)m.fused_image;
+  BFB_REQUIRE(len <= m.pe_len, BFB200_ERR_INVALID_ARG, "sequence length %d exceeds the positional table (%d)", len, m.pe_len);
+  BFB_REQUIRE(len <= 256, BFB200_ERR_UNSUPPORTED, "the tensor-core attention kernel takes sequences of at most 256 tokens (got %d)", len);
+  BFB_CALL(launch_embed(ws.tokens, tok_stride, m.embedding, m.pe, S, len, d, ms, (fl & BFB200_SITE_EMBED) ? 0 : -1, ws.x, st,
+                        ws.x16, fmt));
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int sb = 1 + BFB200_SITES_PER_LAYER * l;
+    BFB_CALL(launch_gemm_tc(ws.x16, d, w16 + img.qkv + (size_t)l * 3 * d * d, nullptr, ws.qkv16, nullptr, 3 * d, R, 3 * d, d, 0,
+                            fmt, st));
+    BFB_CALL(launch_attention_tc(ws.qkv16, ws.att16, S, len, d, m.n_heads, fmt, ms,
+                                 (fl & BFB200_SITE_HEAD_OUT) ? sb + 4 : -1, st));
+    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, nullptr, ws.y, d, R, d, d, 0, fmt, st));
+    // LayerNorm1 output only feeds the FFN: 16-bit copy only (att16 is free again)
+    BFB_CALL(launch_resid_ln(ws.x, ws.y, nullptr, R, len, d, m.ln1_w + (size_t)l * d, m.ln1_b + (size_t)l * d, m.ln_eps, ms,
+                             (fl & BFB200_SITE_ATTN_RESID) ? sb + 1 : -1, (fl & BFB200_SITE_FFN_IN) ? sb + 2 : -1, st,
+                             ws.att16, fmt));
+    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.ff1 + (size_t)l * F * d, m.ff1_b + (size_t)l * F, ws.h16, nullptr, F, R, F, d,
+                            1, fmt, st));
+    BFB_CALL(launch_gemm_tc(ws.h16, F, w16 + img.ff2 + (size_t)l * d * F, m.ff2_b + (size_t)l * d, nullptr, ws.y, d, R, d, F, 0,
+                            fmt, st));
+    // both residuals start from the BLOCK INPUT x (transformer.py:231-233)
+    BFB_CALL(launch_resid_ln(ws.x, ws.y, ws.x2, R, len, d, m.ln2_w + (size_t)l * d, m.ln2_b + (size_t)l * d, m.ln_eps, ms,
+                             (fl & BFB200_SITE_FFN_RESID) ? sb + 3 : -1, (fl & BFB200_SITE_LAYER_OUT) ? sb + 0 : -1, st,
+                             ws.x16, fmt));
+    float* t = ws.x; ws.x = ws.x2; ws.x2 = t;
+  }
+  return BFB200_OK;
+}
+
 }  // namespace bfb
 
 using namespace bfb;
+
+extern "C" int bfb200_compute_path(const bfb200_transformer* model) {
+  if (model == nullptr) return -1;
+  if (model->compute == BFB200_COMPUTE_FP32) return 0;
+  if (use_fused(*model)) return 1;
+  if (use_tc(*model) && tc_shape_ok(*model)) return 2;
+  return -1;
+}
+
+extern "C" size_t bfb200_fused_image_bytes(const bfb200_transformer* model) {
+  if (model == nullptr) return 0;
+  if (use_fused(*model)) return fused_image_bytes(*model);
+  if (use_tc(*model) && tc_shape_ok(*model)) return (tc_image(*model).elems * 2 + 255) & ~(size_t)255;
+  return 0;
+}
+
+extern "C" int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream) {
+  BFB_REQUIRE(model != nullptr, BFB200_ERR_INVALID_ARG, "model is NULL");
+  BFB_DEV(image);
+  BFB_DEV(model->embedding); BFB_DEV(model->pe); BFB_DEV(model->head_w); BFB_DEV(model->head_b);
+  BFB_DEV(model->w_qkv); BFB_DEV(model->w_out); BFB_DEV(model->ln1_w); BFB_DEV(model->ln1_b); BFB_DEV(model->ff1_w);
+  BFB_DEV(model->ff1_b); BFB_DEV(model->ff2_w); BFB_DEV(model->ff2_b); BFB_DEV(model->ln2_w); BFB_DEV(model->ln2_b);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bfb200_transformer& m = *model;
+  if (use_fused(m)) return fused_pack(m, image, image_bytes, st);
+  BFB_REQUIRE(use_tc(m) && tc_shape_ok(m), BFB200_ERR_UNSUPPORTED, "no 16-bit weight image for this model / compute type");
+  const TcImage img = tc_image(m);
+  BFB_REQUIRE(image_bytes >= img.elems * 2, BFB200_ERR_WORKSPACE, "weight image buffer too small: %zu < %zu", image_bytes,
+              img.elems * 2);
+  const size_t L = m.n_layers, d = m.d_model, F = m.d_ff, V = m.ntoken;
+  uint16_t* w16 = (uint16_t*)image;
+  const uint32_t fmt = tc_fmt(m);
+  BFB_CALL(launch_to16(m.w_qkv, w16 + img.qkv, (int64_t)(L * 3 * d * d), fmt, st));
+  BFB_CALL(launch_to16(m.w_out, w16 + img.out, (int64_t)(L * d * d), fmt, st));
+  BFB_CALL(launch_to16(m.ff1_w, w16 + img.ff1, (int64_t)(L * F * d), fmt, st));
+  BFB_CALL(launch_to16(m.ff2_w, w16 + img.ff2, (int64_t)(L * d * F), fmt, st));
+  BFB_CALL(launch_to16(m.head_w, w16 + img.head, (int64_t)(V * d), fmt, st));
+  return BFB200_OK;
+}
 
 extern "C" size_t bfb200_transformer_workspace_bytes(const bfb200_transformer* model, int64_t n_sequences,
                                                      int32_t max_len) {
@@ -152,8 +287,9 @@ extern "C" int bfb200_transformer_forward(const bfb200_transformer* model, const
                                           int64_t index_base, float* logp_out, void* workspace,
                                           size_t workspace_bytes_, void* stream) {
   BFB_CALL(validate_model(model));
-  BFB_REQUIRE(model->compute == BFB200_COMPUTE_FP32, BFB200_ERR_UNSUPPORTED,
-              "bfb200_transformer_forward (all-position log-probs) runs with compute=fp32");
+  BFB_REQUIRE(!use_fused(*model), BFB200_ERR_UNSUPPORTED,
+              "bfb200_transformer_forward (all-position log-probs) is served by the fp32 and the layered tensor-core paths; "
+              "pack this model with compute=fp32");
   BFB_REQUIRE(len >= 0 && batch >= 0, BFB200_ERR_INVALID_ARG, "bad shape (%d, %lld)", len, (long long)batch);
   if (len == 0 || batch == 0) return BFB200_OK;
   BFB_DEV(src);
@@ -175,9 +311,15 @@ extern "C" int bfb200_transformer_forward(const bfb200_transformer* model, const
   if (ms.bits != nullptr)
     BFB_REQUIRE(ms.max_len >= len, BFB200_ERR_INVALID_ARG, "masks.max_len %d < len %d", ms.max_len, len);
   BFB_CALL(launch_init_tokens(src, batch, 0, batch, 1, len, len, m.ntoken, ws.tokens, st));
-  BFB_CALL(forward_chunk(m, ws, batch, len, len, ms, st));
-  BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, batch * len, m.ntoken, m.d_model, 1, 0, 0, st));
-  BFB_CALL(launch_logsoftmax_seqfirst(ws.logits, batch, len, m.ntoken, logp_out, st));
+  if (use_tc(m)) {
+    BFB_CALL(forward_chunk_tc(m, ws, batch, len, len, ms, st));
+    BFB_CALL(launch_gemm_tc(ws.x16, m.d_model, (const uint16_t*)m.fused_image + tc_image(m).head, m.head_b, nullptr, ws.logits,
+                            logits_pitch(m), batch * len, m.ntoken, m.d_model, 0, tc_fmt(m), st));
+  } else {
+    BFB_CALL(forward_chunk(m, ws, batch, len, len, ms, st));
+    BFB_CALL(launch_sgemm(ws.x, m.head_w, m.head_b, ws.logits, batch * len, m.ntoken, m.d_model, 1, 0, 0, st));
+  }
+  BFB_CALL(launch_logsoftmax_seqfirst(ws.logits, batch, len, m.ntoken, logp_out, st, logits_pitch(m)));
   return BFB200_OK;
 }
 
@@ -244,6 +386,9 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
   if (fused)
     BFB_REQUIRE(P + N - 1 <= 16, BFB200_ERR_UNSUPPORTED,
                 "compute=f16 (fused kernel) takes sequences of at most 16 tokens; P + N - 1 = %d", P + N - 1);
+  if (use_tc(m))
+    BFB_REQUIRE(P + N - 1 <= 256, BFB200_ERR_UNSUPPORTED,
+                "the layered tensor-core path takes sequences of at most 256 tokens; P + N - 1 = %d", P + N - 1);
 
   for (int64_t item0 = 0; item0 < a.n_items; item0 += chunk) {
     const int64_t items = (a.n_items - item0 < chunk) ? a.n_items - item0 : chunk;
@@ -264,6 +409,14 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
       if (fused) {
         BFB_CALL(launch_mc_forward_fused(m, ws.tokens, ws.tokens, max_len, S, len, a.scheme, a.mode, a.temperature,
                                          ms, forced, ws.seq_scores, logp, st));
+      } else if (use_tc(m)) {
+        BFB_CALL(forward_chunk_tc(m, ws, S, len, max_len, ms, st));
+        // vocabulary head on the last position only: A rows are len * d elements apart, starting at position len - 1
+        BFB_CALL(launch_gemm_tc(ws.x16 + (size_t)(len - 1) * m.d_model, (int64_t)len * m.d_model,
+                                (const uint16_t*)m.fused_image + tc_image(m).head, m.head_b, nullptr, ws.logits,
+                                logits_pitch(m), S, m.ntoken, m.d_model, 0, tc_fmt(m), st));
+        BFB_CALL(launch_score_step(ws.logits, S, m.ntoken, a.scheme, a.mode, a.temperature, ms, forced, ws.tokens,
+                                   max_len, len, ws.seq_scores, logp, st, logits_pitch(m)));
       } else {
         BFB_CALL(forward_chunk(m, ws, S, len, max_len, ms, st));
         // vocabulary head on the last position only (active_learning.py:62, :103, :146)

@@ -6,6 +6,7 @@
 // Reference arithmetic: src/model/transformer.py (cited per kernel).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace bfb {
 
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
                                                     const float* __restrict__ emb,
                                                     const float* __restrict__ pe, int64_t n_seq, int len,
                                                     int d, float sqrt_d, MaskSource ms, int site,
-                                                    float* __restrict__ x) {
+                                                    float* __restrict__ x, uint16_t* __restrict__ x16,
+                                                    uint32_t fmt) {
   const int d4 = d >> 2;
   const int64_t total = n_seq * len * d4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -75,6 +77,12 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
     o.z = e.z * sqrt_d + p.z;
     o.w = e.w * sqrt_d + p.w;
     reinterpret_cast<float4*>(x)[i] = o;
+    if (x16 != nullptr) {   // 16-bit copy: the operand of the next tensor-core product
+      uint2 w;
+      w.x = fmt == umma::kFmtF16 ? umma::pack_f16x2(o.x, o.y) : umma::pack_bf16x2(o.x, o.y);
+      w.y = fmt == umma::kFmtF16 ? umma::pack_f16x2(o.z, o.w) : umma::pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(x16)[i] = w;
+    }
   }
 }
 
@@ -243,7 +251,8 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__
                                                        float* __restrict__ out, int64_t n_rows, int len,
                                                        int d, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
-                                                       MaskSource ms, int branch_site, int out_site) {
+                                                       MaskSource ms, int branch_site, int out_site,
+                                                       uint16_t* __restrict__ out16, uint32_t fmt) {
   const int lane = threadIdx.x & 31;
   const int d4 = d >> 2;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -301,7 +310,13 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__
           o.z = (keep & 4u) ? o.z * ms.scale : 0.f;
           o.w = (keep & 8u) ? o.w * ms.scale : 0.f;
         }
-        reinterpret_cast<float4*>(out + r * d)[f4] = o;
+        if (out != nullptr) reinterpret_cast<float4*>(out + r * d)[f4] = o;
+        if (out16 != nullptr) {
+          uint2 w;
+          w.x = fmt == umma::kFmtF16 ? umma::pack_f16x2(o.x, o.y) : umma::pack_bf16x2(o.x, o.y);
+          w.y = fmt == umma::kFmtF16 ? umma::pack_f16x2(o.z, o.w) : umma::pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(out16 + r * d)[f4] = w;
+        }
       }
     }
   }
@@ -316,7 +331,7 @@ template <int NPL>
 __global__ void __launch_bounds__(256) score_step_kernel(
     const float* __restrict__ logits, int64_t n_seq, int vocab, int scheme, int mode, float temperature,
     MaskSource ms, const int32_t* __restrict__ forced, int32_t* __restrict__ tokens, int tok_stride,
-    int write_pos, float* __restrict__ seq_scores, float* __restrict__ logp_out) {
+    int write_pos, float* __restrict__ seq_scores, float* __restrict__ logp_out, int pitch) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_seq;
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(256) score_step_kernel(
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
       const int c = lane + 32 * j;
-      l[j] = c < vocab ? __ldg(logits + s * vocab + c) : -INFINITY;
+      l[j] = c < vocab ? __ldg(logits + s * pitch + c) : -INFINITY;
       mx = fmaxf(mx, l[j]);
     }
     mx = warp_max(mx);
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(256) score_step_kernel(
 template <int NPL>
 __global__ void __launch_bounds__(256) logsoftmax_seqfirst_kernel(const float* __restrict__ logits,
                                                                   int64_t n_seq, int len, int vocab,
-                                                                  float* __restrict__ out) {
+                                                                  float* __restrict__ out, int pitch) {
   const int lane = threadIdx.x & 31;
   const int64_t n_rows = n_seq * len;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(256) logsoftmax_seqfirst_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
       const int c = lane + 32 * j;
-      l[j] = c < vocab ? __ldg(logits + r * vocab + c) : -INFINITY;
+      l[j] = c < vocab ? __ldg(logits + r * pitch + c) : -INFINITY;
       mx = fmaxf(mx, l[j]);
     }
     mx = warp_max(mx);
@@ -460,6 +475,21 @@ __global__ void step_mean_kernel(const float* __restrict__ step_scores, int64_t 
   pool_scores[i] = acc / (float)n_steps;
 }
 
+// fp32 -> 16-bit copy (weight image of the layered tensor-core path)
+__global__ void to16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, uint32_t fmt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = fmt == umma::kFmtF16 ? umma::pack_f16x2(src[i], 0.f) : umma::pack_bf16x2(src[i], 0.f);
+    dst[i] = (uint16_t)(w & 0xFFFFu);
+  }
+}
+
+int launch_to16(const float* src, void* dst, int64_t n, uint32_t fmt, cudaStream_t st) {
+  if (n == 0) return BFB200_OK;
+  to16_kernel<<<stride_grid((n + 255) / 256, 8), 256, 0, st>>>(src, (uint16_t*)dst, n, fmt);
+  BFB_LAUNCH_CHECK("to16_kernel", st);
+  return BFB200_OK;
+}
+
 // ---------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------
@@ -474,10 +504,11 @@ int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t it
 }
 
 int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const float* pe, int64_t n_seq,
-                 int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st) {
+                 int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st, void* x16, uint32_t fmt) {
   const int64_t total = n_seq * len * (d >> 2);
   const int grid = stride_grid((total + 255) / 256, 8);
-  embed_kernel<<<grid, 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d, sqrtf((float)d), ms, site, x);
+  embed_kernel<<<grid, 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d, sqrtf((float)d), ms, site, x,
+                                     (uint16_t*)x16, fmt);
   BFB_LAUNCH_CHECK("embed_kernel", st);
   return BFB200_OK;
 }
@@ -519,10 +550,10 @@ int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d
 
 int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,
                     const float* gamma, const float* beta, float eps, const MaskSource& ms,
-                    int branch_site, int out_site, cudaStream_t st) {
+                    int branch_site, int out_site, cudaStream_t st, void* out16, uint32_t fmt) {
   BFB_REQUIRE(d <= 4096, BFB200_ERR_UNSUPPORTED, "d_model %d > 4096", d);
   const int grid = stride_grid((n_rows + 7) / 8, 8);
-#define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site)
+#define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, (uint16_t*)out16, fmt)
   const int d4 = d >> 2;
   if (d4 <= 32) LAUNCH_LN(1);
   else if (d4 <= 64) LAUNCH_LN(2);
@@ -536,10 +567,11 @@ int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, 
 
 int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme, int mode,
                       float temperature, const MaskSource& ms, const int32_t* forced, int32_t* tokens,
-                      int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st) {
+                      int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st, int pitch) {
+  if (pitch <= 0) pitch = vocab;
   BFB_REQUIRE(vocab <= 1024, BFB200_ERR_UNSUPPORTED, "ntoken %d > 1024", vocab);
   const int grid = stride_grid((n_seq + 7) / 8, 8);
-#define LAUNCH_SC(NPL) score_step_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, vocab, scheme, mode, temperature, ms, forced, tokens, tok_stride, write_pos, seq_scores, logp_out)
+#define LAUNCH_SC(NPL) score_step_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, vocab, scheme, mode, temperature, ms, forced, tokens, tok_stride, write_pos, seq_scores, logp_out, pitch)
   if (vocab <= 32) LAUNCH_SC(1);
   else if (vocab <= 64) LAUNCH_SC(2);
   else if (vocab <= 128) LAUNCH_SC(4);
@@ -551,10 +583,11 @@ int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme,
 }
 
 int launch_logsoftmax_seqfirst(const float* logits, int64_t n_seq, int len, int vocab, float* out,
-                               cudaStream_t st) {
+                               cudaStream_t st, int pitch) {
+  if (pitch <= 0) pitch = vocab;
   BFB_REQUIRE(vocab <= 1024, BFB200_ERR_UNSUPPORTED, "ntoken %d > 1024", vocab);
   const int grid = stride_grid((n_seq * len + 7) / 8, 8);
-#define LAUNCH_LS(NPL) logsoftmax_seqfirst_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, len, vocab, out)
+#define LAUNCH_LS(NPL) logsoftmax_seqfirst_kernel<NPL><<<grid, 256, 0, st>>>(logits, n_seq, len, vocab, out, pitch)
   if (vocab <= 32) LAUNCH_LS(1);
   else if (vocab <= 64) LAUNCH_LS(2);
   else if (vocab <= 128) LAUNCH_LS(4);

@@ -332,22 +332,27 @@ class PackedTransformer:
         self.compute = compute
         self._workspace: torch.Tensor | None = None
         self.fused_image: torch.Tensor | None = None
-        if compute == "fp16":
+        self.path = 0   # 0 layered fp32, 1 fused kernel, 2 layered tensor-core path
+        if compute in ("fp16", "bf16"):
             lib = _lib.load()
+            self.path = lib.bfb200_compute_path(C.byref(self.desc))
             nbytes = lib.bfb200_fused_image_bytes(C.byref(self.desc))
-            if nbytes == 0:
+            if self.path < 0 or nbytes == 0:
                 raise NotImplementedError(
-                    "compute='fp16' is served by the fused tcgen05 kernel only (d_model 64, 8 heads, "
-                    f"dim_feedforward <= 64, ntoken <= 128); got d={d} H={H} F={F} V={module.ntoken} L={L}")
+                    f"compute={compute!r} needs the fused kernel's class (fp16: d_model 64, 8 heads, dim_feedforward <= 64, "
+                    "ntoken <= 128) or heads of width 64 with dim_feedforward % 8 == 0 (layered tensor-core path); "
+                    f"got d={d} H={H} F={F} V={module.ntoken} L={L}")
             self.fused_image = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self.desc.fused_image = self.fused_image.data_ptr()
             with torch.cuda.device(device):
                 _lib.check(lib.bfb200_fused_pack(C.byref(self.desc), self.fused_image.data_ptr(), nbytes,
                                                  _stream_ptr(device)))
 
-    def fused_capable(self) -> bool:
-        """True when this model's shape is in the fused tcgen05 kernel's class (compute='fp16')."""
-        return _lib.load().bfb200_fused_image_bytes(C.byref(self.desc)) > 0
+    def path_for(self, compute: str) -> int:
+        """Implementation the library would pick for this model under `compute` (see bfb200_compute_path)."""
+        probe = _lib.Transformer.from_buffer_copy(self.desc)
+        probe.compute = _lib.COMPUTE[compute]
+        return _lib.load().bfb200_compute_path(C.byref(probe))
 
     def workspace(self, nbytes: int) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() < nbytes:
@@ -423,18 +428,21 @@ def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransfo
     return entry[1]
 
 
-FUSED_MAX_LEN = 16  # longest sequence (P + N - 1) the fused fp16 kernel takes
+FUSED_MAX_LEN = 16   # longest sequence (P + N - 1) the fused fp16 kernel takes
+TC_MAX_LEN = 256     # ... and the layered tensor-core path
 
 
 def scoring_pack(module, device: torch.device, prompt_len: int, new_tokens: int, compute: str = "auto") -> PackedTransformer:
-    """Pack used by the MC-scoring loop.  compute='auto' picks the fused fp16 tensor-core kernel whenever the
-    model and sequence lengths are in its class (the reference notebooks' configuration) and the exact fp32
-    CUDA path otherwise; 'fp32' / 'fp16' force one (fp16 raises NotImplementedError outside the class)."""
-    if compute not in ("auto", "fp32", "fp16"):
+    """Pack used by the MC-scoring loop.  compute='auto' picks a tensor-core path whenever the model and sequence
+    lengths are in its class — the fused fp16 kernel for the reference notebooks' configuration, the layered
+    TMA/tcgen05 path for models with heads of width 64 — and the exact fp32 CUDA path otherwise; 'fp32' / 'fp16' /
+    'bf16' force one (raising NotImplementedError outside the class)."""
+    if compute not in ("auto", "fp32", "fp16", "bf16"):
         raise ValueError(f"unknown compute {compute!r}")
     if compute == "auto":
         base = packed(module, device, "fp32")
-        if base.fused_capable() and prompt_len + new_tokens - 1 <= FUSED_MAX_LEN and len(module.layers) >= 1:
+        path, longest = base.path_for("fp16"), prompt_len + new_tokens - 1
+        if (path == 1 and longest <= FUSED_MAX_LEN) or (path == 2 and longest <= TC_MAX_LEN):
             return packed(module, device, "fp16")
         return base
     return packed(module, device, compute)

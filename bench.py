@@ -425,6 +425,26 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
         out[f"gemm_tc[{name} {R}x{n}x{k_}]"] = {"ms": ms, "bound": "tensor", "achieved": tf, "peak": tc_peak,
                                                  "unit": "TFLOP/s", "frac": tf / tc_peak, "peak_source": peak_src + " (burst)"}
         del a, w
+    # scaled configuration end to end: MyTransformer(114, 512, 8, 2048, 6), 256-token sequences, single-step
+    # entropy scoring, T = 50, on the layered tensor-core path; 32 pool items = 1,600 sequences x 256 tokens per pass
+    try:
+        from bayesformer_b200.model.transformer import MyTransformer
+        torch.manual_seed(SEED)
+        big = MyTransformer(114, 512, 8, 2048, 6, bayes_dropout=0.3, bayes=True).eval().to(dev)
+        n_items, t_mc = 32, 50
+        pr = torch.randint(0, 114, (256, n_items), device=dev)
+        pk = engine.scoring_pack(big, dev, 256, 1, "auto")
+        ms = timed(lambda: engine.mc_score_transformer(pk, pr, 1, t_mc, "dropout", "entropy", seed=SEED), reps=3)
+        flops = t_mc * (6 * (8 * 256 * 512 * 512 + 4 * 256 * 512 * 2048 + 2 * 256 * 257 * 512) + 2 * 512 * 114)
+        sps = n_items / (ms * 1e-3)
+        out["scaled_c4_mc_score"] = {"pool_items": n_items, "T_mc": t_mc, "len": 256, "compute": pk.compute, "ms": ms,
+                                     "pool_samples_per_s": sps, "flops_per_pool_sample": flops, "bound": "tensor",
+                                     "achieved": sps * flops / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                                     "unit": "TFLOP/s", "frac": sps * flops / 1e12 / peaks["bf16_tflops_sustained"],
+                                     "peak_source": peak_src + " (sustained)"}
+        del big, pk, pr
+    except Exception as exc:
+        out["scaled_c4_mc_score"] = {"error": repr(exc)}
     # toy classifier, SURVEY C2i
     from bayesformer_b200.model.bayesian_classification import MLP
     torch.manual_seed(SEED)

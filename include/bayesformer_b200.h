@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BFB200_ABI_VERSION 2
+#define BFB200_ABI_VERSION 3
 
 enum {
   BFB200_OK = 0,
@@ -54,7 +54,10 @@ enum {
                               trained model's mid-range probabilities by up to 5 %, fp16 keeps them within
                               1 % (measured).  Served by the
                               fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 16
-                              (the reference notebooks' model); other shapes return BFB200_ERR_UNSUPPORTED */
+                              (the reference notebooks' model).  Other models with heads of width 64 and
+                              sequences of at most 256 tokens (the scaled configuration) run the layered
+                              tensor-core path: TMA-fed tcgen05 GEMMs + tcgen05 attention, fp32 residual stream */,
+  BFB200_COMPUTE_BF16 = 2  /* layered tensor-core path with bf16 operands (heads of width 64, len <= 256) */
 };
 
 /* always-on dropout sites of src/model/transformer.py (bit set = site live) */
@@ -241,12 +244,17 @@ int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * Weight image of the fused MC-forward kernel (compute = BFB200_COMPUTE_F16): every nn.Linear weight of
- * src/model/transformer.py as fp16 in the 128-byte-swizzled K-major shared-memory layout tcgen05.mma reads,
- * followed by the fp32 LayerNorm / bias vectors and the first 16 rows of `pe`.  _bytes returns 0 when the
- * model's shape is outside the fused kernel's class.  Re-pack after every weight update.
+ * 16-bit weight image of the tensor-core paths (model->compute = F16 / BF16), written into model->fused_image's
+ * buffer.  Fused class: every nn.Linear weight of src/model/transformer.py as fp16 in the 128-byte-swizzled K-major
+ * shared-memory layout tcgen05.mma reads, followed by the fp32 LayerNorm / bias vectors and the first 16 rows of
+ * `pe`.  Layered tensor-core path: plain row-major 16-bit copies [W_qkv | W_out | FFN W1 | FFN W2 | head] that the
+ * GEMM kernel reads through TMA.  _bytes returns 0 when no tensor-core path serves the model's shape.  Re-pack
+ * after every weight update.
  */
 size_t bfb200_fused_image_bytes(const bfb200_transformer* model);
+/* which implementation model->compute selects for this shape: 0 layered fp32 kernels, 1 fused MC-forward kernel,
+ * 2 layered tensor-core path, -1 none (BFB200_ERR_UNSUPPORTED at call time) */
+int bfb200_compute_path(const bfb200_transformer* model);
 int bfb200_fused_pack(const bfb200_transformer* model, void* image, size_t image_bytes, void* stream);
 
 /*

@@ -1,0 +1,125 @@
+"""Layered tensor-core path (TMA-fed tcgen05 GEMMs + tcgen05 attention, fp32 residual stream) — the scaled
+configuration's route (d_model 512, 8 heads of 64, F 2048, 6 layers, 256 tokens).  16-bit tolerance
+class: probabilities within 1e-2 of the fp32 reference."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from bayesformer_b200 import _lib, engine as e
+
+    _lib.load()
+    return e
+
+
+def _bits(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+
+
+def _probs_close(got_logp, want_logp, rtol, atol=1e-4):
+    got, want = np.exp(np.asarray(got_logp, np.float64)), np.exp(np.asarray(want_logp, np.float64))
+    err = np.abs(got - want) - (rtol * want + atol)
+    assert err.max() <= 0, f"probabilities off by {np.abs(got - want).max():.3e} (worst excess {err.max():.3e})"
+
+
+@pytest.mark.parametrize("compute,rtol", [("fp16", 1e-2), ("bf16", 5e-2)])
+def test_scaled_c4_forward_against_reference_outputs(engine, dev, compute, rtol):
+    """The reference's stored log-probs for the C4 model (weights / masks regenerated from their seeds and pinned by
+    the fp32 module forward, as in test_gpu_parity.test_scaled_c4_forward)."""
+    from bayesformer_b200.model.transformer import MyTransformer
+    from oracle import ref_shim
+
+    z = H.load("scaled_c4.npz")
+    V, d, Hh, F, L = (int(v) for v in z["dims"])
+    p = float(z["p"])
+    torch.manual_seed(int(z["weight_seed"]))
+    model = MyTransformer(V, d, Hh, F, L, bayes_dropout=p, bayes=True).eval()
+    src = torch.from_numpy(z["src"])
+    log = []
+    torch.manual_seed(int(z["mask_seed"]))
+    with torch.no_grad(), ref_shim.record_dropout(log):
+        cpu_out = model._module_forward(src)
+    np.testing.assert_allclose(cpu_out[-1].numpy(), z["logp_last"], rtol=1e-4, atol=1e-5)
+    pm = R.PackedMasks(1, L, src.shape[1], src.shape[0], d)
+    pm.set(0, R.SITE_EMBED, log[0].numpy())
+    for i in range(L):
+        pm.set(0, R.site_layer_out(i), log[1 + i].numpy())
+    model = model.to(dev)
+    pack = model.native_pack(dev, compute)
+    assert pack.path == 2
+    with torch.no_grad():
+        got = engine.transformer_forward(pack, src.to(dev), mask_bits=_bits(pm.bits, dev)).cpu().numpy()
+    _probs_close(got[-1], z["logp_last"], rtol)
+    _probs_close(got[::37], z["logp_rows"], rtol)
+
+
+@pytest.mark.parametrize("P,N,B,T", [(9, 4, 21, 5), (40, 2, 7, 3), (130, 1, 3, 2), (256, 1, 2, 2), (1, 3, 5, 4)])
+def test_tc_path_matches_exact_path(engine, dev, P, N, B, T):
+    """Same seed => same Philox masks; the fp32 path's tokens are forced into the tensor-core run."""
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(P)
+    model = MyTransformer(50, 128, 2, 72, 2, bayes_dropout=0.2, bayes=True).eval().to(dev)
+    prompts = torch.randint(0, 50, (P, B), device=dev)
+    exact = engine.mc_score_transformer(model.native_pack(dev, "fp32"), prompts, N, T, "dropout", "entropy", seed=7,
+                                        return_logp=True, return_tokens=True)
+    forced = exact.tokens[:, P:].t().contiguous()
+    pack = model.native_pack(dev, "fp16")
+    assert pack.path == 2
+    got = engine.mc_score_transformer(pack, prompts, N, T, "dropout", "entropy", seed=7, forced_tokens=forced,
+                                      return_logp=True)
+    _probs_close(got.logp.cpu().numpy(), exact.logp.cpu().numpy(), 1e-2)
+    np.testing.assert_allclose(got.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=1e-2, atol=1e-3)
+
+
+def test_tc_path_latent_sites_and_chunking(engine, dev):
+    import ctypes as C
+
+    from bayesformer_b200 import _lib
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(3)
+    p = 0.25
+    model = MyTransformer(40, 64, 1, 32, 2, bayes_dropout=p, bayes=True).eval()
+    for layer in model.layers:
+        layer.bayes, layer.bayes_dropout = True, p
+        layer.ff.bayes_dropout = p
+        layer.self_attn.bayes, layer.self_attn.bayes_dropout = True, p
+    model = model.to(dev)
+    prompts = torch.randint(0, 40, (20, 33), device=dev)
+    N, T = 3, 4
+    exact = engine.mc_score_transformer(model.native_pack(dev, "fp32"), prompts, N, T, "dropout", "margin", seed=11,
+                                        return_logp=True, return_tokens=True)
+    forced = exact.tokens[:, 20:].t().contiguous()
+    pack = model.native_pack(dev, "bf16")   # d_model 64 with ONE head of width 64: tensor-core path, not the fused class
+    assert pack.path == 2
+    got = engine.mc_score_transformer(pack, prompts, N, T, "dropout", "margin", seed=11, forced_tokens=forced,
+                                      return_logp=True)
+    _probs_close(got.logp.cpu().numpy(), exact.logp.cpu().numpy(), 6e-2, atol=2e-3)
+    args = _lib.McArgs(n_items=33, prompt_len=20, new_tokens=N, n_draws=T)
+    small = _lib.load().bfb200_mc_workspace_bytes(C.byref(pack.desc), C.byref(args), 4)
+    chunked = engine.mc_score_transformer(pack, prompts, N, T, "dropout", "margin", seed=11, forced_tokens=forced,
+                                          workspace_bytes=small)
+    assert torch.equal(chunked.step_scores, got.step_scores)
+
+
+def test_auto_picks_the_tensor_core_path_for_width_64_heads(engine, dev):
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    big = MyTransformer(114, 512, 8, 2048, 1, bayes_dropout=0.3, bayes=True).eval().to(dev)
+    pack = engine.scoring_pack(big, dev, 256, 1, "auto")
+    assert pack.compute == "fp16" and pack.path == 2
+    assert engine.scoring_pack(big, dev, 300, 1, "auto").compute == "fp32"
