@@ -2,14 +2,17 @@
 // 8 heads, sequences of up to 256 tokens).  Reference arithmetic: src/model/transformer.py:58-65 (per head:
 // softmax(Q K^T / sqrt(dh) + causal mask) V) and :116-124 (optional head-output dropout, concatenation).
 //
-// One CTA (128 threads) per (sequence, head, tile of 128 queries):
-//   1. one thread issues 2-D TMA loads (128-byte swizzle) of the Q tile and of the K rows this tile can attend to,
-//      straight out of the packed (R, 3d) QKV activation; meanwhile all threads read the V rows and write them
-//      TRANSPOSED (dims x keys, K-major) into shared memory, the layout tcgen05.mma wants for the B operand of P V;
+// One CTA (128 threads) per (sequence, head, tile of 128 queries); two CTAs share an SM (96 KB of shared memory and
+// 256 TMEM columns each), so one CTA's softmax overlaps the other's copies and tensor-core work:
+//   1. one thread issues 2-D TMA loads (128-byte swizzle) of the Q tile and of the K and V rows this tile can attend
+//      to, straight out of the packed (R, 3d) QKV activation;
 //   2. S = Q K^T: tcgen05.mma M = 128, N = keys (<= 256), K = 64, fp32 accumulator in 256 TMEM columns;
 //   3. softmax, thread = query row: two passes over the row with tcgen05.ld (max, then exp / sum with the causal
-//      mask), the un-normalised probabilities go to shared memory as the 16-bit A operand (swizzled K-major slabs);
-//   4. O = P V: tcgen05.mma M = 128, N = 64, K = keys into 64 more TMEM columns;
+//      mask), the un-normalised probabilities go to shared memory as the 16-bit A operand (swizzled K-major slabs,
+//      written over the dead Q / K tiles);
+//   4. O = P V: tcgen05.mma M = 128, N = 64, K = keys.  V is consumed exactly as TMA delivered it — keys x dims,
+//      i.e. an MN-major B operand (instruction-descriptor bit 16) — and O accumulates into the first 64 of the S
+//      columns, dead once every probability is in shared memory;
 //   5. epilogue: O row / row sum (+ head-output dropout), converted, one 128-byte line per query row to HBM.
 // Q, K, V, P are 16-bit (fp16 or bf16); scores, softmax statistics and both accumulators are fp32.
 #include <cuda.h>
@@ -27,8 +30,10 @@ constexpr int AT_M = 128;        // queries per CTA
 constexpr int AT_MAXKV = 256;    // keys per CTA
 constexpr uint32_t AT_Q_BYTES = AT_M * 128;
 constexpr uint32_t AT_K_BYTES = AT_MAXKV * 128;
-constexpr uint32_t AT_VT_BYTES = (AT_MAXKV / 64) * 64 * 128;   // 4 slabs of 64 dims x 64 keys
-constexpr uint32_t AT_P_BYTES = (AT_MAXKV / 64) * AT_M * 128;  // 4 slabs of 128 rows x 64 keys
+constexpr uint32_t AT_V_BYTES = AT_MAXKV * 128;                // keys x 64 dims as delivered by TMA
+constexpr uint32_t AT_P_BYTES = (AT_MAXKV / 64) * AT_M * 128;  // 4 slabs of 128 rows x 64 keys, over Q | K | pad
+constexpr uint32_t AT_SMEM = 1024 + AT_P_BYTES + AT_V_BYTES;
+static_assert(AT_P_BYTES >= AT_Q_BYTES + AT_K_BYTES, "P must cover the Q and K tiles it overwrites");
 
 __device__ __forceinline__ void at_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -52,15 +57,15 @@ __device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
   return fmt == umma::kFmtF16 ? umma::pack_f16x2(a, b) : umma::pack_bf16x2(a, b);
 }
 
-__global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__(AT_M, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
-  uint8_t* sVT = sK + AT_K_BYTES;
-  uint8_t* sP = sVT + AT_VT_BYTES;
-  __shared__ uint64_t bar_qk, bar_s, bar_o;
+  uint8_t* sP = smem;                 // written only after S = Q K^T has completed
+  uint8_t* sV = smem + AT_P_BYTES;
+  __shared__ uint64_t bar_qk, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -73,11 +78,12 @@ __global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_cons
   const int64_t row_base = s * a.len;
 
   if (warp == 0) {
-    umma::tmem_alloc(&tmem_slot, 512);
+    umma::tmem_alloc(&tmem_slot, 256);
     umma::tmem_relinquish();
   }
   if (tid == 0) {
     umma::mbar_init(&bar_qk, 1);
+    umma::mbar_init(&bar_v, 1);
     umma::mbar_init(&bar_s, 1);
     umma::mbar_init(&bar_o, 1);
     umma::fence_mbar_init();
@@ -93,34 +99,10 @@ __global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_cons
     at_tma_load_2d(sQ, &map_qkv, h * AT_DH, (int)(row_base + m0), &bar_qk);
     for (int b = 0; b < k_boxes; ++b)
       at_tma_load_2d(sK + b * AT_M * 128, &map_qkv, a.d + h * AT_DH, (int)(row_base + b * AT_M), &bar_qk);
+    umma::mbar_expect_tx(&bar_v, (uint32_t)k_boxes * AT_M * 128u);
+    for (int b = 0; b < k_boxes; ++b)
+      at_tma_load_2d(sV + b * AT_M * 128, &map_qkv, 2 * a.d + h * AT_DH, (int)(row_base + b * AT_M), &bar_v);
   }
-  // V rows -> V^T (dims x keys) in the swizzled K-major slab layout; rows past the activation end are zeros
-  for (int j = tid; j < kvp; j += AT_M) {
-    const int64_t r = row_base + j;
-    uint4 v[8];
-    if (r < a.n_rows) {
-      const uint4* src = reinterpret_cast<const uint4*>(a.qkv + r * 3 * (int64_t)a.d + 2 * a.d + h * AT_DH);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = make_uint4(0, 0, 0, 0);
-    }
-    uint8_t* slab = sVT + (j >> 6) * (64 * 128);
-    const uint32_t kc = (uint32_t)(j & 63) >> 3, ko = (uint32_t)(j & 7) * 2u;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t dim = (uint32_t)(8 * c + e);
-        const uint16_t val = (uint16_t)((w[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-        *reinterpret_cast<uint16_t*>(slab + umma::sw128_offset(dim, kc) + ko) = val;
-      }
-    }
-  }
-  umma::fence_async_smem();
-  __syncthreads();
 
   // ---- S = Q K^T ----
   if (tid == 0) {
@@ -176,13 +158,16 @@ __global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_cons
 
   // ---- O = P V ----
   if (tid == 0) {
+    umma::mbar_wait(&bar_v, 0);
     umma::tc_fence_after_sync();
-    const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, a.fmt);
-    const uint32_t pP = umma::smem_u32(sP), pV = umma::smem_u32(sVT);
+    // B = V as loaded (keys x dims): MN-major, 128-byte rows of 64 dims, 8-key groups 1024 bytes apart;
+    // one K = 16 step consumes two such groups -> 2048 bytes per step
+    const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, a.fmt) | (1u << 16);
+    const uint32_t pP = umma::smem_u32(sP), pV = umma::smem_u32(sV);
     for (int ks = 0; ks < kvp / 16; ++ks) {
       const uint64_t dp = umma::smem_desc_sw128(pP + (ks >> 2) * (AT_M * 128) + (ks & 3) * 32);
-      const uint64_t dv = umma::smem_desc_sw128(pV + (ks >> 2) * (64 * 128) + (ks & 3) * 32);
-      umma::mma_bf16_ss(tmem_base + 256, dp, dv, idesc, ks > 0);
+      const uint64_t dv = umma::smem_desc_sw128(pV + ks * 2048);
+      umma::mma_bf16_ss(tmem_base, dp, dv, idesc, ks > 0);
     }
     umma::mma_commit(&bar_o);
   }
@@ -192,8 +177,8 @@ __global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_cons
   // ---- epilogue ----
   {
     uint32_t r0[32], r1[32];
-    umma::tmem_ld32(tmem_base + lane_base + 256, r0);
-    umma::tmem_ld32(tmem_base + lane_base + 288, r1);
+    umma::tmem_ld32(tmem_base + lane_base, r0);
+    umma::tmem_ld32(tmem_base + lane_base + 32, r1);
     umma::tmem_ld_wait();
     if (q_ok) {
       const float inv = 1.0f / sum;
@@ -223,7 +208,7 @@ __global__ void __launch_bounds__(AT_M, 1) attention_tc_kernel(const __grid_cons
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 256);
 }
 
 typedef CUresult (*AtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -265,7 +250,7 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   a.fmt = fmt; a.inv_sqrt_dh = 1.0f / sqrtf((float)AT_DH); a.site = site; a.ms = ms;
   const int64_t grid = n_seq * n_heads * a.m_tiles;
   BFB_REQUIRE(grid <= 0x7FFFFFFF, BFB200_ERR_UNSUPPORTED, "too many attention tiles in one launch");
-  const size_t smem = 1024 + AT_Q_BYTES + AT_K_BYTES + AT_VT_BYTES + AT_P_BYTES;
+  const size_t smem = AT_SMEM;
   cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   attention_tc_kernel<<<(unsigned)grid, AT_M, smem, st>>>(map, a);
   BFB_LAUNCH_CHECK("attention_tc_kernel", st);

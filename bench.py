@@ -437,7 +437,12 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
         ms = timed(lambda: engine.mc_score_transformer(pk, pr, 1, t_mc, "dropout", "entropy", seed=SEED), reps=3)
         flops = t_mc * (6 * (8 * 256 * 512 * 512 + 4 * 256 * 512 * 2048 + 2 * 256 * 257 * 512) + 2 * 512 * 114)
         sps = n_items / (ms * 1e-3)
-        out["scaled_c4_mc_score"] = {"pool_items": n_items, "T_mc": t_mc, "len": 256, "compute": pk.compute, "ms": ms,
+        with engine.profile(dev) as prof_c4:
+            engine.mc_score_transformer(pk, pr, 1, t_mc, "dropout", "entropy", seed=SEED)
+        tot = sum(v["ms"] for v in prof_c4.kernels.values()) or 1.0
+        c4_shares = {n: {"share": round(v["ms"] / tot, 4), "ms": round(v["ms"], 3), "launches": v["launches"]}
+                     for n, v in sorted(prof_c4.kernels.items(), key=lambda kv: -kv[1]["ms"])}
+        out["scaled_c4_mc_score"] = {"kernels": c4_shares,"pool_items": n_items, "T_mc": t_mc, "len": 256, "compute": pk.compute, "ms": ms,
                                      "pool_samples_per_s": sps, "flops_per_pool_sample": flops, "bound": "tensor",
                                      "achieved": sps * flops / 1e12, "peak": peaks["bf16_tflops_sustained"],
                                      "unit": "TFLOP/s", "frac": sps * flops / 1e12 / peaks["bf16_tflops_sustained"],
