@@ -485,31 +485,32 @@ __device__ __forceinline__ void tmem_store_half(uint32_t taddr, const float (&v)
 }
 
 // LayerNorm over a 64-feature row held as two 32-feature halves in two threads (biased variance, eps inside the
-// sqrt: nn.LayerNorm).  Each half computes its mean and centred sum of squares exactly, the pair exchanges them
-// through `red` and combines with the parallel-variance formula (n_a = n_b = 32):
-//   mean = (m_a + m_b) / 2,  M2 = M2_a + M2_b + 16 (m_a - m_b)^2
-__device__ __forceinline__ void layer_norm_half(float (&v)[HW], float2* __restrict__ red, int row, int h, int bar_id,
-                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                float eps) {
-  float s = 0.f;
+// sqrt: nn.LayerNorm).  Each half computes its mean and centred sum of squares exactly (ln_partial), the pair
+// exchanges them through `red` across a group barrier and combines with the parallel-variance formula
+// (n_a = n_b = 32):  mean = (m_a + m_b) / 2,  M2 = M2_a + M2_b + 16 (m_a - m_b)^2      (ln_finish)
+__device__ __forceinline__ float2 ln_partial(const float (&v)[HW]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HW; ++i) s += v[i];
-  const float m_own = s * (1.0f / HW);
-  float q = 0.f;
+  for (int i = 0; i < HW; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+  const float m_own = ((s0 + s1) + (s2 + s3)) * (1.0f / HW);
+  float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HW; ++i) {
-    const float c = v[i] - m_own;
-    q = fmaf(c, c, q);
+  for (int i = 0; i < HW; i += 2) {
+    const float c0 = v[i] - m_own, c1 = v[i + 1] - m_own;
+    q0 = fmaf(c0, c0, q0);
+    q1 = fmaf(c1, c1, q1);
   }
-  red[h * FROWS + row] = make_float2(m_own, q);
-  umma::group_sync(bar_id, 2 * FROWS);
-  const float2 other = red[(h ^ 1) * FROWS + row];
-  const float dm = m_own - other.x;
-  const float mean = 0.5f * (m_own + other.x);
-  const float var = (q + other.y + 16.0f * dm * dm) * (1.0f / FD);
+  return make_float2(m_own, q0 + q1);
+}
+__device__ __forceinline__ void ln_finish(float (&v)[HW], float2 own, float2 other, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float eps) {
+  const float dm = own.x - other.x;
+  const float mean = 0.5f * (own.x + other.x);
+  const float var = (own.y + other.y + 16.0f * dm * dm) * (1.0f / FD);
   const float rstd = rsqrtf(var + eps);
+  const float shift = -mean * rstd;
 #pragma unroll
-  for (int i = 0; i < HW; ++i) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+  for (int i = 0; i < HW; ++i) v[i] = fmaf(fmaf(v[i], rstd, shift), gamma[i], beta[i]);
 }
 
 template <int MAXLEN>
@@ -567,7 +568,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const int bar_id = 1 + g;
 
   const int len = a.len, spt = a.spt;
-  const int seq_l = row / len, pos = row - seq_l * len;
+  // rows are position-major inside a tile (row = pos * spt + sequence): the rows of the LAST position, the only
+  // ones the vocabulary head consumes, are then contiguous, so that in the last layer whole warps can skip the
+  // work whose results nothing reads (see `live` below)
+  const int pos = row / spt, seq_l = row - pos * spt;
+  const int last_lo = (len - 1) * spt, last_hi = len * spt - 1;              // rows of the last position
+  const bool warp_has_last = (row & ~31) <= last_hi && (row | 31) >= last_lo;   // warp-uniform
   const float sqrt_d = sqrtf((float)FD), inv_sqrt_dh = 1.0f / sqrtf((float)FDH);
   const uint32_t fl = a.site_flags;
   const MaskSource& ms = a.ms;
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   for (int64_t tile = (int64_t)blockIdx.x * FGROUPS + g; tile < a.n_tiles; tile += (int64_t)gridDim.x * FGROUPS) {
     const uint32_t s0 = (uint32_t)tile * (uint32_t)spt;   // n_seq < 2^31 per launch (checked on the host)
     const int nseq = (int)(((uint32_t)a.n_seq - s0) < (uint32_t)spt ? ((uint32_t)a.n_seq - s0) : (uint32_t)spt);
-    const bool row_valid = seq_l < nseq;
+    const bool row_valid = pos < len && seq_l < nseq;
     const uint32_t s = s0 + (row_valid ? (uint32_t)seq_l : 0u);
     const RowRng rr = make_row_rng(ms, s);
 
@@ -627,6 +633,11 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       const uint32_t wl = img_u32 + (uint32_t)l * lay.layer_bytes;
       const float* pl = params + l * PARAMS_PER_LAYER;
       const uint32_t sb = 1u + BFB200_SITES_PER_LAYER * (uint32_t)l;
+      // Last layer: only the last position's output is read (vocabulary head, active_learning.py:146), so its
+      // queries, W_out / LayerNorm / FFN rows and layer-out masks for the other positions are dead work; K and V of
+      // every position are still needed.  `live` is warp-uniform.
+      const bool prune = l + 1 == a.n_layers;
+      const bool live = !prune || warp_has_last;
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
       gemm(descA0, wl, 3 * FD, 4);
@@ -657,12 +668,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       // ---- causal attention (transformer.py:58-65): work item = (sequence, head[, query parity]) ----
       {
         const int npairs = nseq * FH;
-        const int nsplit = npairs * 2 <= FGROUP_THREADS ? 2 : 1;   // few pairs: two threads share one, by query parity
+        // few pairs: two threads share one, by query parity; in the last layer only the last query is live
+        const int nsplit = (!prune && npairs * 2 <= FGROUP_THREADS) ? 2 : 1;
         for (int it = gt; it < npairs * nsplit; it += FGROUP_THREADS) {
           const int p = nsplit == 2 ? it >> 1 : it;
           const int qpar = nsplit == 2 ? (it & 1) : -1;
           const int sl = p >> 3, hd = p & 7;
-          const uint32_t row0 = (uint32_t)(sl * len);
+          const uint32_t row0 = (uint32_t)sl;   // row of (sequence sl, position j) = j * spt + sl
           // K unpacked once for short sequences; the 16-token variant keeps K packed too (4 registers per key)
           constexpr bool kUnpackK = false;   // at 128 registers per thread even 8 unpacked keys spill
           float kf[kUnpackK ? MAXLEN : 1][8];
@@ -670,17 +682,17 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 #pragma unroll
           for (int j = 0; j < MAXLEN; ++j) {
             if (j < len) {
-              const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j, hd));
+              const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd));
               if constexpr (kUnpackK) unpack8(kw, kf[j]);
               else kp[j] = kw;
-              vp[j] = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j, hd));
+              vp[j] = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j * spt, hd));
             }
           }
           const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
           for (int t = 0; t < MAXLEN; ++t) {
-            if (t < len && (qpar < 0 || (t & 1) == qpar)) {
-              uint8_t* qptr = B0 + umma::sw128_offset(row0 + t, hd);
+            if (t < len && (qpar < 0 || (t & 1) == qpar) && (!prune || t == len - 1)) {
+              uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
               float q[8];
               unpack8(*reinterpret_cast<const uint4*>(qptr), q);
               float sc[MAXLEN];
@@ -731,18 +743,35 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         }
       }
 
+      if (!live) {
+        // dead rows of the last layer: take part in the barriers of the three products and the two LayerNorm
+        // exchanges (thread 0 of the group still issues the MMAs inside gemm()), compute nothing
+        gemm(descA0, wl + lay.off_out, FD, 4);
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        gemm(descA0, wl + lay.off_w1, (int)lay.fp, 4);
+        gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        continue;
+      }
+
       // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
       gemm(descA0, wl + lay.off_out, FD, 4);
       {
         const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
         const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
-        float v[HW], x[HW];
+        float v[HW];
         tmem_load_half(tW + h * HW, v);
         if (fl & BFB200_SITE_ATTN_RESID) drop_half(v, k_attn, ms.scale);
-        tmem_load_half(tX, x);
+        {
+          float x[HW];
+          tmem_load_half(tX, x);
 #pragma unroll
-        for (int i = 0; i < HW; ++i) v[i] += x[i];
-        layer_norm_half(v, red, row, h, bar_id, pl + h * HW, pl + 64 + h * HW, a.ln_eps);
+          for (int i = 0; i < HW; ++i) v[i] += x[i];
+        }
+        const float2 own = ln_partial(v);
+        red[h * FROWS + row] = own;
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + h * HW, pl + 64 + h * HW, a.ln_eps);
         if (fl & BFB200_SITE_FFN_IN) drop_half(v, k_ffn_in, ms.scale);
         store_half_f16(B0, row, h, v);
       }
@@ -771,18 +800,24 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (fl & BFB200_SITE_LAYER_OUT) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
-        float v[HW], x[HW];
+        float v[HW];
         tmem_load_half(tW + h * HW, v);
         const float* b2 = pl + 192 + h * HW;
 #pragma unroll
         for (int i = 0; i < HW; ++i) v[i] += b2[i];
         if (fl & BFB200_SITE_FFN_RESID) drop_half(v, k_resid, ms.scale);
-        tmem_load_half(tX, x);
+        {
+          float x[HW];
+          tmem_load_half(tX, x);
 #pragma unroll
-        for (int i = 0; i < HW; ++i) v[i] += x[i];
-        layer_norm_half(v, red, row, h, bar_id, pl + 256 + h * HW, pl + 320 + h * HW, a.ln_eps);
+          for (int i = 0; i < HW; ++i) v[i] += x[i];
+        }
+        const float2 own = ln_partial(v);
+        red[h * FROWS + row] = own;
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + 256 + h * HW, pl + 320 + h * HW, a.ln_eps);
         if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);   // transformer.py:370
-        if (l + 1 < a.n_layers) tmem_store_half(tX, v);
+        if (!prune) tmem_store_half(tX, v);
         store_half_f16(B0, row, h, v);
       }
     }
