@@ -16,7 +16,8 @@ int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d
                      const MaskSource& ms, int site, cudaStream_t st);
 int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,
                     const float* gamma, const float* beta, float eps, const MaskSource& ms,
-                    int branch_site, int out_site, cudaStream_t st, void* out16 = nullptr, uint32_t fmt = 0);
+                    int branch_site, int out_site, cudaStream_t st, void* out16 = nullptr, uint32_t fmt = 0,
+                    const void* y16 = nullptr);
 int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme, int mode,
                       float temperature, const MaskSource& ms, const int32_t* forced, int32_t* tokens,
                       int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st,

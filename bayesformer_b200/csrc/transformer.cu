@@ -215,19 +215,21 @@ static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t 
                             fmt, st));
     BFB_CALL(launch_attention_tc(ws.qkv16, ws.att16, S, len, d, m.n_heads, fmt, ms,
                                  (fl & BFB200_SITE_HEAD_OUT) ? sb + 4 : -1, st));
-    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, nullptr, ws.y, d, R, d, d, 0, fmt, st));
+    // the branch outputs (W_out, FFN2) travel as 16-bit: they are added to the fp32 residual stream right away
+    uint16_t* y16 = reinterpret_cast<uint16_t*>(ws.y);
+    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, y16, nullptr, d, R, d, d, 0, fmt, st));
     // LayerNorm1 output only feeds the FFN: 16-bit copy only (att16 is free again)
     BFB_CALL(launch_resid_ln(ws.x, ws.y, nullptr, R, len, d, m.ln1_w + (size_t)l * d, m.ln1_b + (size_t)l * d, m.ln_eps, ms,
                              (fl & BFB200_SITE_ATTN_RESID) ? sb + 1 : -1, (fl & BFB200_SITE_FFN_IN) ? sb + 2 : -1, st,
-                             ws.att16, fmt));
+                             ws.att16, fmt, y16));
     BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.ff1 + (size_t)l * F * d, m.ff1_b + (size_t)l * F, ws.h16, nullptr, F, R, F, d,
                             1, fmt, st));
-    BFB_CALL(launch_gemm_tc(ws.h16, F, w16 + img.ff2 + (size_t)l * d * F, m.ff2_b + (size_t)l * d, nullptr, ws.y, d, R, d, F, 0,
+    BFB_CALL(launch_gemm_tc(ws.h16, F, w16 + img.ff2 + (size_t)l * d * F, m.ff2_b + (size_t)l * d, y16, nullptr, d, R, d, F, 0,
                             fmt, st));
     // both residuals start from the BLOCK INPUT x (transformer.py:231-233)
     BFB_CALL(launch_resid_ln(ws.x, ws.y, ws.x2, R, len, d, m.ln2_w + (size_t)l * d, m.ln2_b + (size_t)l * d, m.ln_eps, ms,
                              (fl & BFB200_SITE_FFN_RESID) ? sb + 3 : -1, (fl & BFB200_SITE_LAYER_OUT) ? sb + 0 : -1, st,
-                             ws.x16, fmt));
+                             ws.x16, fmt, y16));
     float* t = ws.x; ws.x = ws.x2; ws.x2 = t;
   }
   return BFB200_OK;

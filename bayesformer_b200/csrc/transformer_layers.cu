@@ -246,13 +246,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 // the square root (nn.LayerNorm).
 // ---------------------------------------------------------------------------
 template <int NPL4>
-__global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 4) resid_ln_kernel(const float* __restrict__ x,
                                                        const float* __restrict__ y,
                                                        float* __restrict__ out, int64_t n_rows, int len,
                                                        int d, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
                                                        MaskSource ms, int branch_site, int out_site,
-                                                       uint16_t* __restrict__ out16, uint32_t fmt) {
+                                                       uint16_t* __restrict__ out16, uint32_t fmt,
+                                                       const uint16_t* __restrict__ y16) {
   const int lane = threadIdx.x & 31;
   const int d4 = d >> 2;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__
     const uint32_t t = (uint32_t)(r - s * len);
     const float4* xr = reinterpret_cast<const float4*>(x + r * d);
     const float4* yr = reinterpret_cast<const float4*>(y + r * d);
+    const uint2* yr16 = reinterpret_cast<const uint2*>(y16 + r * d);
     float4 v[NPL4];
     float sum = 0.f;
 #pragma unroll
@@ -270,7 +272,18 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(const float* __restrict__
       v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f4 < d4) {
         const float4 a = __ldg(xr + f4);
-        float4 b = __ldg(yr + f4);
+        float4 b;
+        if (y16 != nullptr) {   // branch delivered by the tensor-core GEMM as 16-bit
+          const uint2 w = __ldg(yr16 + f4);
+          if (fmt == umma::kFmtF16) {
+            const float2 lo = umma::unpack_f16x2(w.x), hi = umma::unpack_f16x2(w.y);
+            b = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            b = make_float4(umma::bf16_lo(w.x), umma::bf16_hi(w.x), umma::bf16_lo(w.y), umma::bf16_hi(w.y));
+          }
+        } else {
+          b = __ldg(yr + f4);
+        }
         if (branch_site >= 0) {
           const uint32_t keep = keep4(ms, s, t, (uint32_t)branch_site, (uint32_t)f4);
           b.x = (keep & 1u) ? b.x * ms.scale : 0.f;
@@ -550,10 +563,10 @@ int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d
 
 int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,
                     const float* gamma, const float* beta, float eps, const MaskSource& ms,
-                    int branch_site, int out_site, cudaStream_t st, void* out16, uint32_t fmt) {
+                    int branch_site, int out_site, cudaStream_t st, void* out16, uint32_t fmt, const void* y16) {
   BFB_REQUIRE(d <= 4096, BFB200_ERR_UNSUPPORTED, "d_model %d > 4096", d);
   const int grid = stride_grid((n_rows + 7) / 8, 8);
-#define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, (uint16_t*)out16, fmt)
+#define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, (uint16_t*)out16, fmt, (const uint16_t*)y16)
   const int d4 = d >> 2;
   if (d4 <= 32) LAUNCH_LN(1);
   else if (d4 <= 64) LAUNCH_LN(2);
