@@ -27,13 +27,17 @@ namespace {
 
 constexpr int AT_DH = 64;
 constexpr int AT_M = 128;        // queries per CTA
-constexpr int AT_MAXKV = 256;    // keys per CTA
+constexpr int AT_MAXKV = 256;    // most keys a CTA attends to
 constexpr uint32_t AT_Q_BYTES = AT_M * 128;
-constexpr uint32_t AT_K_BYTES = AT_MAXKV * 128;
-constexpr uint32_t AT_V_BYTES = AT_MAXKV * 128;                // keys x 64 dims as delivered by TMA
-constexpr uint32_t AT_P_BYTES = (AT_MAXKV / 64) * AT_M * 128;  // 4 slabs of 128 rows x 64 keys, over Q | K | pad
-constexpr uint32_t AT_SMEM = 1024 + AT_P_BYTES + AT_V_BYTES;
-static_assert(AT_P_BYTES >= AT_Q_BYTES + AT_K_BYTES, "P must cover the Q and K tiles it overwrites");
+// shared memory of the variant that attends to at most MAXKV keys (128: the first query tile of a sequence, four
+// CTAs per SM; 256: the second tile, two CTAs per SM):  [ P slabs over Q | K ][ V ]
+template <int MAXKV> struct AtSmem {
+  static constexpr uint32_t K_BYTES = MAXKV * 128;
+  static constexpr uint32_t V_BYTES = MAXKV * 128;                   // keys x 64 dims as delivered by TMA
+  static constexpr uint32_t P_BYTES = (MAXKV / 64) * AT_M * 128;     // slabs of 128 rows x 64 keys
+  static constexpr uint32_t TOTAL = 1024 + P_BYTES + V_BYTES;
+  static_assert(P_BYTES >= AT_Q_BYTES + K_BYTES, "P must cover the Q and K tiles it overwrites");
+};
 
 __device__ __forceinline__ void at_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -46,7 +50,7 @@ struct AttnArgs {
   const uint16_t* qkv;   // (R, 3d)
   uint16_t* out;         // (R, d)
   int64_t n_rows;        // R = n_seq * len
-  int len, d, n_heads, m_tiles;
+  int len, d, n_heads, m_tile;   // this launch handles query tile m_tile of every (sequence, head)
   uint32_t fmt;
   float inv_sqrt_dh;
   int site;              // head-output dropout site or -1
@@ -57,28 +61,28 @@ __device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
   return fmt == umma::kFmtF16 ? umma::pack_f16x2(a, b) : umma::pack_bf16x2(a, b);
 }
 
-__global__ void __launch_bounds__(AT_M, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
-                                                               const AttnArgs a) {
+template <int MAXKV>
+__global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                                  const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
   uint8_t* sP = smem;                 // written only after S = Q K^T has completed
-  uint8_t* sV = smem + AT_P_BYTES;
+  uint8_t* sV = smem + AtSmem<MAXKV>::P_BYTES;
   __shared__ uint64_t bar_qk, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int mt = blockIdx.x % a.m_tiles;
-  const int h = (blockIdx.x / a.m_tiles) % a.n_heads;
-  const int64_t s = blockIdx.x / (a.m_tiles * a.n_heads);
-  const int m0 = mt * AT_M;
+  const int h = blockIdx.x % a.n_heads;
+  const int64_t s = blockIdx.x / a.n_heads;
+  const int m0 = a.m_tile * AT_M;
   const int kv_len = min(a.len, m0 + AT_M);
   const int kvp = (kv_len + 15) & ~15;
   const int64_t row_base = s * a.len;
 
   if (warp == 0) {
-    umma::tmem_alloc(&tmem_slot, 256);
+    umma::tmem_alloc(&tmem_slot, MAXKV);
     umma::tmem_relinquish();
   }
   if (tid == 0) {
@@ -122,8 +126,10 @@ __global__ void __launch_bounds__(AT_M, 2) attention_tc_kernel(const __grid_cons
   const int tq = m0 + tid;                       // query position inside the sequence
   const bool q_ok = tq < a.len;
   const int last_key = q_ok ? tq : -1;           // causal mask (generate_subsequent_mask, transformer.py:275-287)
+  // 32-key chunks past the last query of this warp are masked for all of its rows: no reads, P = 0 (warp-uniform)
+  const int warp_last_key = min(a.len - 1, m0 + warp * 32 + 31);
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < kvp; c0 += 32) {
+  for (int c0 = 0; c0 < kvp && c0 <= warp_last_key; c0 += 32) {
     uint32_t r[32];
     umma::tmem_ld32(tmem_base + lane_base + c0, r);
     umma::tmem_ld_wait();
@@ -133,14 +139,19 @@ __global__ void __launch_bounds__(AT_M, 2) attention_tc_kernel(const __grid_cons
   }
   float sum = 0.f;
   for (int c0 = 0; c0 < kvp; c0 += 32) {
-    uint32_t r[32];
-    umma::tmem_ld32(tmem_base + lane_base + c0, r);
-    umma::tmem_ld_wait();
     float e[32];
+    if (c0 <= warp_last_key) {
+      uint32_t r[32];
+      umma::tmem_ld32(tmem_base + lane_base + c0, r);
+      umma::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      e[i] = (c0 + i <= last_key) ? __expf((__uint_as_float(r[i]) - mx) * a.inv_sqrt_dh) : 0.f;
-      sum += e[i];
+      for (int i = 0; i < 32; ++i) {
+        e[i] = (c0 + i <= last_key) ? __expf((__uint_as_float(r[i]) - mx) * a.inv_sqrt_dh) : 0.f;
+        sum += e[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) e[i] = 0.f;
     }
     uint8_t* slab = sP + (c0 >> 6) * (AT_M * 128);
     const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(AT_M, 2) attention_tc_kernel(const __grid_cons
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem_base, 256);
+  if (warp == 0) umma::tmem_dealloc(tmem_base, MAXKV);
 }
 
 typedef CUresult (*AtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -246,14 +257,22 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.qkv = (const uint16_t*)qkv16; a.out = (uint16_t*)out16; a.n_rows = R;
-  a.len = len; a.d = d; a.n_heads = n_heads; a.m_tiles = (len + AT_M - 1) / AT_M;
+  a.len = len; a.d = d; a.n_heads = n_heads;
   a.fmt = fmt; a.inv_sqrt_dh = 1.0f / sqrtf((float)AT_DH); a.site = site; a.ms = ms;
-  const int64_t grid = n_seq * n_heads * a.m_tiles;
+  const int64_t grid = n_seq * n_heads;
   BFB_REQUIRE(grid <= 0x7FFFFFFF, BFB200_ERR_UNSUPPORTED, "too many attention tiles in one launch");
-  const size_t smem = AT_SMEM;
-  cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  attention_tc_kernel<<<(unsigned)grid, AT_M, smem, st>>>(map, a);
+  // one launch per query tile: tile 0 attends to <= 128 keys (48 KB of shared memory, 128 TMEM columns: four CTAs
+  // per SM), tile 1 to <= 256 (96 KB, 256 columns: two CTAs per SM)
+  cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<128>::TOTAL);
+  a.m_tile = 0;
+  attention_tc_kernel<128><<<(unsigned)grid, AT_M, AtSmem<128>::TOTAL, st>>>(map, a);
   BFB_LAUNCH_CHECK("attention_tc_kernel", st);
+  if (len > AT_M) {
+    cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<256>::TOTAL);
+    a.m_tile = 1;
+    attention_tc_kernel<256><<<(unsigned)grid, AT_M, AtSmem<256>::TOTAL, st>>>(map, a);
+    BFB_LAUNCH_CHECK("attention_tc_kernel", st);
+  }
   return BFB200_OK;
 }
 
