@@ -174,51 +174,71 @@ __global__ void __launch_bounds__(AQ_ROWS) acquire_tma_kernel(const float* __res
       const int st = (int)(k % n_stages);
       umma::mbar_wait(&full_bar[st], (uint32_t)((k / n_stages) & 1));
       float* row = stage_base + (size_t)st * AQ_ROWS * C + tid * C;
-      // The row is walked in rotated order with a warp-uniform trip count; the column is derived from the loop
-      // counter (no serial dependency between iterations).
-      float b1 = -INFINITY, b2 = -INFINITY, ent = 0.f;
+      // The row is walked in rotated order with a warp-uniform trip count, four columns per trip into four
+      // independent accumulator sets (a single warp per scheduler has nothing else to hide the latency of the
+      // max / sum / top-2 dependency chains with).
+      const int C4 = C & ~3;
+      float b1w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, b2w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float entw[4] = {0.f, 0.f, 0.f, 0.f};
+      float b1, b2, ent;
+      auto top2 = [](float& t1, float& t2, float v) {
+        t2 = fmaxf(t2, fminf(t1, v));
+        t1 = fmaxf(t1, v);
+      };
       if (IS_LOGP) {
         // probs = softmax(log-probs), as dropout_uncertainty does (active_learning.py:147):
         // e = exp(l - max), z = sum e, p = e / z.  The scores are taken on e and rescaled, and the entropy uses
         // log p = (l - max) - log z exactly (log(p + 1e-10) differs from it only where p < 1e-8).
-        float mx = -INFINITY;
-#pragma unroll 4
-        for (int j = 0; j < C; ++j) mx = fmaxf(mx, row[col(j)]);
-        float z = 0.f, el = 0.f;
-        auto body = [&](int c) {
+        float mxw[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int j = 0; j < C4; j += 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) mxw[w] = fmaxf(mxw[w], row[col(j + w)]);
+        }
+        for (int j = C4; j < C; ++j) mxw[0] = fmaxf(mxw[0], row[col(j)]);
+        const float mx = fmaxf(fmaxf(mxw[0], mxw[1]), fmaxf(mxw[2], mxw[3]));
+        float zw[4] = {0.f, 0.f, 0.f, 0.f};
+        auto body = [&](int c, int w) {
           const float d = row[c] - mx;
           const float e = __expf(d);
-          z += e;
-          if (need & 4u) el = fmaf(e, fmaxf(d, -1e30f), el);
-          if (need & 3u) {
-            b2 = fmaxf(b2, fminf(b1, e));
-            b1 = fmaxf(b1, e);
-          }
+          zw[w] += e;
+          if (need & 4u) entw[w] = fmaf(e, fmaxf(d, -1e30f), entw[w]);
+          if (need & 3u) top2(b1w[w], b2w[w], e);
           if (WANT_MEAN_P) row[c] = e;
         };
-#pragma unroll 4
-        for (int j = 0; j < C; ++j) body(col(j));
+        for (int j = 0; j < C4; j += 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) body(col(j + w), w);
+        }
+        for (int j = C4; j < C; ++j) body(col(j), 0);
+        const float z = (zw[0] + zw[1]) + (zw[2] + zw[3]);
         const float inv_z = 1.0f / z;
+        b1 = b1w[0]; b2 = b2w[0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) { top2(b1, b2, b2w[w]); top2(b1, b2, b1w[w]); }
         b1 *= inv_z;
         b2 *= inv_z;
-        ent = el * inv_z - __logf(z);   // sum p log p
+        ent = ((entw[0] + entw[1]) + (entw[2] + entw[3])) * inv_z - __logf(z);   // sum p log p
         if (WANT_MEAN_P) {
           auto accum = [&](int c) { acc[c] = t == 0 ? row[c] * inv_z : fmaf(row[c], inv_z, acc[c]); };
 #pragma unroll 4
           for (int j = 0; j < C; ++j) accum(col(j));
         }
       } else {
-        auto body = [&](int c) {
+        auto body = [&](int c, int w) {
           const float p = row[c];
-          if (need & 3u) {
-            b2 = fmaxf(b2, fminf(b1, p));
-            b1 = fmaxf(b1, p);
-          }
-          if (need & 4u) ent = fmaf(p, __logf(p + 1e-10f), ent);
+          if (need & 3u) top2(b1w[w], b2w[w], p);
+          if (need & 4u) entw[w] = fmaf(p, __logf(p + 1e-10f), entw[w]);
           if (WANT_MEAN_P) acc[c] = t == 0 ? p : acc[c] + p;
         };
-#pragma unroll 4
-        for (int j = 0; j < C; ++j) body(col(j));
+        for (int j = 0; j < C4; j += 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) body(col(j + w), w);
+        }
+        for (int j = C4; j < C; ++j) body(col(j), 0);
+        b1 = b1w[0]; b2 = b2w[0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) { top2(b1, b2, b2w[w]); top2(b1, b2, b1w[w]); }
+        ent = (entw[0] + entw[1]) + (entw[2] + entw[3]);
       }
       a_max += b1;
       a_margin += b1 - b2;
