@@ -263,3 +263,39 @@ def test_select_samples_uses_fused_kernel_and_agrees_with_exact_ranking(engine, 
     # different Philox streams per call: the overlap is bounded by the MC noise floor (~150/200 for
     # entropy on trained weights), far above chance (200*200/3000 = 13)
     assert len(set(picked) & set(exact)) >= 110
+
+
+def test_weight_updates_invalidate_the_packed_images(engine, dev, c2):
+    """Active-learning rounds fine-tune the model in place between acquisitions (reference utils.train,
+    src/libs/utils.py:68-78): the fp32 pack and the fp16 weight image must follow the parameters."""
+    import random
+
+    from bayesformer_b200.libs import preprocessing, utils
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    model = H.build_model(sd, float(z["p"]), True).to(dev)
+    prompts = torch.from_numpy(z["prompts"]).to(dev)
+    N = int(z["N"])
+    before = engine.mc_score_transformer(engine.scoring_pack(model, dev, 4, N), prompts, N, 4, "dropout", "entropy", seed=5)
+    pack_before = engine.scoring_pack(model, dev, 4, N)
+    assert engine.scoring_pack(model, dev, 4, N) is pack_before          # cached while the weights are unchanged
+    tok = ReversedPairingTokenizer()
+    random.seed(0)
+    data = preprocessing.create_dataset(64, 3)
+    with torch.enable_grad():
+        utils.train(model, data, data[:32], 1, 16, 1e-2, tok.ntokens, tok, dev)   # eager autograd, in-place AdamW steps
+    model.eval()
+    pack_after = engine.scoring_pack(model, dev, 4, N)
+    assert pack_after is not pack_before
+    after = engine.mc_score_transformer(pack_after, prompts, N, 4, "dropout", "entropy", seed=5)
+    assert not torch.allclose(after.step_scores, before.step_scores)
+    exact = engine.mc_score_transformer(model.native_pack(dev, "fp32"), prompts, N, 4, "dropout", "entropy", seed=5,
+                                        return_tokens=True)
+    forced = exact.tokens[:, 4:].t().contiguous()
+    again = engine.mc_score_transformer(pack_after, prompts, N, 4, "dropout", "entropy", seed=5, forced_tokens=forced)
+    np.testing.assert_allclose(again.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=2e-2, atol=2e-3)
+    # a deep copy (active_learning.ipynb cell 24) gets its own packs
+    import copy
+    clone = copy.deepcopy(model)
+    assert engine.scoring_pack(clone, dev, 4, N) is not pack_after
