@@ -332,22 +332,21 @@ __global__ void __launch_bounds__(128) mlp_mc_kernel(
     for (int t = 0; t < n_draws; ++t) {
       float logit = 0.f;
 #pragma unroll
-      for (int j4 = 0; j4 < HCAP / 4; ++j4) {
-        if (j4 * 4 < hidden) {
-          uint32_t keep;
+      for (int j8 = 0; j8 < HCAP / 8; ++j8) {
+        if (j8 * 8 < hidden) {
+          uint32_t keep;   // 8 hidden units per Philox call (16-bit decisions)
           if (mask_bits != nullptr) {
-            const uint32_t w = mask_bits[((int64_t)t * n_items + item) * words + (j4 >> 3)];
-            keep = (w >> ((j4 & 7) * 4)) & 0xFu;
+            const uint32_t w = mask_bits[((int64_t)t * n_items + item) * words + (j8 >> 2)];
+            keep = (w >> ((j8 & 3) * 8)) & 0xFFu;
           } else {
             const uint4 r = philox4x32_10(
                 make_uint4((uint32_t)(index_base + item), (uint32_t)t, 0u,
-                           (BFB200_SITE_MLP_HIDDEN << 16) | (uint32_t)j4), key);
-            keep = (r.x >= threshold ? 1u : 0u) | (r.y >= threshold ? 2u : 0u) |
-                   (r.z >= threshold ? 4u : 0u) | (r.w >= threshold ? 8u : 0u);
+                           (BFB200_SITE_MLP_HIDDEN << 16) | (uint32_t)j8), key);
+            keep = keep8_of(r, threshold);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = j4 * 4 + q;
+          for (int q = 0; q < 8; ++q) {
+            const int j = j8 * 8 + q;
             if (j < hidden && ((keep >> q) & 1u)) logit = fmaf(h[j] * scale, s_w2[j], logit);
           }
         }

@@ -83,12 +83,22 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// keep-threshold for drop probability p: keep iff word >= threshold.
+// Bernoulli decisions are taken on the 16-bit halves of the Philox words (two decisions per word, eight per
+// call): a feature is KEPT iff its half >= threshold16(p) = min(65535, floor(p * 65536)).  Keep probability
+// = 1 - threshold16 / 65536, i.e. p is resolved to 1.5e-5.
 __host__ inline uint32_t keep_threshold(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0;
   if (t <= 0.0) return 0u;
-  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  if (t >= 65535.0) return 65535u;
   return (uint32_t)t;
+}
+
+// 8 keep bits from one Philox call: bit j <- half (j & 1) of word (j >> 1)
+__host__ __device__ __forceinline__ uint32_t keep8_of(const uint4& r, uint32_t thr) {
+  return ((r.x & 0xFFFFu) >= thr ? 1u : 0u) | ((r.x >> 16) >= thr ? 2u : 0u) |
+         ((r.y & 0xFFFFu) >= thr ? 4u : 0u) | ((r.y >> 16) >= thr ? 8u : 0u) |
+         ((r.z & 0xFFFFu) >= thr ? 16u : 0u) | ((r.z >> 16) >= thr ? 32u : 0u) |
+         ((r.w & 0xFFFFu) >= thr ? 64u : 0u) | ((r.w >> 16) >= thr ? 128u : 0u);
 }
 
 // Where the dropout masks of one launch come from (see bfb200_masks).
@@ -108,7 +118,8 @@ struct MaskSource {
   uint32_t draw_base;    // used when n_draws == 1 (plain forward: draw id of the call)
 };
 
-// 4 keep bits (bit j = feature 4*f4 + j) for (local sequence s, position pos, site).
+// 4 keep bits (bit j = feature 4*f4 + j) for (local sequence s, position pos, site).  Philox counter =
+// (item, draw, step << 16 | pos, site << 16 | feature >> 3): one call covers 8 features.
 __device__ __forceinline__ uint32_t keep4(const MaskSource& m, int64_t s, uint32_t pos,
                                           uint32_t site, uint32_t f4) {
   if (m.bits != nullptr) {
@@ -119,10 +130,9 @@ __device__ __forceinline__ uint32_t keep4(const MaskSource& m, int64_t s, uint32
   }
   const uint64_t item = (uint64_t)(m.item_base + s / m.n_draws);
   const uint32_t draw = m.draw_base + (uint32_t)(s % m.n_draws);
-  const uint4 ctr = make_uint4((uint32_t)item, draw, (m.step << 16) | pos, (site << 16) | f4);
+  const uint4 ctr = make_uint4((uint32_t)item, draw, (m.step << 16) | pos, (site << 16) | (f4 >> 1));
   const uint4 r = philox4x32_10(ctr, m.key);
-  return (r.x >= m.threshold ? 1u : 0u) | (r.y >= m.threshold ? 2u : 0u) |
-         (r.z >= m.threshold ? 4u : 0u) | (r.w >= m.threshold ? 8u : 0u);
+  return (keep8_of(r, m.threshold) >> ((f4 & 1u) * 4u)) & 0xFu;
 }
 
 // ----------------------------------------------------------------------------

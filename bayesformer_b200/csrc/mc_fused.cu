@@ -171,123 +171,20 @@ __device__ __forceinline__ RowRng make_row_rng(const MaskSource& m, uint32_t s) 
   return r;
 }
 
-__device__ __forceinline__ uint32_t keep4_of(const uint4& r, uint32_t thr) {
-  return (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
-}
-
-// 64 keep bits of one (row, site) from the Philox stream: bit f = feature f.  Deliberately NOT inlined: the
-// seven dropout sites of the kernel share this one copy of the rounds (the kernel is instruction-fetch
-// sensitive); arguments are scalars so nothing spills to local memory at the call, and four counters are
-// advanced together so the rounds of independent streams interleave.
-__device__ __noinline__ uint64_t philox_keep64(uint32_t key_x, uint32_t key_y, uint32_t threshold, uint32_t item,
-                                               uint32_t draw, uint32_t c2, uint32_t c3) {
-  const uint2 key = make_uint2(key_x, key_y);
-  uint64_t out = 0;
-#pragma unroll 1
-  for (uint32_t f4 = 0; f4 < 16; f4 += 4) {
-    const uint4 r0 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 0)), key);
-    const uint4 r1 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 1)), key);
-    const uint4 r2 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 2)), key);
-    const uint4 r3 = philox4x32_10(make_uint4(item, draw, c2, c3 | (f4 + 3)), key);
-    const uint32_t k16 = keep4_of(r0, threshold) | (keep4_of(r1, threshold) << 4) |
-                         (keep4_of(r2, threshold) << 8) | (keep4_of(r3, threshold) << 12);
-    out |= (uint64_t)k16 << (4 * f4);
-  }
-  return out;
-}
-
-// 32 keep bits: features [4 * (c3 & 0xFFFF), ... + 32) of the (row, site) encoded in (c2, c3); same stream as
-// philox_keep64, eight counters, four advanced together
+// 32 keep bits of one half row from the Philox stream: features [8 * c3_call, 8 * c3_call + 32) of the (row, site)
+// encoded in (c2, c3): four calls of eight 16-bit decisions each.  Deliberately NOT inlined: the seven dropout
+// sites of the kernel share this one copy of the rounds (the kernel is instruction-fetch sensitive); arguments are
+// scalars so nothing spills to local memory at the call; the four counters advance together so the rounds of
+// independent streams interleave.
 __device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, uint32_t threshold, uint32_t item,
                                                uint32_t draw, uint32_t c2, uint32_t c3) {
   const uint2 key = make_uint2(key_x, key_y);
-  uint32_t out = 0;
-#pragma unroll 1
-  for (uint32_t f4 = 0; f4 < 8; f4 += 4) {
-    const uint4 r0 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 0), key);
-    const uint4 r1 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 1), key);
-    const uint4 r2 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 2), key);
-    const uint4 r3 = philox4x32_10(make_uint4(item, draw, c2, c3 + f4 + 3), key);
-    const uint32_t k16 = keep4_of(r0, threshold) | (keep4_of(r1, threshold) << 4) |
-                         (keep4_of(r2, threshold) << 8) | (keep4_of(r3, threshold) << 12);
-    out |= k16 << (4 * f4);
-  }
-  return out;
-}
-
-__device__ __forceinline__ uint64_t row_keep_mask(const MaskSource& m, uint32_t item, uint32_t draw, uint32_t seq_local,
-                                                  uint32_t pos, uint32_t site) {
-  if (m.bits != nullptr) {   // mask-injection mode: 64 bits = two packed words of the row
-    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + seq_local)) * m.max_len + pos;
-    const uint32_t* w = m.bits + row * m.words;
-    return (uint64_t)w[0] | ((uint64_t)w[1] << 32);
-  }
-  return philox_keep64(m.key.x, m.key.y, m.threshold, item, draw, (m.step << 16) | pos, site << 16);
-}
-
-// v[0..63] = keep ? v * scale : 0 for one row; `k` = row_keep_mask(...) taken BEFORE the row is loaded into
-// registers, so the call does not have to save 64 live values
-__device__ __forceinline__ void drop_row(float (&v)[FD], uint64_t k, float scale) {
-  const uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
-#pragma unroll
-  for (uint32_t j = 0; j < 32; ++j) {
-    v[j] = ((lo >> j) & 1u) ? v[j] * scale : 0.f;
-    v[32 + j] = ((hi >> j) & 1u) ? v[32 + j] * scale : 0.f;
-  }
-}
-
-__device__ __forceinline__ void store_row_f16(uint8_t* tile, uint32_t row, const float (&v)[FD]) {
-#pragma unroll
-  for (uint32_t c = 0; c < 8; ++c) {
-    uint4 w;
-    w.x = umma::pack_f16x2(v[8 * c + 0], v[8 * c + 1]);
-    w.y = umma::pack_f16x2(v[8 * c + 2], v[8 * c + 3]);
-    w.z = umma::pack_f16x2(v[8 * c + 4], v[8 * c + 5]);
-    w.w = umma::pack_f16x2(v[8 * c + 6], v[8 * c + 7]);
-    *reinterpret_cast<uint4*>(tile + umma::sw128_offset(row, c)) = w;
-  }
-}
-
-__device__ __forceinline__ void tmem_load_row64(uint32_t taddr, float (&v)[FD]) {
-  uint32_t a[32], b[32];
-  umma::tmem_ld32(taddr, a);
-  umma::tmem_ld32(taddr + 32, b);
-  umma::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = __uint_as_float(a[i]);
-    v[32 + i] = __uint_as_float(b[i]);
-  }
-}
-
-__device__ __forceinline__ void tmem_store_row64(uint32_t taddr, const float (&v)[FD]) {
-  uint32_t a[32], b[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    a[i] = __float_as_uint(v[i]);
-    b[i] = __float_as_uint(v[32 + i]);
-  }
-  umma::tmem_st32(taddr, a);
-  umma::tmem_st32(taddr + 32, b);
-  umma::tmem_st_wait();
-}
-
-// LayerNorm of one row held in registers (biased variance, eps inside the sqrt: nn.LayerNorm)
-__device__ __forceinline__ void layer_norm_row(float (&v)[FD], const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, float eps) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < FD; ++i) s += v[i];
-  const float mean = s * (1.0f / FD);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < FD; ++i) {
-    const float c = v[i] - mean;
-    q = fmaf(c, c, q);
-  }
-  const float rstd = rsqrtf(q * (1.0f / FD) + eps);
-#pragma unroll
-  for (int i = 0; i < FD; ++i) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+  const uint4 r0 = philox4x32_10(make_uint4(item, draw, c2, c3 + 0), key);
+  const uint4 r1 = philox4x32_10(make_uint4(item, draw, c2, c3 + 1), key);
+  const uint4 r2 = philox4x32_10(make_uint4(item, draw, c2, c3 + 2), key);
+  const uint4 r3 = philox4x32_10(make_uint4(item, draw, c2, c3 + 3), key);
+  return keep8_of(r0, threshold) | (keep8_of(r1, threshold) << 8) | (keep8_of(r2, threshold) << 16) |
+         (keep8_of(r3, threshold) << 24);
 }
 
 __device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
@@ -453,7 +350,7 @@ __device__ __forceinline__ uint32_t half_keep_mask(const MaskSource& m, const Ro
     const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + rr.seq_local)) * m.max_len + pos;
     return m.bits[row * m.words + h];
   }
-  return philox_keep32(m.key.x, m.key.y, m.threshold, rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (8u * h));
+  return philox_keep32(m.key.x, m.key.y, m.threshold, rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h));
 }
 
 __device__ __forceinline__ void store_half_f16(uint8_t* tile, uint32_t row, uint32_t h, const float (&v)[HW]) {

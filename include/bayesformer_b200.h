@@ -121,10 +121,10 @@ typedef struct bfb200_transformer {
 /*
  * Source of dropout masks.
  *  - bits == NULL: counter-based Philox4x32-10, key = (seed_lo, seed_hi), counter =
- *      (global item index, draw, (step << 16) | position, (site << 16) | (feature >> 2));
- *      feature f uses output word f & 3 and is KEPT iff word >= keep_threshold(p) =
- *      min(2^32 - 1, floor(p * 2^32)).  Results do not depend on batching, chunking
- *      or the GPU a pool item lands on.
+ *      (global item index, draw, (step << 16) | position, (site << 16) | (feature >> 3));
+ *      one call decides 8 features: feature f uses the 16-bit half (f & 1) of output word (f >> 1) & 3
+ *      and is KEPT iff half >= min(65535, floor(p * 65536)) (p resolved to 1.5e-5).  Results do not
+ *      depend on batching, chunking or the GPU a pool item lands on.
  *  - bits != NULL (mask-injection mode used by the parity tests): bit-packed keep
  *      masks, little-endian bit order inside uint32 words, laid out
  *      [step][site][sequence][position < max_len][ceil(d/32) words]

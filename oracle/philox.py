@@ -35,34 +35,44 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def keep_threshold(p: float) -> int:
-    """keep iff word >= threshold; mirrors bfb::keep_threshold (common.cuh)."""
-    t = float(np.float32(p)) * 4294967296.0
+    """16-bit decision threshold: keep iff half-word >= threshold; mirrors bfb::keep_threshold (common.cuh)."""
+    t = float(np.float32(p)) * 65536.0
     if t <= 0.0:
         return 0
-    if t >= 4294967295.0:
-        return 0xFFFFFFFF
+    if t >= 65535.0:
+        return 65535
     return int(t)
+
+
+def _keep8(words, thr: int) -> np.ndarray:
+    """(..., 8) bool from the four uint32 output words of one call: bit j <- half (j & 1) of word (j >> 1)
+    (bfb::keep8_of)."""
+    thr = np.uint32(thr)
+    halves = []
+    for w in words:
+        halves.append((w & np.uint32(0xFFFF)) >= thr)
+        halves.append((w >> np.uint32(16)) >= thr)
+    return np.stack(halves, axis=-1)
 
 
 def dropout_keep(seed: int, p: float, items, draws, step: int, site: int, n_pos: int, d: int) -> np.ndarray:
     """Keep mask (n_seq, n_pos, d) bool for sequences given by parallel arrays (items, draws).
 
-    Counter = (item, draw, (step << 16) | pos, (site << 16) | (feature >> 2)); feature f uses word f & 3
-    (include/bayesformer_b200.h, `bfb200_masks`).
+    Counter = (item, draw, (step << 16) | pos, (site << 16) | (feature >> 3)); feature f uses the 16-bit half
+    f & 1 of word (f >> 1) & 3 (include/bayesformer_b200.h, `bfb200_masks`).
     """
     items = np.asarray(items, dtype=np.uint64)
     draws = np.asarray(draws, dtype=np.uint32)
     n_seq = items.shape[0]
-    d4 = (d + 3) // 4
+    d8 = (d + 7) // 8
     c0 = (items & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None, None]
     c1 = draws[:, None, None]
     pos = np.arange(n_pos, dtype=np.uint32)[None, :, None]
     c2 = (np.uint32(step) << np.uint32(16)) | pos
-    f4 = np.arange(d4, dtype=np.uint32)[None, None, :]
-    c3 = (np.uint32(site) << np.uint32(16)) | f4
+    f8 = np.arange(d8, dtype=np.uint32)[None, None, :]
+    c3 = (np.uint32(site) << np.uint32(16)) | f8
     words = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    thr = np.uint32(keep_threshold(p))
-    keep = np.stack([w >= thr for w in words], axis=-1).reshape(n_seq, n_pos, d4 * 4)
+    keep = _keep8(words, keep_threshold(p)).reshape(n_seq, n_pos, d8 * 8)
     return keep[:, :, :d]
 
 
@@ -79,11 +89,10 @@ def sampling_uniform(seed: int, items, draws, step: int) -> np.ndarray:
 def mlp_keep(seed: int, p: float, items, n_draws: int, hidden: int) -> np.ndarray:
     """Keep mask (T, B, hidden) of the MLP hidden-layer dropout (site 0x100, step 0, pos 0)."""
     items = np.asarray(items, dtype=np.uint64)
-    h4 = (hidden + 3) // 4
+    h8 = (hidden + 7) // 8
     c0 = (items & np.uint64(0xFFFFFFFF)).astype(np.uint32)[None, :, None]
     c1 = np.arange(n_draws, dtype=np.uint32)[:, None, None]
-    c3 = (np.uint32(0x100) << np.uint32(16)) | np.arange(h4, dtype=np.uint32)[None, None, :]
+    c3 = (np.uint32(0x100) << np.uint32(16)) | np.arange(h8, dtype=np.uint32)[None, None, :]
     words = philox4x32_10(c0, c1, np.uint32(0), c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    thr = np.uint32(keep_threshold(p))
-    keep = np.stack([w >= thr for w in words], axis=-1).reshape(n_draws, items.shape[0], h4 * 4)
+    keep = _keep8(words, keep_threshold(p)).reshape(n_draws, items.shape[0], h8 * 8)
     return keep[:, :, :hidden]

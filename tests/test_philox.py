@@ -29,7 +29,8 @@ def test_vectorised_matches_scalar():
 
 def test_keep_rate_and_threshold():
     assert philox.keep_threshold(0.0) == 0
-    assert philox.keep_threshold(0.5) == 2**31
+    assert philox.keep_threshold(0.5) == 2**15
+    assert philox.keep_threshold(1.0) == 65535
     keep = philox.dropout_keep(42, 0.3, np.arange(64), np.zeros(64, dtype=np.uint32), 0, 0, 8, 64)
     assert keep.shape == (64, 8, 64)
     assert abs(keep.mean() - 0.7) < 0.01
