@@ -241,6 +241,75 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// causal attention for short sequences and narrow heads (len <= 8, dh == 8: the notebook model on the fp32 path).
+// thread = (sequence, head): K and V of the pair live in registers, queries are walked in order; consecutive
+// threads read consecutive heads of one row = 256 contiguous bytes.  Same arithmetic as attention_kernel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_small_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                              int64_t n_seq, int len, int d, int n_heads, float sqrt_dh,
+                                                              MaskSource ms, int site) {
+  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_seq * n_heads) return;
+  const int64_t s = pair / n_heads;
+  const int h = (int)(pair - s * n_heads);
+  const float* base = qkv + s * len * 3 * (int64_t)d + h * 8;
+  float k[8][8], v[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < len) {
+      const float4* kr = reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + d);
+      const float4* vr = reinterpret_cast<const float4*>(base + (int64_t)j * 3 * d + 2 * d);
+      const float4 k0 = __ldg(kr), k1 = __ldg(kr + 1), v0 = __ldg(vr), v1 = __ldg(vr + 1);
+      k[j][0] = k0.x; k[j][1] = k0.y; k[j][2] = k0.z; k[j][3] = k0.w; k[j][4] = k1.x; k[j][5] = k1.y; k[j][6] = k1.z; k[j][7] = k1.w;
+      v[j][0] = v0.x; v[j][1] = v0.y; v[j][2] = v0.z; v[j][3] = v0.w; v[j][4] = v1.x; v[j][5] = v1.y; v[j][6] = v1.z; v[j][7] = v1.w;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (t < len) {
+      const float4* qr = reinterpret_cast<const float4*>(base + (int64_t)t * 3 * d);
+      const float4 q0 = __ldg(qr), q1 = __ldg(qr + 1);
+      const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      float sc[8];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j <= t; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a = fmaf(q[c], k[j][c], a);
+        a = a / sqrt_dh;
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+      }
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j <= t; ++j) {
+        sc[j] = expf(sc[j] - mx);
+        z += sc[j];
+      }
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j <= t; ++j) {
+        const float pj = sc[j] / z;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, v[j][c], o[c]);
+      }
+      if (site >= 0) {
+#pragma unroll
+        for (int f4 = 0; f4 < 2; ++f4) {
+          const uint32_t keep = keep4(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)(h * 2 + f4));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[4 * f4 + c] = ((keep >> c) & 1u) ? o[4 * f4 + c] * ms.scale : 0.f;
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(out + (s * len + t) * (int64_t)d + h * 8);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // out = dropout_out( LayerNorm(x + dropout_branch(y)) )     (transformer.py:226-233, :370)
 // one warp per row, 128-bit loads, statistics by warp shuffle; biased variance, eps inside
 // the square root (nn.LayerNorm).
@@ -539,6 +608,13 @@ int launch_sgemm(const float* A, const float* W, const float* bias, float* C, in
 int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d, int n_heads,
                      const MaskSource& ms, int site, cudaStream_t st) {
   const int dh = d / n_heads;
+  if (dh == 8 && len <= 8) {
+    const int64_t pairs = n_seq * n_heads;
+    attention_small_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(qkv, out, n_seq, len, d, n_heads,
+                                                                            sqrtf((float)dh), ms, site);
+    BFB_LAUNCH_CHECK("attention_small_kernel", st);
+    return BFB200_OK;
+  }
   const size_t smem = ((size_t)len * (2 * dh + 1) + 4 * (size_t)dh + 4 * (size_t)len) * sizeof(float);
   BFB_REQUIRE(len <= 1024, BFB200_ERR_UNSUPPORTED, "sequence length %d > 1024", len);
   BFB_REQUIRE(smem <= 227 * 1024, BFB200_ERR_UNSUPPORTED,
