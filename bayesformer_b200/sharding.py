@@ -87,3 +87,38 @@ def select_samples_sharded(model, local_prompts: torch.Tensor, new_tokens: int, 
             final = engine.merge_topk_keys(gather_candidate_keys(keys, nb_samples, group), nb_samples)
         _, idx = engine.unpack_keys(final)
         return idx.tolist()
+
+
+def repad_prompts(prompts: torch.Tensor, prompt_len: int, pad_id: int) -> torch.Tensor:
+    """Left-pad a shard's `(P_local, B)` prompts with PAD to the GLOBAL prompt length (the reference pads every
+    prompt of the pool to the pool-wide maximum, preprocessing.py:59-64)."""
+    p_local, n = prompts.shape
+    if p_local > prompt_len:
+        raise ValueError("global prompt length smaller than a shard's")
+    if p_local == prompt_len:
+        return prompts
+    pad = torch.full((prompt_len - p_local, n), pad_id, dtype=prompts.dtype, device=prompts.device)
+    return torch.cat((pad, prompts), 0)
+
+
+def select_samples_distributed(model, tokenizer, pool_dataset, device, nb_samples: int = 200, compute: str = "dropout",
+                               mode: str = "max", seed: int | None = None, n_draws: int = 20, group=None) -> list[int]:
+    """`select_samples(model, tokenizer, pool_dataset, device, ...)` (reference active_learning.py:158-211) with the
+    pool sharded over the ranks of `group`: every rank passes the SAME full `pool_dataset`, tokenises only its own
+    contiguous shard, agrees on the global prompt / answer lengths with one 2-element all-reduce(MAX) (set-up, not
+    the data path), scores its shard and exchanges k candidate keys.  Every rank returns the same global indices."""
+    from bayesformer_b200.configs import constants
+    from bayesformer_b200.libs import preprocessing
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(pool_dataset), world, rank)
+    model.eval()
+    prompts, _, p_len, a_len, _, _ = preprocessing.get_batch(pool_dataset, tokenizer, lo, hi - lo)
+    dims = torch.tensor([p_len, a_len], dtype=torch.int64, device=torch.device(device))
+    if world > 1:
+        dist.all_reduce(dims, op=dist.ReduceOp.MAX, group=group)
+    p_len, a_len = int(dims[0]), int(dims[1])
+    prompts = repad_prompts(prompts, p_len, tokenizer.token_to_id[constants.PAD_TOKEN])
+    return select_samples_sharded(model, prompts, a_len + 1, device, nb_samples=nb_samples, compute=compute, mode=mode,
+                                  index_base=lo, n_total=len(pool_dataset), seed=seed, n_draws=n_draws, group=group)

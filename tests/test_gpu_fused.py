@@ -299,3 +299,34 @@ def test_weight_updates_invalidate_the_packed_images(engine, dev, c2):
     import copy
     clone = copy.deepcopy(model)
     assert engine.scoring_pack(clone, dev, 4, N) is not pack_after
+
+
+def test_sharded_selection_equals_single_device_selection(engine, dev, c2):
+    """a pool scored as G shards (global index bases, same seed) and merged through the candidate keys
+    acquires exactly the indices of the unsharded run — 1-GPU and 8-GPU runs agree bit for bit."""
+    import random
+
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    tok = ReversedPairingTokenizer()
+    random.seed(9)
+    pool = preprocessing.create_dataset(4003, 3)
+    X, _, P, A, _, _ = preprocessing.get_batch(pool, tok, 0, len(pool))
+    X = X.to(dev)
+    model = H.build_model(sd, float(z["p"]), True).to(dev)
+    pack = engine.scoring_pack(model, dev, P, A + 1)
+    k, seed, G = 200, 1234, 8
+    whole = engine.mc_score_transformer(pack, X, A + 1, 20, "dropout", "entropy", seed=seed)
+    _, want = engine.unpack_keys(engine.topk_keys(whole.pool_scores, k))
+    keys = []
+    n = X.shape[1]
+    for g in range(G):
+        lo, hi = n * g // G, n * (g + 1) // G
+        part = engine.mc_score_transformer(pack, X[:, lo:hi].contiguous(), A + 1, 20, "dropout", "entropy", seed=seed,
+                                           index_base=lo)
+        assert torch.equal(part.pool_scores, whole.pool_scores[lo:hi])
+        keys.append(engine.topk_keys(part.pool_scores, k, index_base=lo))
+    _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
+    assert torch.equal(got, want)

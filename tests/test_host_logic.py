@@ -191,3 +191,20 @@ def test_vectorised_pool_tokenisation_is_bit_identical():
     t0 = time.perf_counter()
     preprocessing.get_batch(big, tok, 0, len(big))
     assert time.perf_counter() - t0 < 2.0   # the per-item path needs ~2.2 s for 100 k items
+
+
+def test_repad_prompts_matches_whole_pool_padding():
+    """A shard whose prompts are all short is padded up to the pool-wide prompt length, exactly as the reference's
+    whole-pool get_batch would have padded it."""
+    from bayesformer_b200 import sharding
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    tok = ReversedPairingTokenizer()
+    pool = [("007+003=", "10"), ("000+009=", "9")] * 40 + [("440+420=", "860")] * 80
+    X, _, P, _, _, _ = preprocessing.get_batch(pool, tok, 0, len(pool))
+    Xa, _, Pa, _, _, _ = preprocessing.get_batch(pool, tok, 0, 80)
+    assert Pa < P
+    assert torch.equal(sharding.repad_prompts(Xa, P, tok.token_to_id["<PAD>"] if "<PAD>" in tok.token_to_id else 112), X[:, :80])
+    with pytest.raises(ValueError):
+        sharding.repad_prompts(X, Pa, 112)
