@@ -2,8 +2,9 @@
 // 8 heads, sequences of up to 256 tokens).  Reference arithmetic: src/model/transformer.py:58-65 (per head:
 // softmax(Q K^T / sqrt(dh) + causal mask) V) and :116-124 (optional head-output dropout, concatenation).
 //
-// One CTA (128 threads) per (sequence, head, tile of 128 queries); two CTAs share an SM (96 KB of shared memory and
-// 256 TMEM columns each), so one CTA's softmax overlaps the other's copies and tensor-core work:
+// One CTA (256 threads: two per query row, alternating 32-key chunks) per (sequence, head, tile of 128 queries);
+// two to four CTAs share an SM (48 / 96 KB of shared memory, 128 / 256 TMEM columns each), so one CTA's softmax
+// overlaps the others' copies and tensor-core work:
 //   1. one thread issues 2-D TMA loads (128-byte swizzle) of the Q tile and of the K and V rows this tile can attend
 //      to, straight out of the packed (R, 3d) QKV activation;
 //   2. S = Q K^T: tcgen05.mma M = 128, N = keys (<= 256), K = 64, fp32 accumulator in 256 TMEM columns;
@@ -62,7 +63,7 @@ __device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
 }
 
 template <int MAXKV>
-__global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                                   const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -72,8 +73,10 @@ __global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kerne
   uint8_t* sV = smem + AtSmem<MAXKV>::P_BYTES;
   __shared__ uint64_t bar_qk, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_max[2][AT_M], s_sum[2][AT_M];
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (AT_M - 1), half = tid >> 7;   // warps w and w + 4 share TMEM lane quarter w & 3
   const int h = blockIdx.x % a.n_heads;
   const int64_t s = blockIdx.x / a.n_heads;
   const int m0 = a.m_tile * AT_M;
@@ -121,15 +124,15 @@ __global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kerne
   umma::mbar_wait(&bar_s, 0);
   umma::tc_fence_after_sync();
 
-  // ---- softmax over the keys j <= query position, thread = query row ----
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const int tq = m0 + tid;                       // query position inside the sequence
+  // ---- softmax over the keys j <= query position; two threads per query row, alternating 32-key chunks ----
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int tq = m0 + row;                       // query position inside the sequence
   const bool q_ok = tq < a.len;
   const int last_key = q_ok ? tq : -1;           // causal mask (generate_subsequent_mask, transformer.py:275-287)
   // 32-key chunks past the last query of this warp are masked for all of its rows: no reads, P = 0 (warp-uniform)
-  const int warp_last_key = min(a.len - 1, m0 + warp * 32 + 31);
+  const int warp_last_key = min(a.len - 1, m0 + (warp & 3) * 32 + 31);
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < kvp && c0 <= warp_last_key; c0 += 32) {
+  for (int c0 = 32 * half; c0 < kvp && c0 <= warp_last_key; c0 += 64) {
     uint32_t r[32];
     umma::tmem_ld32(tmem_base + lane_base + c0, r);
     umma::tmem_ld_wait();
@@ -137,8 +140,11 @@ __global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kerne
     for (int i = 0; i < 32; ++i)
       if (c0 + i <= last_key) mx = fmaxf(mx, __uint_as_float(r[i]));
   }
+  s_max[half][row] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, s_max[half ^ 1][row]);
   float sum = 0.f;
-  for (int c0 = 0; c0 < kvp; c0 += 32) {
+  for (int c0 = 32 * half; c0 < kvp; c0 += 64) {
     float e[32];
     if (c0 <= warp_last_key) {
       uint32_t r[32];
@@ -160,12 +166,14 @@ __global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kerne
       uint4 w;
       w.x = at_pack2(e[8 * c], e[8 * c + 1], a.fmt); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], a.fmt);
       w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], a.fmt); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], a.fmt);
-      *reinterpret_cast<uint4*>(slab + umma::sw128_offset(tid, ch0 + c)) = w;
+      *reinterpret_cast<uint4*>(slab + umma::sw128_offset(row, ch0 + c)) = w;
     }
   }
+  s_sum[half][row] = sum;
   umma::fence_async_smem();
   umma::tc_fence_before_sync();
   __syncthreads();
+  sum += s_sum[half ^ 1][row];
 
   // ---- O = P V ----
   if (tid == 0) {
@@ -185,31 +193,27 @@ __global__ void __launch_bounds__(AT_M, MAXKV == 128 ? 4 : 2) attention_tc_kerne
   umma::mbar_wait(&bar_o, 0);
   umma::tc_fence_after_sync();
 
-  // ---- epilogue ----
+  // ---- epilogue: thread (row, half) takes output dims [32 half, 32 half + 32) ----
   {
-    uint32_t r0[32], r1[32];
-    umma::tmem_ld32(tmem_base + lane_base, r0);
-    umma::tmem_ld32(tmem_base + lane_base + 32, r1);
+    uint32_t r0[32];
+    umma::tmem_ld32(tmem_base + lane_base + 32 * half, r0);
     umma::tmem_ld_wait();
     if (q_ok) {
       const float inv = 1.0f / sum;
-      float o[AT_DH];
+      float o[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = __uint_as_float(r0[i]) * inv;
-        o[32 + i] = __uint_as_float(r1[i]) * inv;
-      }
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r0[i]) * inv;
       if (a.site >= 0) {   // transformer.py:116-122
 #pragma unroll
-        for (int f4 = 0; f4 < AT_DH / 4; ++f4) {
-          const uint32_t keep = keep4(a.ms, s, (uint32_t)tq, (uint32_t)a.site, (uint32_t)(h * (AT_DH / 4) + f4));
+        for (int f4 = 0; f4 < 8; ++f4) {
+          const uint32_t keep = keep4(a.ms, s, (uint32_t)tq, (uint32_t)a.site, (uint32_t)(h * (AT_DH / 4) + 8 * half + f4));
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[4 * f4 + q] = ((keep >> q) & 1u) ? o[4 * f4 + q] * a.ms.scale : 0.f;
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(a.out + (row_base + tq) * (int64_t)a.d + h * AT_DH);
+      uint4* dst = reinterpret_cast<uint4*>(a.out + (row_base + tq) * (int64_t)a.d + h * AT_DH + 32 * half);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint4 w;
         w.x = at_pack2(o[8 * c], o[8 * c + 1], a.fmt); w.y = at_pack2(o[8 * c + 2], o[8 * c + 3], a.fmt);
         w.z = at_pack2(o[8 * c + 4], o[8 * c + 5], a.fmt); w.w = at_pack2(o[8 * c + 6], o[8 * c + 7], a.fmt);
@@ -265,12 +269,12 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   // per SM), tile 1 to <= 256 (96 KB, 256 columns: two CTAs per SM)
   cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<128>::TOTAL);
   a.m_tile = 0;
-  attention_tc_kernel<128><<<(unsigned)grid, AT_M, AtSmem<128>::TOTAL, st>>>(map, a);
+  attention_tc_kernel<128><<<(unsigned)grid, 2 * AT_M, AtSmem<128>::TOTAL, st>>>(map, a);
   BFB_LAUNCH_CHECK("attention_tc_kernel", st);
   if (len > AT_M) {
     cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<256>::TOTAL);
     a.m_tile = 1;
-    attention_tc_kernel<256><<<(unsigned)grid, AT_M, AtSmem<256>::TOTAL, st>>>(map, a);
+    attention_tc_kernel<256><<<(unsigned)grid, 2 * AT_M, AtSmem<256>::TOTAL, st>>>(map, a);
     BFB_LAUNCH_CHECK("attention_tc_kernel", st);
   }
   return BFB200_OK;
