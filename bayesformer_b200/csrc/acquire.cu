@@ -116,169 +116,282 @@ __global__ void __launch_bounds__(256) acquire_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------------------
 // HBM-streaming acquisition kernel for n_classes <= 128 (SURVEY 8d "Acquisition kernel standalone").
 // A tile of 128 consecutive items of one draw is a contiguous byte range of x, so it is fetched by ONE 1-D bulk
-// TMA copy (cp.async.bulk -> shared memory, completion on an mbarrier) into a ring of stages; the copy engine
-// keeps HBM busy while the 128 threads each reduce their own item from shared memory (thread = item: no
-// shuffles, 32 items per warp instruction).  A thread walks its row starting at a thread-dependent rotation when
-// n_classes is even, which makes the stride-C shared-memory reads conflict-free for every C.
-// Draws are visited in index order and divided by T at the end, as the reference's `uncertainties += ...` loop.
+// TMA copy (cp.async.bulk -> shared memory, completion on an mbarrier) into a ring of stages.  Sixteen warps drain
+// the ring; each releases a stage (per-stage "empty" barrier) as soon as its rows are in registers, and one lane
+// refills released stages opportunistically (it only blocks when the load it is about to consume is missing).  An item is
+// owned by FOUR adjacent lanes (a warp = 8 items): each lane pulls its quarter of the row from shared memory into
+// registers with 64-bit loads (32-bit when n_classes is odd), releases the stage at once, and reduces in
+// registers; the four partial results meet through two xor-shuffles.  The predictive mean accumulates in
+// registers across the draws, so a row is read from shared memory exactly once per draw.
+// Bank conflicts: item i starts its walk at a rotation s_i chosen so that the 4 (8 for 32-bit loads) items served
+// by one shared-memory wavefront start 4 load-units apart: conflict-free for every n_classes.
+// Draws are visited in index order and divided by T at the end, as the reference's `uncertainties += ...` loop
+// (active_learning.py:141-155).
 // ---------------------------------------------------------------------------
-constexpr int AQ_ROWS = 128;
+constexpr int AQ_ROWS = 128;                      // items per tile
+constexpr int AQ_SPLIT = 4;                       // lanes per item
+constexpr int AQ_CONSUMERS = AQ_ROWS * AQ_SPLIT;  // 16 consumer warps
+constexpr int AQ_THREADS = AQ_CONSUMERS;          // lane 0 of warp 0 doubles as the producer (a 17th warp would
+                                                  // cost every thread a quarter of its registers)
+constexpr int AQ_MAX_STAGES = 8;
 
-template <bool IS_LOGP, bool WANT_MEAN_P>
-__global__ void __launch_bounds__(AQ_ROWS) acquire_tma_kernel(const float* __restrict__ x, int n_draws,
-                                                               int64_t n_items, int64_t n_tiles, int n_classes,
-                                                               int n_stages, uint32_t need,  // bit0 max, 1 margin, 2 entropy
-                                                               float* __restrict__ mean_p,
-                                                               float* __restrict__ score_of_mean,
-                                                               float* __restrict__ mean_of_scores,
-                                                               float* __restrict__ single_out, int single_mode) {
+__device__ __forceinline__ void aq_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float aq_ex2(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void aq_top2(float& t1, float& t2, float v) {
+  t2 = fmaxf(t2, fminf(t1, v));
+  t1 = fmaxf(t1, v);
+}
+// merge the (largest, second largest) pairs of the four lanes of an item
+__device__ __forceinline__ void aq_top2_quad(float& b1, float& b2) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+    const float o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+    b2 = fmaxf(fminf(b1, o1), fmaxf(b2, o2));
+    b1 = fmaxf(b1, o1);
+  }
+}
+__device__ __forceinline__ float aq_sum_quad(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// VEC = floats per shared-memory load (2 when n_classes is even); NSTEPS = loads per lane and draw
+// (ceil(ceil(C / VEC) / 4) <= NSTEPS).
+template <int VEC, int NSTEPS, bool IS_LOGP, bool WANT_MEAN_P>
+__global__ void __launch_bounds__(AQ_THREADS, 1) acquire_tma_kernel(const float* __restrict__ x, int n_draws,
+                                                                     int64_t n_items, int64_t n_tiles, int n_classes,
+                                                                     int n_stages, uint32_t need,  // bit0 max, 1 margin, 2 entropy
+                                                                     float* __restrict__ mean_p,
+                                                                     float* __restrict__ score_of_mean,
+                                                                     float* __restrict__ mean_of_scores,
+                                                                     float* __restrict__ single_out, int single_mode) {
   extern __shared__ __align__(128) uint8_t aq_smem[];
-  __shared__ uint64_t full_bar[4];
+  __shared__ uint64_t full_bar[AQ_MAX_STAGES], empty_bar[AQ_MAX_STAGES];
+  constexpr int NV = NSTEPS * VEC;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int C = n_classes;
   const uint32_t tile_bytes = (uint32_t)AQ_ROWS * C * 4u;
-  float* stage_base = reinterpret_cast<float*>(aq_smem);
-  float* acc_tile = WANT_MEAN_P ? stage_base + (size_t)n_stages * AQ_ROWS * C : nullptr;
   const int tid = threadIdx.x;
   const int64_t draw_stride = n_items * (int64_t)C;
 
   if (tid == 0) {
-    for (int i = 0; i < n_stages; ++i) umma::mbar_init(&full_bar[i], 1);
+    for (int i = 0; i < n_stages; ++i) {
+      umma::mbar_init(&full_bar[i], 1);
+      umma::mbar_init(&empty_bar[i], AQ_CONSUMERS / 32);
+    }
     umma::fence_mbar_init();
   }
   __syncthreads();
 
   // flattened sequence of (tile, draw) loads of this CTA; load k goes to stage k % n_stages
   const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int64_t n_loads = my_tiles * n_draws;
-  auto issue = [&](int64_t k) {
-    const int64_t tile = blockIdx.x + (k / n_draws) * gridDim.x;
-    const int t = (int)(k % n_draws);
-    const int st = (int)(k % n_stages);
-    umma::mbar_expect_tx(&full_bar[st], tile_bytes);
-    umma::bulk_g2s(stage_base + (size_t)st * AQ_ROWS * C, x + t * draw_stride + tile * AQ_ROWS * (int64_t)C, tile_bytes,
-                   &full_bar[st]);
-  };
-  if (tid == 0)
-    for (int64_t k = 0; k < n_stages && k < n_loads; ++k) issue(k);
 
-  const int rot = (C & 1) ? 0 : tid % C;   // even C: start column differs per thread -> no bank conflicts
-  auto col = [&](int j) { const int c = rot + j; return c >= C ? c - C : c; };
+  // ---- consumers ----
+  const int lane = tid & 31;
+  const int q = lane & (AQ_SPLIT - 1);
+  const int i_tile = tid >> 2;                     // item of the tile
+  const int nvec = (C + VEC - 1) / VEC;            // load units per row (VEC == 2 only for even C)
+  constexpr int NB = 32 / VEC, G = NB / AQ_SPLIT;  // load units per wavefront; items per wavefront
+  int rot = (AQ_SPLIT * (i_tile % G) - (int)(((int64_t)i_tile * (C / VEC)) % NB)) % NB;
+  if (rot < 0) rot += NB;
+  rot %= nvec;
+  uint32_t off[NSTEPS];      // byte offset inside a stage of this lane's j-th load unit (valid iff 4j + q < nvec)
+#pragma unroll
+  for (int j = 0; j < NSTEPS; ++j) {
+    int v = AQ_SPLIT * j + q + rot;
+    if (v >= nvec) v -= nvec;
+    off[j] = AQ_SPLIT * j + q < nvec ? (uint32_t)(i_tile * C + v * VEC) * 4u : 0u;
+  }
+  const float pad = IS_LOGP ? -INFINITY : 0.f;
   const float inv_t = 1.0f / (float)n_draws;
-  int64_t k = 0;
+  int st = 0;
+  uint32_t phase = 0;
+
+  // producer state (thread 0 only): loads issued so far, and where the next one goes
+  const int64_t n_loads = my_tiles * n_draws;
+  int64_t issued = 0, consumed = 0, p_it = 0;
+  int p_t = 0, p_st = 0;
+  uint32_t p_phase = 0;
+  auto produce = [&](bool block) {
+    while (issued < n_loads) {
+      if (issued >= n_stages) {   // the stage must have been released by all sixteen warps
+        if (block) {
+          umma::mbar_wait(&empty_bar[p_st], p_phase ^ 1u);
+        } else {
+          uint32_t done;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(done)
+              : "r"(umma::smem_u32(&empty_bar[p_st])), "r"(p_phase ^ 1u)
+              : "memory");
+          if (!done) break;
+        }
+      }
+      const float* src = x + (blockIdx.x + p_it * gridDim.x) * AQ_ROWS * (int64_t)C + p_t * draw_stride;
+      umma::mbar_expect_tx(&full_bar[p_st], tile_bytes);
+      umma::bulk_g2s(aq_smem + (size_t)p_st * tile_bytes, src, tile_bytes, &full_bar[p_st]);
+      ++issued;
+      if (++p_t == n_draws) { p_t = 0; ++p_it; }
+      if (++p_st == n_stages) { p_st = 0; p_phase ^= 1u; }
+      block = false;
+    }
+  };
+  if (tid == 0) produce(false);
   for (int64_t it = 0; it < my_tiles; ++it) {
     const int64_t tile = blockIdx.x + it * gridDim.x;
-    const int64_t item = tile * AQ_ROWS + tid;
+    const int64_t item = tile * AQ_ROWS + i_tile;
     float a_max = 0.f, a_margin = 0.f, a_ent = 0.f;
-    float* acc = WANT_MEAN_P ? acc_tile + tid * C : nullptr;
-    for (int t = 0; t < n_draws; ++t, ++k) {
-      const int st = (int)(k % n_stages);
-      umma::mbar_wait(&full_bar[st], (uint32_t)((k / n_stages) & 1));
-      float* row = stage_base + (size_t)st * AQ_ROWS * C + tid * C;
-      // The row is walked in rotated order with a warp-uniform trip count, four columns per trip into four
-      // independent accumulator sets (a single warp per scheduler has nothing else to hide the latency of the
-      // max / sum / top-2 dependency chains with).
-      const int C4 = C & ~3;
-      float b1w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, b2w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      float entw[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[WANT_MEAN_P ? NV : 1];
+    if (WANT_MEAN_P) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[j] = 0.f;
+    }
+    for (int t = 0; t < n_draws; ++t) {
+      if (tid == 0 && issued <= consumed) produce(true);
+      umma::mbar_wait(&full_bar[st], phase);
+      const uint8_t* base = aq_smem + (size_t)st * tile_bytes;
+      float val[NV];
+#pragma unroll
+      for (int j = 0; j < NSTEPS; ++j) {
+        const bool ok = AQ_SPLIT * j + q < nvec;
+        if (VEC == 2) {
+          const float2 v2 = ok ? *reinterpret_cast<const float2*>(base + off[j]) : make_float2(pad, pad);
+          val[2 * j] = v2.x;
+          val[2 * j + 1] = v2.y;
+        } else {
+          val[j] = ok ? *reinterpret_cast<const float*>(base + off[j]) : pad;
+        }
+      }
+      // the row is in registers: hand the stage back to the producer
+      __syncwarp();
+      if (lane == 0) aq_mbar_arrive(&empty_bar[st]);
+      if (++st == n_stages) { st = 0; phase ^= 1u; }
+      if (tid == 0) { ++consumed; produce(false); }
+
+      float b1a = -INFINITY, b2a = -INFINITY, b1b = -INFINITY, b2b = -INFINITY, enta = 0.f, entb = 0.f;
       float b1, b2, ent;
-      auto top2 = [](float& t1, float& t2, float v) {
-        t2 = fmaxf(t2, fminf(t1, v));
-        t1 = fmaxf(t1, v);
-      };
       if (IS_LOGP) {
         // probs = softmax(log-probs), as dropout_uncertainty does (active_learning.py:147):
         // e = exp(l - max), z = sum e, p = e / z.  The scores are taken on e and rescaled, and the entropy uses
         // log p = (l - max) - log z exactly (log(p + 1e-10) differs from it only where p < 1e-8).
-        float mxw[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int j = 0; j < C4; j += 4) {
+        float mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) mxw[w] = fmaxf(mxw[w], row[col(j + w)]);
+        for (int j = 0; j < NV; j += 2) {
+          mxa = fmaxf(mxa, val[j]);
+          if (j + 1 < NV) mxb = fmaxf(mxb, val[j + 1]);
         }
-        for (int j = C4; j < C; ++j) mxw[0] = fmaxf(mxw[0], row[col(j)]);
-        const float mx = fmaxf(fmaxf(mxw[0], mxw[1]), fmaxf(mxw[2], mxw[3]));
-        float zw[4] = {0.f, 0.f, 0.f, 0.f};
-        auto body = [&](int c, int w) {
-          const float d = row[c] - mx;
-          const float e = __expf(d);
-          zw[w] += e;
-          if (need & 4u) entw[w] = fmaf(e, fmaxf(d, -1e30f), entw[w]);
-          if (need & 3u) top2(b1w[w], b2w[w], e);
-          if (WANT_MEAN_P) row[c] = e;
-        };
-        for (int j = 0; j < C4; j += 4) {
+        float mx = fmaxf(mxa, mxb);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mxs = mx * LOG2E;
+        float za = 0.f, zb = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) body(col(j + w), w);
+        for (int j = 0; j < NV; ++j) {
+          const float d2 = fmaf(val[j], LOG2E, -mxs);   // (l - max) / ln 2
+          const float e = aq_ex2(d2);
+          if (j & 1) {
+            zb += e;
+            if (need & 4u) entb = fmaf(e, fmaxf(d2, -1e30f), entb);
+            if (need & 3u) aq_top2(b1b, b2b, e);
+          } else {
+            za += e;
+            if (need & 4u) enta = fmaf(e, fmaxf(d2, -1e30f), enta);
+            if (need & 3u) aq_top2(b1a, b2a, e);
+          }
+          if (WANT_MEAN_P) val[j] = e;
         }
-        for (int j = C4; j < C; ++j) body(col(j), 0);
-        const float z = (zw[0] + zw[1]) + (zw[2] + zw[3]);
+        const float z = aq_sum_quad(za + zb);
         const float inv_z = 1.0f / z;
-        b1 = b1w[0]; b2 = b2w[0];
-#pragma unroll
-        for (int w = 1; w < 4; ++w) { top2(b1, b2, b2w[w]); top2(b1, b2, b1w[w]); }
+        b1 = b1a; b2 = b2a;
+        if (need & 3u) {
+          aq_top2(b1, b2, b2b);
+          aq_top2(b1, b2, b1b);
+          aq_top2_quad(b1, b2);
+        }
         b1 *= inv_z;
         b2 *= inv_z;
-        ent = ((entw[0] + entw[1]) + (entw[2] + entw[3])) * inv_z - __logf(z);   // sum p log p
+        ent = 0.f;
+        if (need & 4u) ent = aq_sum_quad(enta + entb) * LN2 * inv_z - __logf(z);   // sum p log p
         if (WANT_MEAN_P) {
-          auto accum = [&](int c) { acc[c] = t == 0 ? row[c] * inv_z : fmaf(row[c], inv_z, acc[c]); };
-#pragma unroll 4
-          for (int j = 0; j < C; ++j) accum(col(j));
+#pragma unroll
+          for (int j = 0; j < NV; ++j) acc[j] = fmaf(val[j], inv_z, acc[j]);
         }
       } else {
-        auto body = [&](int c, int w) {
-          const float p = row[c];
-          if (need & 3u) top2(b1w[w], b2w[w], p);
-          if (need & 4u) entw[w] = fmaf(p, __logf(p + 1e-10f), entw[w]);
-          if (WANT_MEAN_P) acc[c] = t == 0 ? p : acc[c] + p;
-        };
-        for (int j = 0; j < C4; j += 4) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) body(col(j + w), w);
+        for (int j = 0; j < NV; ++j) {
+          const float p = val[j];
+          if (j & 1) {
+            if (need & 3u) aq_top2(b1b, b2b, p);
+            if (need & 4u) entb = fmaf(p, __logf(p + 1e-10f), entb);
+          } else {
+            if (need & 3u) aq_top2(b1a, b2a, p);
+            if (need & 4u) enta = fmaf(p, __logf(p + 1e-10f), enta);
+          }
+          if (WANT_MEAN_P) acc[j] += p;
         }
-        for (int j = C4; j < C; ++j) body(col(j), 0);
-        b1 = b1w[0]; b2 = b2w[0];
-#pragma unroll
-        for (int w = 1; w < 4; ++w) { top2(b1, b2, b2w[w]); top2(b1, b2, b1w[w]); }
-        ent = (entw[0] + entw[1]) + (entw[2] + entw[3]);
+        b1 = b1a; b2 = b2a;
+        if (need & 3u) {
+          aq_top2(b1, b2, b2b);
+          aq_top2(b1, b2, b1b);
+          aq_top2_quad(b1, b2);
+        }
+        ent = 0.f;
+        if (need & 4u) ent = aq_sum_quad(enta + entb);
       }
       a_max += b1;
       a_margin += b1 - b2;
       a_ent -= ent;
-      // this stage is consumed: refill it with the load n_stages ahead (generic-proxy accesses of the stage are
-      // ordered before the copy engine's overwrite)
-      umma::fence_async_smem();
-      __syncthreads();
-      if (tid == 0 && k + n_stages < n_loads) issue(k + n_stages);
     }
-    if (mean_of_scores != nullptr) {
-      if (need & 1u) mean_of_scores[item] = a_max * inv_t;
-      if (need & 2u) mean_of_scores[n_items + item] = a_margin * inv_t;
-      if (need & 4u) mean_of_scores[2 * n_items + item] = a_ent * inv_t;
+    if (q == 0) {
+      if (mean_of_scores != nullptr) {
+        if (need & 1u) mean_of_scores[item] = a_max * inv_t;
+        if (need & 2u) mean_of_scores[n_items + item] = a_margin * inv_t;
+        if (need & 4u) mean_of_scores[2 * n_items + item] = a_ent * inv_t;
+      }
+      if (single_out != nullptr)
+        single_out[item] = (single_mode == BFB200_MODE_MAX ? a_max : single_mode == BFB200_MODE_MARGIN ? a_margin : a_ent) * inv_t;
     }
-    if (single_out != nullptr)
-      single_out[item] = (single_mode == BFB200_MODE_MAX ? a_max : single_mode == BFB200_MODE_MARGIN ? a_margin : a_ent) * inv_t;
     if (WANT_MEAN_P) {
       float b1 = -INFINITY, b2 = -INFINITY, ent = 0.f;
-      auto fin = [&](int c) {
-        const float p = acc[c] * inv_t;
-        acc[c] = p;
-        b2 = fmaxf(b2, fminf(b1, p));
-        b1 = fmaxf(b1, p);
-        ent = fmaf(p, __logf(p + 1e-10f), ent);
-      };
-#pragma unroll 4
-      for (int j = 0; j < C; ++j) fin(col(j));
+      float* dst = mean_p != nullptr ? mean_p + tile * AQ_ROWS * (int64_t)C : nullptr;
+#pragma unroll
+      for (int j = 0; j < NSTEPS; ++j) {
+        if (AQ_SPLIT * j + q < nvec) {
+#pragma unroll
+          for (int w = 0; w < VEC; ++w) {
+            const float p = acc[VEC * j + w] * inv_t;
+            acc[VEC * j + w] = p;
+            aq_top2(b1, b2, p);
+            ent = fmaf(p, __logf(p + 1e-10f), ent);
+          }
+          if (dst != nullptr) {   // the lanes of an item write adjacent 8-byte pieces of its row
+            if (VEC == 2)
+              __stcs(reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(dst) + off[j]),
+                     make_float2(acc[2 * j], acc[2 * j + 1]));
+            else
+              __stcs(reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + off[j]), acc[j]);
+          }
+        }
+      }
       if (score_of_mean != nullptr) {
-        score_of_mean[item] = b1;
-        score_of_mean[n_items + item] = b1 - b2;
-        score_of_mean[2 * n_items + item] = -ent;
+        aq_top2_quad(b1, b2);
+        ent = aq_sum_quad(ent);
+        if (q == 0) {
+          score_of_mean[item] = b1;
+          score_of_mean[n_items + item] = b1 - b2;
+          score_of_mean[2 * n_items + item] = -ent;
+        }
       }
-      __syncthreads();
-      if (mean_p != nullptr) {   // the tile of predictive means is contiguous in mean_p: coalesced 128-bit stores
-        float4* dst = reinterpret_cast<float4*>(mean_p + tile * AQ_ROWS * (int64_t)C);
-        const float4* src = reinterpret_cast<const float4*>(acc_tile);
-        for (int i = tid; i < AQ_ROWS * C / 4; i += AQ_ROWS) dst[i] = src[i];
-      }
-      __syncthreads();
     }
   }
 }
@@ -463,32 +576,55 @@ static int aq_sm_count() {
 
 // Launch the TMA-staged kernel on the full 128-item tiles of x; returns the number of items it covered (0 when
 // the shape or alignment is outside its class, in which case the warp-per-item kernels take everything).
+template <int VEC, int NSTEPS>
+static void aq_launch(bool is_logp, bool want_mean, int grid, size_t smem, cudaStream_t st, const float* x, int n_draws,
+                      int64_t n_items, int64_t n_tiles, int n_classes, int n_stages, uint32_t need, float* mean_p,
+                      float* score_of_mean, float* mean_of_scores, float* single_out, int single_mode) {
+#define AQ_LAUNCH(LOGP, MEAN)                                                                                    \
+  do {                                                                                                           \
+    cudaFuncSetAttribute(acquire_tma_kernel<VEC, NSTEPS, LOGP, MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smem);                                                                             \
+    acquire_tma_kernel<VEC, NSTEPS, LOGP, MEAN><<<grid, AQ_THREADS, smem, st>>>(                                  \
+        x, n_draws, n_items, n_tiles, n_classes, n_stages, need, mean_p, score_of_mean, mean_of_scores,          \
+        single_out, single_mode);                                                                                \
+  } while (0)
+  if (is_logp) { if (want_mean) AQ_LAUNCH(true, true); else AQ_LAUNCH(true, false); }
+  else         { if (want_mean) AQ_LAUNCH(false, true); else AQ_LAUNCH(false, false); }
+#undef AQ_LAUNCH
+}
+
 static int64_t launch_acquire_tma(const float* x, int is_logp, int n_draws, int64_t n_items, int n_classes,
                                   uint32_t need, float* mean_p, float* score_of_mean, float* mean_of_scores,
                                   float* single_out, int single_mode, cudaStream_t st, int* rc) {
   *rc = BFB200_OK;
   const int64_t n_tiles = n_items / AQ_ROWS;
-  if (n_tiles == 0 || n_classes > 128) return 0;
+  if (n_tiles == 0 || n_classes > 128 || n_classes < 2) return 0;
   if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return 0;
   if (n_draws > 1 && ((n_items * (int64_t)n_classes) & 3) != 0) return 0;   // every draw's tile 16-byte aligned
   const bool want_mean = mean_p != nullptr || score_of_mean != nullptr;
-  if (want_mean && mean_p != nullptr && (reinterpret_cast<uintptr_t>(mean_p) & 15u) != 0) return 0;
+  if (mean_p != nullptr && (reinterpret_cast<uintptr_t>(mean_p) & 7u) != 0) return 0;
   const size_t tile_bytes = (size_t)AQ_ROWS * n_classes * sizeof(float);
-  int n_stages = (int)((200 * 1024 - (want_mean ? tile_bytes : 0)) / tile_bytes);
-  if (n_stages > 4) n_stages = 4;
+  int n_stages = (int)((200 * 1024) / tile_bytes);
+  if (n_stages > AQ_MAX_STAGES) n_stages = AQ_MAX_STAGES;
   if (n_stages < 2) return 0;
-  const size_t smem = tile_bytes * (n_stages + (want_mean ? 1 : 0));
-  int64_t grid = n_tiles < aq_sm_count() ? n_tiles : aq_sm_count();
-#define AQ_LAUNCH(LOGP, MEAN)                                                                              \
-  do {                                                                                                     \
-    cudaFuncSetAttribute(acquire_tma_kernel<LOGP, MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    acquire_tma_kernel<LOGP, MEAN><<<(int)grid, AQ_ROWS, smem, st>>>(x, n_draws, n_items, n_tiles, n_classes,   \
-                                                                     n_stages, need, mean_p, score_of_mean,  \
-                                                                     mean_of_scores, single_out, single_mode); \
-  } while (0)
-  if (is_logp) { if (want_mean) AQ_LAUNCH(true, true); else AQ_LAUNCH(true, false); }
-  else         { if (want_mean) AQ_LAUNCH(false, true); else AQ_LAUNCH(false, false); }
-#undef AQ_LAUNCH
+  const size_t smem = tile_bytes * n_stages;
+  const int grid = (int)(n_tiles < aq_sm_count() ? n_tiles : aq_sm_count());
+  const int vec = (n_classes & 1) ? 1 : 2;
+  const int steps = ((n_classes + vec - 1) / vec + AQ_SPLIT - 1) / AQ_SPLIT;
+#define AQ_GO(VEC, NSTEPS)                                                                                        \
+  aq_launch<VEC, NSTEPS>(is_logp != 0, want_mean, grid, smem, st, x, n_draws, n_items, n_tiles, n_classes, n_stages, \
+                         need, mean_p, score_of_mean, mean_of_scores, single_out, single_mode)
+  if (vec == 2) {
+    if (steps <= 4) AQ_GO(2, 4);
+    else if (steps <= 8) AQ_GO(2, 8);
+    else if (steps <= 15) AQ_GO(2, 15);
+    else AQ_GO(2, 16);
+  } else {
+    if (steps <= 8) AQ_GO(1, 8);
+    else if (steps <= 17) AQ_GO(1, 17);
+    else AQ_GO(1, 32);
+  }
+#undef AQ_GO
   count_launch("acquire_tma_kernel", st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
