@@ -143,6 +143,11 @@ __device__ __forceinline__ float aq_ex2(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ float aq_lg2(float v) {   // v >= 1e-10 here: flush-to-zero never triggers
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ void aq_top2(float& t1, float& t2, float v) {
   t2 = fmaxf(t2, fminf(t1, v));
   t1 = fmaxf(t1, v);
@@ -332,10 +337,10 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acquire_tma_kernel(const float*
           const float p = val[j];
           if (j & 1) {
             if (need & 3u) aq_top2(b1b, b2b, p);
-            if (need & 4u) entb = fmaf(p, __logf(p + 1e-10f), entb);
+            if (need & 4u) entb = fmaf(p, aq_lg2(p + 1e-10f), entb);
           } else {
             if (need & 3u) aq_top2(b1a, b2a, p);
-            if (need & 4u) enta = fmaf(p, __logf(p + 1e-10f), enta);
+            if (need & 4u) enta = fmaf(p, aq_lg2(p + 1e-10f), enta);
           }
           if (WANT_MEAN_P) acc[j] += p;
         }
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acquire_tma_kernel(const float*
           aq_top2_quad(b1, b2);
         }
         ent = 0.f;
-        if (need & 4u) ent = aq_sum_quad(enta + entb);
+        if (need & 4u) ent = aq_sum_quad(enta + entb) * LN2;   // sum p log(p + 1e-10), logs taken in base 2
       }
       a_max += b1;
       a_margin += b1 - b2;
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acquire_tma_kernel(const float*
             const float p = acc[VEC * j + w] * inv_t;
             acc[VEC * j + w] = p;
             aq_top2(b1, b2, p);
-            ent = fmaf(p, __logf(p + 1e-10f), ent);
+            ent = fmaf(p, aq_lg2(p + 1e-10f), ent);
           }
           if (dst != nullptr) {   // the lanes of an item write adjacent 8-byte pieces of its row
             if (VEC == 2)
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acquire_tma_kernel(const float*
       }
       if (score_of_mean != nullptr) {
         aq_top2_quad(b1, b2);
-        ent = aq_sum_quad(ent);
+        ent = aq_sum_quad(ent) * LN2;
         if (q == 0) {
           score_of_mean[item] = b1;
           score_of_mean[n_items + item] = b1 - b2;

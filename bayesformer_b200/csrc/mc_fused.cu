@@ -187,10 +187,51 @@ __device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, u
          (keep8_of(r3, threshold) << 24);
 }
 
-__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
-  const float2 a = umma::unpack_f16x2(w.x), b = umma::unpack_f16x2(w.y);
-  const float2 c = umma::unpack_f16x2(w.z), d = umma::unpack_f16x2(w.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+
+// Mixed-precision FMA, d = a * b + c with fp16 a, b taken straight from a half of a packed word and fp32 c, d
+// (PTX fma.rn.f32.f16, SASS FHFMA with .H0/.H1 operand selectors): the attention phase multiplies the fp16 Q / K / V
+// tiles without unpacking them.  The product of two fp16 values is exact in fp32, so this is the arithmetic of
+// "unpack, then FFMA" at half the instructions.
+#define BFB_FH(NAME, ASEL, BSEL)                                                                              \
+  __device__ __forceinline__ float NAME(uint32_t a, uint32_t b, float c) {                                    \
+    float d;                                                                                                  \
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"                  \
+        "fma.rn.f32.f16 %0, " ASEL ", " BSEL ", %3;\n\t}"                                                     \
+        : "=f"(d)                                                                                             \
+        : "r"(a), "r"(b), "f"(c));                                                                            \
+    return d;                                                                                                 \
+  }
+BFB_FH(fh_ll, "al", "bl")
+BFB_FH(fh_hh, "ah", "bh")
+BFB_FH(fh_lh, "al", "bh")
+BFB_FH(fh_hl, "ah", "bl")
+#undef BFB_FH
+
+__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b) {
+  float d = fh_ll(a.x, b.x, 0.f);
+  d = fh_hh(a.x, b.x, d);
+  d = fh_ll(a.y, b.y, d);
+  d = fh_hh(a.y, b.y, d);
+  d = fh_ll(a.z, b.z, d);
+  d = fh_hh(a.z, b.z, d);
+  d = fh_ll(a.w, b.w, d);
+  return fh_hh(a.w, b.w, d);
+}
+// o[0..8) += p * v[0..8), p = half `HI` of pp
+template <bool HI>
+__device__ __forceinline__ void axpy8_f16(uint32_t pp, const uint4& v, float (&o)[8]) {
+  if (HI) {
+    o[0] = fh_hl(pp, v.x, o[0]); o[1] = fh_hh(pp, v.x, o[1]); o[2] = fh_hl(pp, v.y, o[2]); o[3] = fh_hh(pp, v.y, o[3]);
+    o[4] = fh_hl(pp, v.z, o[4]); o[5] = fh_hh(pp, v.z, o[5]); o[6] = fh_hl(pp, v.w, o[6]); o[7] = fh_hh(pp, v.w, o[7]);
+  } else {
+    o[0] = fh_ll(pp, v.x, o[0]); o[1] = fh_lh(pp, v.x, o[1]); o[2] = fh_ll(pp, v.y, o[2]); o[3] = fh_lh(pp, v.y, o[3]);
+    o[4] = fh_ll(pp, v.z, o[4]); o[5] = fh_lh(pp, v.z, o[5]); o[6] = fh_ll(pp, v.w, o[6]); o[7] = fh_lh(pp, v.w, o[7]);
+  }
+}
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // reductions over an aligned group of `n` (power of two <= 32) lanes
@@ -471,7 +512,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const int pos = row / spt, seq_l = row - pos * spt;
   const int last_lo = (len - 1) * spt, last_hi = len * spt - 1;              // rows of the last position
   const bool warp_has_last = (row & ~31) <= last_hi && (row | 31) >= last_lo;   // warp-uniform
-  const float sqrt_d = sqrtf((float)FD), inv_sqrt_dh = 1.0f / sqrtf((float)FDH);
+  const float sqrt_d = sqrtf((float)FD);
+  const float qk_scale_log2e = 1.4426950408889634f / sqrtf((float)FDH);   // scores / sqrt(dh), in base-2 exponent units
   const uint32_t fl = a.site_flags;
   const MaskSource& ms = a.ms;
 
@@ -572,16 +614,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           const int qpar = nsplit == 2 ? (it & 1) : -1;
           const int sl = p >> 3, hd = p & 7;
           const uint32_t row0 = (uint32_t)sl;   // row of (sequence sl, position j) = j * spt + sl
-          // K unpacked once for short sequences; the 16-token variant keeps K packed too (4 registers per key)
-          constexpr bool kUnpackK = false;   // at 128 registers per thread even 8 unpacked keys spill
-          float kf[kUnpackK ? MAXLEN : 1][8];
-          uint4 kp[kUnpackK ? 1 : MAXLEN], vp[MAXLEN];
+          // K and V stay packed (4 registers per key / value row); the dot products read the fp16 halves in place
+          uint4 kp[MAXLEN], vp[MAXLEN];
 #pragma unroll
           for (int j = 0; j < MAXLEN; ++j) {
             if (j < len) {
-              const uint4 kw = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd));
-              if constexpr (kUnpackK) unpack8(kw, kf[j]);
-              else kp[j] = kw;
+              kp[j] = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd));
               vp[j] = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j * spt, hd));
             }
           }
@@ -590,42 +628,37 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           for (int t = 0; t < MAXLEN; ++t) {
             if (t < len && (qpar < 0 || (t & 1) == qpar) && (!prune || t == len - 1)) {
               uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
-              float q[8];
-              unpack8(*reinterpret_cast<const uint4*>(qptr), q);
+              const uint4 qw = *reinterpret_cast<const uint4*>(qptr);
               float sc[MAXLEN];
               float mx = -INFINITY;
 #pragma unroll
               for (int j = 0; j <= t; ++j) {
-                float d = 0.f;
-                float kj[8];
-                if constexpr (kUnpackK) {
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) kj[c] = kf[j][c];
-                } else {
-                  unpack8(kp[j], kj);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d = fmaf(q[c], kj[c], d);
-                d = d * inv_sqrt_dh;
-                sc[j] = d;
-                mx = fmaxf(mx, d);
+                sc[j] = dot8_f16(qw, kp[j]);
+                mx = fmaxf(mx, sc[j]);
               }
+              // softmax weights e_j = exp((s_j - max) / sqrt(dh)) in fp32, handed to the fp16-operand PV product as
+              // a (high, low) pair of halves: e_j = hi_j + lo_j to 2^-22, so the product keeps fp32 weights
+              const float nmx = -mx * qk_scale_log2e;
+              uint32_t ph[(MAXLEN + 1) / 2], pl[(MAXLEN + 1) / 2];
               float z = 0.f;
 #pragma unroll
-              for (int j = 0; j <= t; ++j) {
-                sc[j] = __expf(sc[j] - mx);
-                z += sc[j];
+              for (int j = 0; j <= t; j += 2) {
+                const float e0 = ex2_approx(fmaf(sc[j], qk_scale_log2e, nmx));
+                const float e1 = j + 1 <= t ? ex2_approx(fmaf(sc[j + 1], qk_scale_log2e, nmx)) : 0.f;
+                z += e0 + e1;
+                ph[j >> 1] = umma::pack_f16x2(e0, e1);
+                const float2 hi = umma::unpack_f16x2(ph[j >> 1]);
+                pl[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
               }
               const float inv_z = __fdividef(1.0f, z);
               float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int j = 0; j <= t; ++j) {
-                const float pj = sc[j] * inv_z;
-                float vj[8];
-                unpack8(vp[j], vj);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = fmaf(pj, vj[c], o[c]);
+                if (j & 1) { axpy8_f16<true>(ph[j >> 1], vp[j], o); axpy8_f16<true>(pl[j >> 1], vp[j], o); }
+                else       { axpy8_f16<false>(ph[j >> 1], vp[j], o); axpy8_f16<false>(pl[j >> 1], vp[j], o); }
               }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] *= inv_z;
               if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
                 const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
 #pragma unroll
