@@ -270,12 +270,12 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<128>::TOTAL);
   a.m_tile = 0;
   attention_tc_kernel<128><<<(unsigned)grid, 2 * AT_M, AtSmem<128>::TOTAL, st>>>(map, a);
-  BFB_LAUNCH_CHECK("attention_tc_kernel", st);
+  BFB_LAUNCH_CHECK("attention_tc_kernel<128>", st);
   if (len > AT_M) {
     cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<256>::TOTAL);
     a.m_tile = 1;
     attention_tc_kernel<256><<<(unsigned)grid, 2 * AT_M, AtSmem<256>::TOTAL, st>>>(map, a);
-    BFB_LAUNCH_CHECK("attention_tc_kernel", st);
+    BFB_LAUNCH_CHECK("attention_tc_kernel<256>", st);
   }
   return BFB200_OK;
 }

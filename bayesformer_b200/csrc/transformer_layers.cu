@@ -405,6 +405,144 @@ __global__ void __launch_bounds__(256, 4) resid_ln_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------
+// Tensor-core path variants of the two elementwise kernels (16-bit branch in, fp32 and / or 16-bit out).  A thread
+// owns EIGHT contiguous features, which is exactly one Philox call of the mask stream (common.cuh: one call decides
+// eight features) — the float4-per-thread kernels above evaluate every call twice.  Per thread and group: 2 x 128-bit
+// loads of the fp32 residual, one 128-bit load of the 16-bit branch, one 128-bit store of the 16-bit output.
+// ---------------------------------------------------------------------------
+// 8 keep bits (bit j = feature 8 g + j) for (local sequence s, position pos, site)
+__device__ __forceinline__ uint32_t keep8(const MaskSource& m, int64_t s, uint32_t pos, uint32_t site, uint32_t g) {
+  if (m.bits != nullptr) {
+    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + s)) * m.max_len + pos;
+    return (m.bits[row * m.words + (g >> 2)] >> ((g & 3u) * 8u)) & 0xFFu;
+  }
+  const uint64_t item = (uint64_t)(m.item_base + s / m.n_draws);
+  const uint32_t draw = m.draw_base + (uint32_t)(s % m.n_draws);
+  return keep8_of(philox4x32_10(make_uint4((uint32_t)item, draw, (m.step << 16) | pos, (site << 16) | g), m.key), m.threshold);
+}
+
+__device__ __forceinline__ void drop8(float (&v)[8], uint32_t keep, float scale) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * scale : 0.f;
+}
+__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load8_16(const uint16_t* p, uint32_t fmt, float (&v)[8]) {
+  const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fmt == umma::kFmtF16) {
+      const float2 f = umma::unpack_f16x2(ww[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    } else {
+      v[2 * i] = umma::bf16_lo(ww[i]); v[2 * i + 1] = umma::bf16_hi(ww[i]);
+    }
+  }
+}
+__device__ __forceinline__ void store8_16(uint16_t* p, uint32_t fmt, const float (&v)[8]) {
+  uint4 w;
+  if (fmt == umma::kFmtF16) {
+    w.x = umma::pack_f16x2(v[0], v[1]); w.y = umma::pack_f16x2(v[2], v[3]);
+    w.z = umma::pack_f16x2(v[4], v[5]); w.w = umma::pack_f16x2(v[6], v[7]);
+  } else {
+    w.x = umma::pack_bf16x2(v[0], v[1]); w.y = umma::pack_bf16x2(v[2], v[3]);
+    w.z = umma::pack_bf16x2(v[4], v[5]); w.w = umma::pack_bf16x2(v[6], v[7]);
+  }
+  *reinterpret_cast<uint4*>(p) = w;
+}
+
+// x = dropout_E(embedding[tok]) * sqrt(d) + pe[t], fp32 and 16-bit copies      (transformer.py:355-362, :269-272)
+__global__ void __launch_bounds__(256) embed16_kernel(const int32_t* __restrict__ tokens, int tok_stride,
+                                                      const float* __restrict__ emb, const float* __restrict__ pe,
+                                                      int64_t n_seq, int len, int d, float sqrt_d, MaskSource ms, int site,
+                                                      float* __restrict__ x, uint16_t* __restrict__ x16, uint32_t fmt) {
+  const int d8 = d >> 3;
+  const int64_t total = n_seq * len * d8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d8;
+    const int g = (int)(i - r * d8);
+    const int64_t s = r / len;
+    const int t = (int)(r - s * len);
+    const int tok = tokens[s * tok_stride + t];
+    float e[8], p[8];
+    load8_f32(emb + (int64_t)tok * d + 8 * g, e);
+    load8_f32(pe + (int64_t)t * d + 8 * g, p);
+    if (site >= 0) drop8(e, keep8(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)g), ms.scale);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = e[c] * sqrt_d + p[c];
+    store8_f32(x + i * 8, e);
+    store8_16(x16 + i * 8, fmt, e);
+  }
+}
+
+// out = dropout_out( LayerNorm(x + dropout_branch(y16)) ), one warp per row      (transformer.py:226-233, :370)
+template <int NJ>
+__global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restrict__ x, const uint16_t* __restrict__ y16,
+                                                         float* __restrict__ out, uint16_t* __restrict__ out16,
+                                                         int64_t n_rows, int len, int d, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, MaskSource ms,
+                                                         int branch_site, int out_site, uint32_t fmt) {
+  const int lane = threadIdx.x & 31;
+  const int d8 = d >> 3;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
+    const int64_t s = r / len;
+    const uint32_t t = (uint32_t)(r - s * len);
+    float v[NJ][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int g = lane + 32 * j;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[j][c] = 0.f;
+      if (g < d8) {
+        float b[8];
+        load8_f32(x + r * d + 8 * g, v[j]);
+        load8_16(y16 + r * d + 8 * g, fmt, b);
+        if (branch_site >= 0) drop8(b, keep8(ms, s, t, (uint32_t)branch_site, (uint32_t)g), ms.scale);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[j][c] += b[c];
+        sum += ((v[j][0] + v[j][1]) + (v[j][2] + v[j][3])) + ((v[j][4] + v[j][5]) + (v[j][6] + v[j][7]));
+      }
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (lane + 32 * j < d8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float a = v[j][c] - mean;
+          sq = fmaf(a, a, sq);
+        }
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int g = lane + 32 * j;
+      if (g < d8) {
+        float gm[8], bt[8], o[8];
+        load8_f32(gamma + 8 * g, gm);
+        load8_f32(beta + 8 * g, bt);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = (v[j][c] - mean) * rstd * gm[c] + bt[c];
+        if (out_site >= 0) drop8(o, keep8(ms, s, t, (uint32_t)out_site, (uint32_t)g), ms.scale);
+        if (out != nullptr) store8_f32(out + r * d + 8 * g, o);
+        if (out16 != nullptr) store8_16(out16 + r * d + 8 * g, fmt, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // last-position logits -> log-softmax -> probabilities -> per-draw score + next token
 // (transformer.py:375; active_learning.py:62-68, :103-112, :146-152)
 // one warp per sequence.
@@ -587,6 +725,13 @@ int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t it
 
 int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const float* pe, int64_t n_seq,
                  int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st, void* x16, uint32_t fmt) {
+  if (x16 != nullptr && (d & 7) == 0) {
+    const int64_t total8 = n_seq * len * (d >> 3);
+    embed16_kernel<<<stride_grid((total8 + 255) / 256, 8), 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d,
+                                                                        sqrtf((float)d), ms, site, x, (uint16_t*)x16, fmt);
+    BFB_LAUNCH_CHECK("embed16_kernel", st);
+    return BFB200_OK;
+  }
   const int64_t total = n_seq * len * (d >> 2);
   const int grid = stride_grid((total + 255) / 256, 8);
   embed_kernel<<<grid, 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d, sqrtf((float)d), ms, site, x,
@@ -642,6 +787,16 @@ int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, 
                     int branch_site, int out_site, cudaStream_t st, void* out16, uint32_t fmt, const void* y16) {
   BFB_REQUIRE(d <= 4096, BFB200_ERR_UNSUPPORTED, "d_model %d > 4096", d);
   const int grid = stride_grid((n_rows + 7) / 8, 8);
+  if (y16 != nullptr && (d & 7) == 0 && d <= 2048) {   // tensor-core path: eight features per thread
+#define LAUNCH_LN16(NJ) resid_ln16_kernel<NJ><<<grid, 256, 0, st>>>(x, (const uint16_t*)y16, out, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, fmt)
+    if (d <= 256) LAUNCH_LN16(1);
+    else if (d <= 512) LAUNCH_LN16(2);
+    else if (d <= 1024) LAUNCH_LN16(4);
+    else LAUNCH_LN16(8);
+#undef LAUNCH_LN16
+    BFB_LAUNCH_CHECK(out_site >= 0 || branch_site >= 0 ? "resid_ln16_kernel[dropout]" : "resid_ln16_kernel", st);
+    return BFB200_OK;
+  }
 #define LAUNCH_LN(NPL4) resid_ln_kernel<NPL4><<<grid, 256, 0, st>>>(x, y, out, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, (uint16_t*)out16, fmt, (const uint16_t*)y16)
   const int d4 = d >> 2;
   if (d4 <= 32) LAUNCH_LN(1);
