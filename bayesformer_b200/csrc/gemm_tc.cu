@@ -2,13 +2,13 @@
 // nn.Linear of src/model/transformer.py (:33-35 Q/K/V, :100 W_out, :152-154 FFN, :336 vocabulary head) over the
 // R = B * T_mc * len token rows of a chunk, for models outside the fused kernel's class (d_model 512, F 2048 ...).
 //
-// sm_100a design (the canonical Blackwell GEMM): persistent CTAs, 192 threads in three roles
+// sm_100a design (the canonical Blackwell GEMM): persistent CTAs, 320 threads in three roles
 //   warp 0      one lane issues 2-D TMA loads (cp.async.bulk.tensor, 128-byte swizzle) of the 128 x 64 A tile and
 //               the BN x 64 W tile into a 4-stage shared-memory ring, completion on `full` mbarriers;
 //   warp 1      one lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN, K = 16 x 4 per stage) into one of
 //               two TMEM accumulator stages; tcgen05.commit releases the ring slot (`empty`) and, after the last
 //               K block, hands the accumulator to the epilogue (`acc_full`);
-//   warps 2-5   epilogue: thread = accumulator row; tcgen05.ld 32 columns at a time, + bias (staged in shared memory),
+//   warps 2-9   epilogue: thread = accumulator row (two warps per TMEM lane quarter, half of the columns each); tcgen05.ld 32 columns at a time, + bias,
 //               ReLU, convert, write a 32-row x 128-byte slab into swizzled shared memory and hand it to a 2-D TMA
 //               store (cp.async.bulk.tensor ... global.shared::cta), double-buffered per warp, so every global
 //               write is a full 128-byte line and M / N tails are clipped by the copy engine; then `acc_empty`.
@@ -16,6 +16,7 @@
 // zero-filled by TMA and masked in the epilogue.  Tiles are walked N-fastest so an A row block stays in L2 while
 // all of its N tiles are produced.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -27,9 +28,9 @@ namespace {
 
 constexpr int GM = 128;       // tile rows (UMMA M)
 constexpr int GK = 64;        // K per stage: one 128-byte swizzle row of 16-bit elements
-constexpr int GSTAGES_MAX = 4;
 constexpr int GACC = 2;       // TMEM accumulator stages
-constexpr int GTHREADS = 192;
+constexpr int GEPI_WARPS = 8;   // two epilogue warps per TMEM lane quarter, half of the tile columns each
+constexpr int GTHREADS = 64 + 32 * GEPI_WARPS;
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -63,6 +64,89 @@ struct GemmArgs {
   int64_t ldc;             // output row pitch in elements (= N)
 };
 
+// Epilogue of one accumulator stage for one warp: columns [c_begin, c_begin + 32 * NCH) of its 32 TMEM lanes ->
+// (+ bias)(ReLU) -> swizzled 32-row slabs -> 2-D TMA stores.  The tcgen05.ld of chunk i + 1 is in flight while chunk
+// i is converted and staged.
+template <int NCH>
+__device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtensorMap* map_c16, const CUtensorMap* map_c32,
+                                                 uint32_t tacc, int n_base, int row0,
+                                                 int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane) {
+  constexpr uint32_t SLAB_BYTES = 32 * 128;
+  const bool has_bias = g.bias != nullptr;
+  uint32_t r[2][32];
+  if (n_base + c_begin < g.N) umma::tmem_ld32(tacc + c_begin, r[0]);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = c_begin + 32 * ch;
+    const int n0 = n_base + c0;
+    if (n0 < g.N) {   // warp-uniform: columns past N are outside the matrix
+      umma::tmem_ld_wait();
+      if (ch + 1 < NCH && n0 + 32 < g.N) umma::tmem_ld32(tacc + c0 + 32, r[(ch + 1) & 1]);
+      float v[32];
+      if (has_bias) {   // the same 32 addresses for every lane: broadcast loads that hit L1 after the first tile row
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = n0 + i < g.N ? __ldg(g.bias + n0 + i) : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = __uint_as_float(r[ch & 1][i]) + v[i];
+        v[i] = g.relu ? fmaxf(x, 0.f) : x;
+      }
+      if (g.out32 != nullptr) {
+        uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
+        tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(slab + umma::sw128_offset(lane, c)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        umma::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(map_c32, slab, n0, row0);
+          tma_store_commit();
+        }
+        ++slab_i;
+      }
+      if (g.out16 != nullptr) {
+        // two 32-column chunks share one 128-byte slab row: even chunk -> bytes [0, 64), odd chunk -> [64, 128)
+        uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
+        const int half = ch & 1;   // c_begin is a multiple of 64
+        if (half == 0) {
+          tma_store_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 w;
+          const int i = 8 * c;
+          if (g.fmt == umma::kFmtF16) {
+            w.x = umma::pack_f16x2(v[i], v[i + 1]); w.y = umma::pack_f16x2(v[i + 2], v[i + 3]);
+            w.z = umma::pack_f16x2(v[i + 4], v[i + 5]); w.w = umma::pack_f16x2(v[i + 6], v[i + 7]);
+          } else {
+            w.x = umma::pack_bf16x2(v[i], v[i + 1]); w.y = umma::pack_bf16x2(v[i + 2], v[i + 3]);
+            w.z = umma::pack_bf16x2(v[i + 4], v[i + 5]); w.w = umma::pack_bf16x2(v[i + 6], v[i + 7]);
+          }
+          *reinterpret_cast<uint4*>(slab + umma::sw128_offset(lane, 4 * half + c)) = w;
+        }
+        const bool last_chunk = half == 1 || n0 + 32 >= g.N || ch + 1 >= NCH;
+        if (last_chunk) {
+          umma::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(map_c16, slab, n0 - 32 * half, row0);
+            tma_store_commit();
+          }
+          ++slab_i;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int GSTAGES>
 __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_w,
@@ -73,10 +157,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t A_BYTES = GM * GK * 2, W_BYTES = BN * GK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
   constexpr uint32_t SLAB_BYTES = 32 * 128;   // 32 rows x 128 bytes, one TMA-store box
-  uint8_t* slabs = smem + GSTAGES * STAGE_BYTES;            // 4 epilogue warps x 2 slabs
+  uint8_t* slabs = smem + GSTAGES * STAGE_BYTES;            // GEPI_WARPS x 2 slabs
   __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[GACC][BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles_m = (g.M + GM - 1) / GM;
@@ -95,7 +178,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
     for (int i = 0; i < GACC; ++i) {
       umma::mbar_init(&acc_full[i], 1);
-      umma::mbar_init(&acc_empty[i], 4);   // one arrival per epilogue warp
+      umma::mbar_init(&acc_empty[i], GEPI_WARPS);   // one arrival per epilogue warp
     }
     umma::fence_mbar_init();
   }
@@ -145,9 +228,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 -> TMEM lane quarters 2, 3, 0, 1 =====
-    const int q = warp & 3;
-    const int et = (warp - 2) * 32 + lane;   // 0..127 over the epilogue warps
+    // ===== epilogue: warps 2..9; warp w drains TMEM lane quarter w & 3, column half (w - 2) >> 2 =====
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * 2u * SLAB_BYTES;
     uint32_t tcount = 0, slab_i = 0;
@@ -155,78 +237,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int64_t mb = tile / tiles_n;
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
-      // bias of this tile's columns -> shared memory (the stage's previous user finished two tiles ago)
-      for (int i = et; i < BN; i += 128) {
-        const int n = nb * BN + i;
-        bias_s[as][i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
       umma::mbar_wait(&acc_full[as], aph);
       umma::tc_fence_after_sync();
-      const int row0 = (int)(mb * GM) + q * 32;         // first row of this warp's slab
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int n0 = nb * BN + c0;
-        if (n0 >= g.N) break;   // warp-uniform: the remaining columns are outside the matrix
-        uint32_t r[32];
-        umma::tmem_ld32(tmem_base + lane_base + as * BN + c0, r);
-        umma::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]) + bias_s[as][c0 + i];
-          if (g.relu) x = fmaxf(x, 0.f);
-          v[i] = x;
-        }
-        if (g.out32 != nullptr) {
-          uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
-          tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(slab + umma::sw128_offset(lane, c)) =
-                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          umma::fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&map_c32, slab, n0, row0);
-            tma_store_commit();
-          }
-          ++slab_i;
-        }
-        if (g.out16 != nullptr) {
-          // two 32-column chunks share one 128-byte slab row: even chunk -> bytes [0, 64), odd chunk -> [64, 128)
-          uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
-          const int half = (c0 >> 5) & 1;
-          if (half == 0) {
-            tma_store_wait_read<1>();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 w;
-            const int i = 8 * c;
-            if (g.fmt == umma::kFmtF16) {
-              w.x = umma::pack_f16x2(v[i], v[i + 1]); w.y = umma::pack_f16x2(v[i + 2], v[i + 3]);
-              w.z = umma::pack_f16x2(v[i + 4], v[i + 5]); w.w = umma::pack_f16x2(v[i + 6], v[i + 7]);
-            } else {
-              w.x = umma::pack_bf16x2(v[i], v[i + 1]); w.y = umma::pack_bf16x2(v[i + 2], v[i + 3]);
-              w.z = umma::pack_bf16x2(v[i + 4], v[i + 5]); w.w = umma::pack_bf16x2(v[i + 6], v[i + 7]);
-            }
-            *reinterpret_cast<uint4*>(slab + umma::sw128_offset(lane, 4 * half + c)) = w;
-          }
-          const bool last_chunk = half == 1 || n0 + 32 >= g.N || c0 + 32 >= BN;
-          if (last_chunk) {
-            umma::fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&map_c16, slab, n0 - 32 * half, row0);
-              tma_store_commit();
-            }
-            ++slab_i;
-          }
-        }
-      }
+      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN,
+                                (int)(mb * GM) + q * 32, chalf * (BN / 2), my_slabs, slab_i, lane);
       umma::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -238,6 +252,175 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
   umma::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem_base, GACC * BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-SM variant (N > 128): a cluster of two CTAs owns a 256 x 256 output tile and the even CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) for the pair.  Each CTA stages only ITS 128 rows of A and ITS 128 of the 256
+// W rows per K block — 32 KB instead of 48 KB per 128 x 256 x 64 of work — which is what lifts the kernel off the
+// L2 -> SM bandwidth ceiling the one-SM tiling sits on (128 x 256 tiles with K = 512 need ~11.5 TB/s of L2 reads at
+// 1 PFLOP/s; the L2 delivers ~12 TB/s).  Protocol (all mbarriers count 1 unless noted):
+//   full[s]      in the LEADER's shared memory; the leader's producer expects the bytes of BOTH CTAs' copies, the
+//                follower's TMA loads complete on it (cp.async.bulk.tensor ... .cta_group::2, remote mbarrier);
+//   empty[s]     one per CTA; the leader's MMA warp releases both with one multicast tcgen05.commit;
+//   acc_full[a]  one per CTA, same multicast commit after the last K block;
+//   acc_empty[a] in the leader (count 16): every epilogue warp of both CTAs arrives (the follower's remotely).
+// Each CTA's epilogue drains its own 128 TMEM lanes exactly like the one-SM kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int G2_BN = 256;          // tile columns (UMMA N); each CTA stages G2_BN / 2 rows of W
+constexpr int G2_STAGES = 5;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {   // shared::cta -> shared::cluster of `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D TMA load into this CTA's shared memory, completion bytes on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(umma::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread -> arrive on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   umma::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
+    gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_c16, const __grid_constant__ CUtensorMap map_c32, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BN = G2_BN, WROWS = G2_BN / 2, GSTAGES = G2_STAGES;
+  constexpr uint32_t A_BYTES = GM * GK * 2, W_BYTES = WROWS * GK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  constexpr uint32_t SLAB_BYTES = 32 * 128;
+  uint8_t* slabs = smem + GSTAGES * STAGE_BYTES;
+  __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int64_t tiles_m = (g.M + 2 * GM - 1) / (2 * GM);
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int64_t n_tiles = tiles_m * tiles_n;
+  const int k_blocks = (g.K + GK - 1) / GK;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(&tmem_slot)),
+                 "r"((uint32_t)(GACC * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < GSTAGES; ++i) {
+      umma::mbar_init(&full_bar[i], 1);
+      umma::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < GACC; ++i) {
+      umma::mbar_init(&acc_full[i], 1);
+      umma::mbar_init(&acc_empty[i], 2 * GEPI_WARPS);   // every epilogue warp of both CTAs
+    }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything signals them
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A, own 128 rows of the W tile =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int64_t mb = tile / tiles_n;
+        const int nb = (int)(tile - mb * tiles_n);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          umma::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          if (rank == 0) umma::mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          const uint32_t bar = mapa_rank(umma::smem_u32(&full_bar[s]), 0);
+          tma_load_2d_2sm(sa, &map_a, kb * GK, (int)(mb * 2 * GM + rank * GM), bar);
+          tma_load_2d_2sm(sa + A_BYTES, &map_w, kb * GK, nb * BN + (int)rank * WROWS, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA drives both tensor cores =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma::instr_desc_16bit(2 * GM, BN, g.fmt);
+      uint32_t it = 0, tcount = 0;
+      for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
+        const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+        umma::mbar_wait(&acc_empty[as], aph ^ 1u);   // both epilogues have drained this accumulator stage
+        umma::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          umma::mbar_wait(&full_bar[s], ph);
+          umma::tc_fence_after_sync();
+          const uint32_t sa = umma::smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma::smem_desc_sw128(sa), dw = umma::smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GK / 16; ++k) mma_f16_ss_2sm(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
+          mma_commit_2sm(&empty_bar[s]);
+        }
+        mma_commit_2sm(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warps 2..9 over this CTA's 128 rows; lane quarter w & 3, column half (w - 2) >> 2 =====
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * 2u * SLAB_BYTES;
+    const uint32_t acc_empty_leader0 = mapa_rank(umma::smem_u32(&acc_empty[0]), 0);
+    uint32_t tcount = 0, slab_i = 0;
+    for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
+      const int64_t mb = tile / tiles_n;
+      const int nb = (int)(tile - mb * tiles_n);
+      const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+      umma::mbar_wait(&acc_full[as], aph);
+      umma::tc_fence_after_sync();
+      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN,
+                                (int)(mb * 2 * GM) + (int)rank * GM + q * 32, chalf * (BN / 2), my_slabs, slab_i, lane);
+      umma::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + as * (uint32_t)sizeof(uint64_t));
+    }
+    tma_store_wait_read<0>();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // nobody retires while its peer may still signal its barriers or read its shared memory
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(GACC * BN)) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -295,17 +478,6 @@ int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* b
   BFB_REQUIRE(out32 == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(out32) & 15u) == 0),
               BFB200_ERR_UNSUPPORTED, "fp32 GEMM output needs a row pitch (%lld) that is a multiple of 4 elements and a "
               "16-byte aligned buffer", (long long)ldc);
-  const int BN = N > 128 ? 256 : 128;
-  CUtensorMap map_a, map_w, map_c16, map_c32;
-  BFB_CALL(make_map(&map_a, A, M, K, a_pitch, GM, fmt));
-  BFB_CALL(make_map(&map_w, W, N, K, K, BN, fmt));
-  // outputs: 32-row x 128-byte store boxes; an absent output reuses the other's map (never dereferenced)
-  if (out16 != nullptr) BFB_CALL(make_map(&map_c16, out16, M, N, ldc, 32, fmt, 2));
-  if (out32 != nullptr) BFB_CALL(make_map(&map_c32, out32, M, N, ldc, 32, fmt, 4));
-  if (out16 == nullptr) map_c16 = map_c32;
-  if (out32 == nullptr) map_c32 = map_c16;
-  GemmArgs g;
-  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = ldc;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -313,10 +485,33 @@ int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* b
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
+  static const bool one_sm_only = getenv("BFB200_GEMM_1SM") != nullptr;   // A/B switch for measurements
+  const bool two_sm = N > 128 && !one_sm_only;
+  const int BN = N > 128 ? 256 : 128;
+  CUtensorMap map_a, map_w, map_c16, map_c32;
+  BFB_CALL(make_map(&map_a, A, M, K, a_pitch, GM, fmt));
+  BFB_CALL(make_map(&map_w, W, N, K, K, two_sm ? G2_BN / 2 : BN, fmt));
+  // outputs: 32-row x 128-byte store boxes; an absent output reuses the other's map (never dereferenced)
+  if (out16 != nullptr) BFB_CALL(make_map(&map_c16, out16, M, N, ldc, 32, fmt, 2));
+  if (out32 != nullptr) BFB_CALL(make_map(&map_c32, out32, M, N, ldc, 32, fmt, 4));
+  if (out16 == nullptr) map_c16 = map_c32;
+  if (out32 == nullptr) map_c32 = map_c16;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = ldc;
+  if (two_sm) {
+    const int64_t n_tiles = ((M + 2 * GM - 1) / (2 * GM)) * ((N + G2_BN - 1) / G2_BN);
+    const int64_t max_clusters = sms / 2;
+    const int grid = 2 * (int)(n_tiles < max_clusters ? n_tiles : max_clusters);
+    const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
+    cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm2_tc_kernel<<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, g);
+    BFB_LAUNCH_CHECK("gemm_tc_kernel", st);
+    return BFB200_OK;
+  }
   const int64_t n_tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   const int stages = BN == 256 ? 3 : 4;
-  const size_t smem = 1024 + (size_t)stages * (GM * GK * 2 + BN * GK * 2) + 8 * 32 * 128;
+  const size_t smem = 1024 + (size_t)stages * (GM * GK * 2 + BN * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
   if (BN == 256) {
     cudaFuncSetAttribute(gemm_tc_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     gemm_tc_kernel<256, 3><<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, g);
