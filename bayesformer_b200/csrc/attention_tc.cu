@@ -125,36 +125,61 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   umma::tc_fence_after_sync();
 
   // ---- softmax over the keys j <= query position; two threads per query row, alternating 32-key chunks ----
+  // A warp's 32 rows are queries m0 + 32 w + lane and a chunk is 32 keys, so every chunk is, for the WHOLE warp,
+  // either entirely visible (c0 + 31 <= first query of the warp), the diagonal one (c0 = first query: key i of the
+  // chunk is visible to lane l iff i <= l), or entirely masked — no per-element causal test outside the diagonal
+  // (generate_subsequent_mask, transformer.py:275-287).
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int lane = tid & 31;
   const int tq = m0 + row;                       // query position inside the sequence
   const bool q_ok = tq < a.len;
-  const int last_key = q_ok ? tq : -1;           // causal mask (generate_subsequent_mask, transformer.py:275-287)
-  // 32-key chunks past the last query of this warp are masked for all of its rows: no reads, P = 0 (warp-uniform)
-  const int warp_last_key = min(a.len - 1, m0 + (warp & 3) * 32 + 31);
-  float mx = -INFINITY;
-  for (int c0 = 32 * half; c0 < kvp && c0 <= warp_last_key; c0 += 64) {
+  const int warp_first = m0 + (warp & 3) * 32;   // first query row of this warp = its diagonal chunk
+  const float cs = a.inv_sqrt_dh * 1.4426950408889634f;   // scores / sqrt(dh), as a base-2 exponent
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  for (int c0 = 32 * half; c0 <= warp_first && c0 < kvp; c0 += 64) {
     uint32_t r[32];
     umma::tmem_ld32(tmem_base + lane_base + c0, r);
     umma::tmem_ld_wait();
+    if (c0 < warp_first) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (c0 + i <= last_key) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));     mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, i <= lane ? __uint_as_float(r[i]) : -INFINITY);
+        mx1 = fmaxf(mx1, i + 1 <= lane ? __uint_as_float(r[i + 1]) : -INFINITY);
+        mx2 = fmaxf(mx2, i + 2 <= lane ? __uint_as_float(r[i + 2]) : -INFINITY);
+        mx3 = fmaxf(mx3, i + 3 <= lane ? __uint_as_float(r[i + 3]) : -INFINITY);
+      }
+    }
   }
+  float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   s_max[half][row] = mx;
   __syncthreads();
-  mx = fmaxf(mx, s_max[half ^ 1][row]);
-  float sum = 0.f;
+  mx = fmaxf(mx, s_max[half ^ 1][row]);   // finite: key 0 is visible to every query
+  const float nmx = -mx * cs;
+  float sm0 = 0.f, sm1 = 0.f, sm2 = 0.f, sm3 = 0.f;
   for (int c0 = 32 * half; c0 < kvp; c0 += 64) {
     float e[32];
-    if (c0 <= warp_last_key) {
+    if (c0 <= warp_first) {
       uint32_t r[32];
       umma::tmem_ld32(tmem_base + lane_base + c0, r);
       umma::tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        e[i] = (c0 + i <= last_key) ? __expf((__uint_as_float(r[i]) - mx) * a.inv_sqrt_dh) : 0.f;
-        sum += e[i];
+        float ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(r[i]), cs, nmx)));
+        e[i] = ex;
       }
+      if (c0 == warp_first) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = i <= lane ? e[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) { sm0 += e[i]; sm1 += e[i + 1]; sm2 += e[i + 2]; sm3 += e[i + 3]; }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) e[i] = 0.f;
@@ -169,6 +194,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
       *reinterpret_cast<uint4*>(slab + umma::sw128_offset(row, ch0 + c)) = w;
     }
   }
+  float sum = (sm0 + sm1) + (sm2 + sm3);
   s_sum[half][row] = sum;
   umma::fence_async_smem();
   umma::tc_fence_before_sync();
