@@ -62,7 +62,83 @@ struct GemmArgs {
   int relu;
   uint32_t fmt;            // umma::kFmtF16 / kFmtBF16
   int64_t ldc;             // output row pitch in elements (= N)
+  // fused epilogues of the tensor-core transformer path (launch_gemm_tc_ex):
+  int resid;               // two-SM kernel: out16 = acc (+ bias) + R16, a 16-bit matrix shaped like the output whose tiles the
+                           // TMA producer streams through the operand ring (map_r)
+  float2* stats_out;       // with resid: per-row (sum, sum of squares) of the fp32 result, accumulated atomically
+  const float2* stats_in;  // row-affine mode: out = rstd_r * (acc - mean_r * col_s[n]) + col_c[n], (mean, rstd) from the
+  const float* col_s;      //   (sum, sum of squares) of a row of `stats_width` values — LayerNorm folded into this product
+  const float* col_c;
+  float stats_inv_width, stats_eps;
+  int vec_ok;              // bias / col_s / col_c are 16-byte aligned: full chunks read them with 128-bit loads
 };
+
+// The arithmetic of one 32-column chunk of one accumulator row.  FULL: all 32 columns are inside the matrix and the
+// per-column vectors are 16-byte aligned (128-bit broadcast loads, no guards).
+//   plain     : v = acc (+ bias) (ReLU)
+//   affine    : v = rstd (acc - mean col_s) + col_c (ReLU)            LayerNorm folded into this product
+//   residual  : v += R16 row (read from the ring slot TMA filled), and the row's running sum / sum of squares
+template <bool FULL>
+__device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&acc)[32], float (&v)[32], int n0, float r_mean,
+                                           float r_rstd, const uint8_t* box, int resid_row, int half, float& st_sum,
+                                           float& st_sq) {
+  auto load32 = [&](const float* src, float (&dst)[32]) {
+    if (FULL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + n0) + i);
+        dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = n0 + i < g.N ? __ldg(src + n0 + i) : 0.f;
+    }
+  };
+  if (g.stats_in != nullptr) {
+    float cs_[32];
+    load32(g.col_s, cs_);
+    load32(g.col_c, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(r_rstd, fmaf(-r_mean, cs_[i], __uint_as_float(acc[i])), v[i]);
+  } else if (g.bias != nullptr) {
+    load32(g.bias, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(acc[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  }
+  if (g.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (g.resid) {
+    // chunk = bytes [64 half, +64) of row `resid_row` of a swizzled box of 128 rows x 64 columns
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 w = *reinterpret_cast<const uint4*>(box + umma::sw128_offset((uint32_t)resid_row, 4 * half + c));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (g.fmt == umma::kFmtF16) {   // v += x: one mixed-precision FMA against a packed 1.0 per value
+          v[8 * c + 2 * k] = umma::fh_ll(ww[k], 0x3C003C00u, v[8 * c + 2 * k]);
+          v[8 * c + 2 * k + 1] = umma::fh_hl(ww[k], 0x3C003C00u, v[8 * c + 2 * k + 1]);
+        } else {
+          v[8 * c + 2 * k] += umma::bf16_lo(ww[k]);
+          v[8 * c + 2 * k + 1] += umma::bf16_hi(ww[k]);
+        }
+      }
+    }
+    if (g.stats_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = (FULL || n0 + i < g.N) ? v[i] : 0.f;
+        st_sum += x;
+        st_sq = fmaf(x, x, st_sq);
+      }
+    }
+  }
+}
 
 // Epilogue of one accumulator stage for one warp: columns [c_begin, c_begin + 32 * NCH) of its 32 TMEM lanes ->
 // (+ bias)(ReLU) -> swizzled 32-row slabs -> 2-D TMA stores.  The tcgen05.ld of chunk i + 1 is in flight while chunk
@@ -70,9 +146,16 @@ struct GemmArgs {
 template <int NCH>
 __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtensorMap* map_c16, const CUtensorMap* map_c32,
                                                  uint32_t tacc, int n_base, int row0,
-                                                 int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane) {
+                                                 int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane,
+                                                 const uint8_t* resid_rows, int resid_row) {
   constexpr uint32_t SLAB_BYTES = 32 * 128;
-  const bool has_bias = g.bias != nullptr;
+  const bool affine = g.stats_in != nullptr;
+  float r_mean = 0.f, r_rstd = 1.f, st_sum = 0.f, st_sq = 0.f;
+  if (affine && row0 + lane < g.M) {   // thread = output row: its LayerNorm statistics
+    const float2 st = __ldg(g.stats_in + row0 + lane);
+    r_mean = st.x * g.stats_inv_width;
+    r_rstd = rsqrtf(fmaxf(st.y * g.stats_inv_width - r_mean * r_mean, 0.f) + g.stats_eps);
+  }
   uint32_t r[2][32];
   if (n_base + c_begin < g.N) umma::tmem_ld32(tacc + c_begin, r[0]);
 #pragma unroll
@@ -83,18 +166,11 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
       umma::tmem_ld_wait();
       if (ch + 1 < NCH && n0 + 32 < g.N) umma::tmem_ld32(tacc + c0 + 32, r[(ch + 1) & 1]);
       float v[32];
-      if (has_bias) {   // the same 32 addresses for every lane: broadcast loads that hit L1 after the first tile row
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = n0 + i < g.N ? __ldg(g.bias + n0 + i) : 0.f;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = __uint_as_float(r[ch & 1][i]) + v[i];
-        v[i] = g.relu ? fmaxf(x, 0.f) : x;
-      }
+      const uint8_t* box = resid_rows + (uint32_t)(ch >> 1) * (GM * 128u);
+      if (n0 + 32 <= g.N && g.vec_ok)   // warp-uniform: the whole chunk is inside the matrix -> no per-column guards
+        chunk_math<true>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
+      else
+        chunk_math<false>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
       if (g.out32 != nullptr) {
         uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
         tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
@@ -144,6 +220,10 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
         }
       }
     }
+  }
+  if (g.resid && g.stats_out != nullptr && row0 + lane < g.M) {
+    atomicAdd(&g.stats_out[row0 + lane].x, st_sum);
+    atomicAdd(&g.stats_out[row0 + lane].y, st_sq);
   }
 }
 
@@ -237,10 +317,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int64_t mb = tile / tiles_n;
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+      const int row0 = (int)(mb * GM) + q * 32;
       umma::mbar_wait(&acc_full[as], aph);
       umma::tc_fence_after_sync();
-      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN,
-                                (int)(mb * GM) + q * 32, chalf * (BN / 2), my_slabs, slab_i, lane);
+      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
+                                my_slabs, slab_i, lane, nullptr, 0);
       umma::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -311,14 +392,15 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const __grid_constant__ CUtensorMap map_c16, const __grid_constant__ CUtensorMap map_c32, const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap map_c16, const __grid_constant__ CUtensorMap map_c32,
+                    const __grid_constant__ CUtensorMap map_r, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BN = G2_BN, WROWS = G2_BN / 2, GSTAGES = G2_STAGES;
   constexpr uint32_t A_BYTES = GM * GK * 2, W_BYTES = WROWS * GK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
   constexpr uint32_t SLAB_BYTES = 32 * 128;
   uint8_t* slabs = smem + GSTAGES * STAGE_BYTES;
-  __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
+  __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], rfull_bar[GSTAGES], acc_full[GACC], acc_empty[GACC];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,6 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     for (int i = 0; i < GSTAGES; ++i) {
       umma::mbar_init(&full_bar[i], 1);
       umma::mbar_init(&empty_bar[i], 1);
+      umma::mbar_init(&rfull_bar[i], 1);
     }
     for (int i = 0; i < GACC; ++i) {
       umma::mbar_init(&acc_full[i], 1);
@@ -368,21 +451,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           tma_load_2d_2sm(sa, &map_a, kb * GK, (int)(mb * 2 * GM + rank * GM), bar);
           tma_load_2d_2sm(sa + A_BYTES, &map_w, kb * GK, nb * BN + (int)rank * WROWS, bar);
         }
+        if (g.resid) {
+          // the tile's residual rows of this CTA ride the same ring: one slot per 128 output columns (two swizzled boxes of
+          // 128 rows x 64 columns), completion on this CTA's own rfull barrier; the epilogue warps hand the slot back
+          const int n_rs = nb * BN + 128 < g.N ? 2 : 1;
+          for (int rs = 0; rs < n_rs; ++rs, ++it) {
+            const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+            umma::mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* sr = smem + s * STAGE_BYTES;
+            umma::mbar_expect_tx(&rfull_bar[s], 2u * GM * 128u);
+            tma_load_2d(sr, &map_r, nb * BN + rs * 128, (int)(mb * 2 * GM + rank * GM), &rfull_bar[s]);
+            tma_load_2d(sr + GM * 128, &map_r, nb * BN + rs * 128 + 64, (int)(mb * 2 * GM + rank * GM), &rfull_bar[s]);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the leader CTA drives both tensor cores =====
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = umma::instr_desc_16bit(2 * GM, BN, g.fmt);
-      uint32_t it = 0, tcount = 0;
+      // full_bar[s] completes a phase only when slot s carries operands (residual slots complete rfull_bar instead),
+      // so its parity is tracked per slot rather than derived from the ring position
+      uint32_t it = 0, tcount = 0, fphase = 0;
       for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
         const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
         umma::mbar_wait(&acc_empty[as], aph ^ 1u);   // both epilogues have drained this accumulator stage
         umma::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
-          umma::mbar_wait(&full_bar[s], ph);
+          const uint32_t s = it % GSTAGES;
+          umma::mbar_wait(&full_bar[s], (fphase >> s) & 1u);
+          fphase ^= 1u << s;
           umma::tc_fence_after_sync();
           const uint32_t sa = umma::smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = umma::smem_desc_sw128(sa), dw = umma::smem_desc_sw128(sa + A_BYTES);
@@ -391,6 +490,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           mma_commit_2sm(&empty_bar[s]);
         }
         mma_commit_2sm(&acc_full[as]);
+        if (g.resid) {   // the residual slots of this tile are not MMA operands
+          const int64_t mb_ = tile / tiles_n;
+          const int nb_ = (int)(tile - mb_ * tiles_n);
+          it += nb_ * BN + 128 < g.N ? 2u : 1u;
+        }
       }
     }
   } else {
@@ -399,15 +503,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * 2u * SLAB_BYTES;
     const uint32_t acc_empty_leader0 = mapa_rank(umma::smem_u32(&acc_empty[0]), 0);
-    uint32_t tcount = 0, slab_i = 0;
+    uint32_t tcount = 0, slab_i = 0, ring_it = 0, rphase = 0;
     for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
       const int64_t mb = tile / tiles_n;
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
+      const int row0 = (int)(mb * 2 * GM) + (int)rank * GM + q * 32;
       umma::mbar_wait(&acc_full[as], aph);
       umma::tc_fence_after_sync();
-      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN,
-                                (int)(mb * 2 * GM) + (int)rank * GM + q * 32, chalf * (BN / 2), my_slabs, slab_i, lane);
+      const uint8_t* resid_rows = nullptr;
+      uint32_t rslot = 0;
+      const int n_rs = nb * BN + 128 < g.N ? 2 : 1;
+      if (g.resid) {
+        ring_it += (uint32_t)k_blocks;                 // this tile's operand slots
+        for (int rs = 0; rs < n_rs; ++rs) {            // every warp tracks the phase of every residual slot
+          const uint32_t sl = (ring_it + (uint32_t)rs) % GSTAGES;
+          if (rs == chalf) {
+            rslot = sl;
+            umma::mbar_wait(&rfull_bar[sl], (rphase >> sl) & 1u);
+            resid_rows = smem + sl * STAGE_BYTES;
+          }
+          rphase ^= 1u << sl;
+        }
+      }
+      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
+                                my_slabs, slab_i, lane, resid_rows, q * 32 + lane);
+      if (g.resid) {
+        if (chalf < n_rs) {   // the four warps that read this slot hand it back to the producer
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + chalf) : "memory");
+          if (q == 0 && lane == 0) mbar_arrive(&empty_bar[rslot]);
+        }
+        ring_it += (uint32_t)n_rs;
+      }
       umma::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + as * (uint32_t)sizeof(uint64_t));
@@ -466,7 +593,18 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t pi
 
 int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
                    int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, cudaStream_t st) {
+  return launch_gemm_tc_ex(A, a_pitch, W, bias, out16, out32, ldc, M, N, K, relu, fmt, GemmFusion(), st);
+}
+
+int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
+                      int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, const GemmFusion& fu, cudaStream_t st) {
   if (M == 0 || N == 0) return BFB200_OK;
+  BFB_REQUIRE(fu.resid16 == nullptr || (fu.resid16 != out16 && (reinterpret_cast<uintptr_t>(fu.resid16) & 15u) == 0 &&
+                                        (fu.resid_pitch & 7) == 0 && (N & 7) == 0),
+              BFB200_ERR_INVALID_ARG, "a residual operand needs its own 16-byte aligned buffer, a row pitch and an N that are "
+              "multiples of 8");
+  BFB_REQUIRE(fu.stats_in == nullptr || (fu.col_s != nullptr && fu.col_c != nullptr && fu.stats_width > 0),
+              BFB200_ERR_INVALID_ARG, "row-affine epilogue needs col_s, col_c and stats_width");
   BFB_REQUIRE((K & 7) == 0 && (a_pitch & 7) == 0, BFB200_ERR_UNSUPPORTED,
               "tensor-core GEMM needs K (%d) and the A row pitch (%lld) to be multiples of 8", K, (long long)a_pitch);
   BFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0,
@@ -498,13 +636,21 @@ int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* b
   if (out32 == nullptr) map_c32 = map_c16;
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out16 = out16; g.out32 = out32; g.relu = relu; g.fmt = fmt; g.ldc = ldc;
+  g.resid = fu.resid16 != nullptr ? 1 : 0;
+  BFB_REQUIRE(!g.resid || two_sm, BFB200_ERR_UNSUPPORTED, "the residual epilogue is served by the two-SM kernel (N > 128)");
+  CUtensorMap map_r = map_c16;
+  if (g.resid) BFB_CALL(make_map(&map_r, fu.resid16, M, N, fu.resid_pitch, GM, fmt, 2));
+  g.stats_out = fu.stats_out; g.stats_in = fu.stats_in; g.col_s = fu.col_s; g.col_c = fu.col_c;
+  g.stats_inv_width = fu.stats_width > 0 ? 1.0f / (float)fu.stats_width : 0.f;
+  g.stats_eps = fu.stats_eps;
+  g.vec_ok = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(fu.col_s) | reinterpret_cast<uintptr_t>(fu.col_c)) & 15u) == 0;
   if (two_sm) {
     const int64_t n_tiles = ((M + 2 * GM - 1) / (2 * GM)) * ((N + G2_BN - 1) / G2_BN);
     const int64_t max_clusters = sms / 2;
     const int grid = 2 * (int)(n_tiles < max_clusters ? n_tiles : max_clusters);
     const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
     cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm2_tc_kernel<<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, g);
+    gemm2_tc_kernel<<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, map_r, g);
     BFB_LAUNCH_CHECK("gemm_tc_kernel", st);
     return BFB200_OK;
   }

@@ -18,6 +18,8 @@ int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, 
                     const float* gamma, const float* beta, float eps, const MaskSource& ms,
                     int branch_site, int out_site, cudaStream_t st, void* out16 = nullptr, uint32_t fmt = 0,
                     const void* y16 = nullptr);
+int launch_ln16_apply(const void* v16, const float2* stats, void* out16, int64_t n_rows, int len, int d, const float* gamma,
+                      const float* beta, float eps, const MaskSource& ms, int out_site, uint32_t fmt, cudaStream_t st);
 int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme, int mode,
                       float temperature, const MaskSource& ms, const int32_t* forced, int32_t* tokens,
                       int tok_stride, int write_pos, float* seq_scores, float* logp_out, cudaStream_t st,
@@ -25,6 +27,10 @@ int launch_score_step(const float* logits, int64_t n_seq, int vocab, int scheme,
 int launch_logsoftmax_seqfirst(const float* logits, int64_t n_seq, int len, int vocab, float* out,
                                cudaStream_t st, int pitch = 0);
 int launch_to16(const float* src, void* dst, int64_t n, uint32_t fmt, cudaStream_t st);
+// LayerNorm folded into the product that consumes it: w16g = W * diag(gamma) (16-bit), col_s[n] = sum_k w16g[n, k],
+// col_c[n] = sum_k W[n, k] beta[k] + b[n]; W (L, N, K), b (L, N), gamma / beta (L, K)
+int launch_fold_ln_pack(const float* W, const float* b, const float* gamma, const float* beta, int L, int N, int K,
+                        uint32_t fmt, void* w16g, float* col_s, float* col_c, cudaStream_t st);
 int launch_reduce_draws(const float* seq_scores, int64_t n_items_chunk, int n_draws, float* dst,
                         cudaStream_t st);
 int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, float* pool_scores,
@@ -43,6 +49,23 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
 // TMA-fed tcgen05 GEMM (gemm_tc.cu): C = A W^T (+ bias)(ReLU), 16-bit operands (fmt: umma::kFmtF16 / kFmtBF16)
 int launch_gemm_tc(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
                    int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, cudaStream_t st);
+// Fused epilogues of the same kernel:
+//   resid16 / stats_out : out16 = acc (+ bias) + R16, and (sum, sum of squares) of every fp32 result row accumulated
+//                         atomically into stats_out (M float2, zeroed by the caller) — residual add + LayerNorm statistics;
+//   stats_in / col_s / col_c : out = rstd_r * (acc - mean_r * col_s[n]) + col_c[n] (ReLU) — a LayerNorm folded into the
+//                         product that consumes it ((mean, rstd) of row r from stats_in over stats_width values).
+struct GemmFusion {
+  const void* resid16 = nullptr;
+  int64_t resid_pitch = 0;
+  float2* stats_out = nullptr;
+  const float2* stats_in = nullptr;
+  const float* col_s = nullptr;
+  const float* col_c = nullptr;
+  int stats_width = 0;
+  float stats_eps = 0.f;
+};
+int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float* bias, void* out16, float* out32,
+                      int64_t ldc, int64_t M, int N, int K, int relu, uint32_t fmt, const GemmFusion& fu, cudaStream_t st);
 
 
 // tcgen05 causal attention for heads of width 64 (attention_tc.cu): qkv16 (R, 3d) -> out16 (R, d)

@@ -188,24 +188,10 @@ __device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, u
 }
 
 
-// Mixed-precision FMA, d = a * b + c with fp16 a, b taken straight from a half of a packed word and fp32 c, d
-// (PTX fma.rn.f32.f16, SASS FHFMA with .H0/.H1 operand selectors): the attention phase multiplies the fp16 Q / K / V
-// tiles without unpacking them.  The product of two fp16 values is exact in fp32, so this is the arithmetic of
-// "unpack, then FFMA" at half the instructions.
-#define BFB_FH(NAME, ASEL, BSEL)                                                                              \
-  __device__ __forceinline__ float NAME(uint32_t a, uint32_t b, float c) {                                    \
-    float d;                                                                                                  \
-    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"                  \
-        "fma.rn.f32.f16 %0, " ASEL ", " BSEL ", %3;\n\t}"                                                     \
-        : "=f"(d)                                                                                             \
-        : "r"(a), "r"(b), "f"(c));                                                                            \
-    return d;                                                                                                 \
-  }
-BFB_FH(fh_ll, "al", "bl")
-BFB_FH(fh_hh, "ah", "bh")
-BFB_FH(fh_lh, "al", "bh")
-BFB_FH(fh_hl, "ah", "bl")
-#undef BFB_FH
+using umma::fh_ll;
+using umma::fh_hh;
+using umma::fh_lh;
+using umma::fh_hl;
 
 __device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b) {
   float d = fh_ll(a.x, b.x, 0.f);

@@ -23,6 +23,7 @@ struct Workspace {
   uint16_t* att16;  // (R, d) attention output, then LayerNorm1 output
   uint16_t* h16;    // (R, F)
   float* x2;        // (R, d) next block input
+  float2* stats;    // (R) per-row (sum, sum of squares) of LayerNorm1's input
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -45,9 +46,12 @@ static uint32_t tc_fmt(const bfb200_transformer& m) {
 }
 static int logits_pitch(const bfb200_transformer& m) { return use_tc(m) ? (m.ntoken + 3) & ~3 : m.ntoken; }
 
-// 16-bit weight image of the layered tensor-core path: [W_qkv | W_out | FFN W1 | FFN W2 | head], element offsets
+// 16-bit weight image of the layered tensor-core path: [W_qkv | W_out | FFN W1 | FFN W2 | head | W1 * gamma1 |
+// col_s (fp32) | col_c (fp32)], offsets in 16-bit elements.  The last three serve LayerNorm1 folded into the first
+// FFN product (forward_chunk_tc): W1g = W1 * diag(gamma1), col_s[n] = sum_k W1g[n, k] (of the ROUNDED 16-bit values
+// the tensor core multiplies), col_c = W1 beta1 + b1.
 struct TcImage {
-  size_t qkv, out, ff1, ff2, head, elems;
+  size_t qkv, out, ff1, ff2, head, ff1g, col_s, col_c, elems;
 };
 static TcImage tc_image(const bfb200_transformer& m) {
   const size_t L = m.n_layers, d = m.d_model, F = m.d_ff, V = m.ntoken;
@@ -57,7 +61,10 @@ static TcImage tc_image(const bfb200_transformer& m) {
   t.ff1 = t.out + L * d * d;
   t.ff2 = t.ff1 + L * F * d;
   t.head = t.ff2 + L * d * F;
-  t.elems = t.head + V * d;
+  t.ff1g = (t.head + V * d + 7) & ~(size_t)7;
+  t.col_s = t.ff1g + L * F * d;
+  t.col_c = t.col_s + 2 * L * F;
+  t.elems = t.col_c + 2 * L * F;
   return t;
 }
 
@@ -69,7 +76,7 @@ static size_t workspace_bytes(const bfb200_transformer& m, int64_t n_seq, int ma
   if (use_tc(m)) {
     const size_t Vp = (size_t)logits_pitch(m);
     return 256 + align256((size_t)n_seq * max_len * sizeof(int32_t)) + 3 * align256(R * d * 4) +
-           2 * align256(R * d * 2) + align256(R * 3 * d * 2) + align256(R * F * 2) +
+           2 * align256(R * d * 2) + align256(R * 3 * d * 2) + align256(R * F * 2) + align256(R * 8) +
            align256((full_logits ? R : (size_t)n_seq) * Vp * 4) + align256((size_t)n_seq * 4);
   }
   size_t b = 256;
@@ -104,6 +111,7 @@ static Workspace carve(void* base, const bfb200_transformer& m, int64_t n_seq, i
     w.att16 = (uint16_t*)take(R * d * 2);
     w.qkv16 = (uint16_t*)take(R * 3 * d * 2);
     w.h16 = (uint16_t*)take(R * F * 2);
+    w.stats = (float2*)take(R * 8);
     w.logits = (float*)take((full_logits ? R : (size_t)n_seq) * Vp * 4);
     w.seq_scores = (float*)take((size_t)n_seq * 4);
     w.att = w.x1 = w.qkv = w.h = nullptr;
@@ -197,7 +205,8 @@ static int forward_chunk(const bfb200_transformer& m, Workspace& ws, int64_t S, 
   return BFB200_OK;
 }
 
-// One forward pass of the layered tensor-core path; leaves the last block's output in ws.x (fp32) and ws.x16.
+// One forward pass of the layered tensor-core path; leaves the last block's output in ws.x16 (and, outside the fp16
+// residual-stream mode, in ws.x as fp32).
 static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t S, int len, int tok_stride,
                             const MaskSource& ms, cudaStream_t st) {
   const int d = m.d_model, F = m.d_ff;
@@ -207,8 +216,14 @@ static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t 
   const uint16_t* w16 = (const uint16_t*)m.fused_image;
   BFB_REQUIRE(len <= m.pe_len, BFB200_ERR_INVALID_ARG, "sequence length %d exceeds the positional table (%d)", len, m.pe_len);
   BFB_REQUIRE(len <= 256, BFB200_ERR_UNSUPPORTED, "the tensor-core attention kernel takes sequences of at most 256 tokens (got %d)", len);
-  BFB_CALL(launch_embed(ws.tokens, tok_stride, m.embedding, m.pe, S, len, d, ms, (fl & BFB200_SITE_EMBED) ? 0 : -1, ws.x, st,
-                        ws.x16, fmt));
+  // fp16 operands and none of the latent dropout sites around the residual adds (the reference default): the residual
+  // stream itself travels as fp16 — every product's epilogue adds it and accumulates the LayerNorm statistics, the
+  // fp32 copy of x is never written.  (bf16's 8-bit mantissa keeps the fp32 stream.)
+  // (the fused epilogues live in the two-SM GEMM kernel, which serves products with more than 128 output columns)
+  const bool fold = d > 128 && !(fl & (BFB200_SITE_ATTN_RESID | BFB200_SITE_FFN_IN));
+  const bool lite = fold && fmt == umma::kFmtF16 && !(fl & BFB200_SITE_FFN_RESID);
+  BFB_CALL(launch_embed(ws.tokens, tok_stride, m.embedding, m.pe, S, len, d, ms, (fl & BFB200_SITE_EMBED) ? 0 : -1,
+                        lite ? nullptr : ws.x, st, ws.x16, fmt));
   for (int l = 0; l < m.n_layers; ++l) {
     const int sb = 1 + BFB200_SITES_PER_LAYER * l;
     BFB_CALL(launch_gemm_tc(ws.x16, d, w16 + img.qkv + (size_t)l * 3 * d * d, nullptr, ws.qkv16, nullptr, 3 * d, R, 3 * d, d, 0,
@@ -217,13 +232,44 @@ static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t 
                                  (fl & BFB200_SITE_HEAD_OUT) ? sb + 4 : -1, st));
     // the branch outputs (W_out, FFN2) travel as 16-bit: they are added to the fp32 residual stream right away
     uint16_t* y16 = reinterpret_cast<uint16_t*>(ws.y);
-    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, y16, nullptr, d, R, d, d, 0, fmt, st));
-    // LayerNorm1 output only feeds the FFN: 16-bit copy only (att16 is free again)
-    BFB_CALL(launch_resid_ln(ws.x, ws.y, nullptr, R, len, d, m.ln1_w + (size_t)l * d, m.ln1_b + (size_t)l * d, m.ln_eps, ms,
-                             (fl & BFB200_SITE_ATTN_RESID) ? sb + 1 : -1, (fl & BFB200_SITE_FFN_IN) ? sb + 2 : -1, st,
-                             ws.att16, fmt, y16));
-    BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.ff1 + (size_t)l * F * d, m.ff1_b + (size_t)l * F, ws.h16, nullptr, F, R, F, d,
-                            1, fmt, st));
+    if (fold) {
+      // No dropout site touches LayerNorm1's input or output (the reference default, transformer.py:226-228 latent):
+      // LayerNorm1 only feeds the first FFN product, so it is folded into the two products around it instead of
+      // running as a kernel.  W_out's epilogue adds the block input (its 16-bit copy), writes v = x + attn W_out^T
+      // as the next A operand and accumulates each row's sum / sum of squares; the FFN1 product runs on v with
+      // W1 * gamma1 and its epilogue applies rstd (acc - mean col_s) + col_c, ReLU.
+      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(float2), st);
+      BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+      GemmFusion add;
+      add.resid16 = ws.x16; add.resid_pitch = d; add.stats_out = ws.stats;
+      BFB_CALL(launch_gemm_tc_ex(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, y16, nullptr, d, R, d, d, 0, fmt, add, st));
+      GemmFusion ln;
+      ln.stats_in = ws.stats; ln.stats_width = d; ln.stats_eps = m.ln_eps;
+      ln.col_s = reinterpret_cast<const float*>(w16 + img.col_s) + (size_t)l * F;
+      ln.col_c = reinterpret_cast<const float*>(w16 + img.col_c) + (size_t)l * F;
+      BFB_CALL(launch_gemm_tc_ex(y16, d, w16 + img.ff1g + (size_t)l * F * d, nullptr, ws.h16, nullptr, F, R, F, d, 1, fmt, ln, st));
+    } else {
+      BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.out + (size_t)l * d * d, nullptr, y16, nullptr, d, R, d, d, 0, fmt, st));
+      // LayerNorm1 output only feeds the FFN: 16-bit copy only (att16 is free again)
+      BFB_CALL(launch_resid_ln(ws.x, ws.y, nullptr, R, len, d, m.ln1_w + (size_t)l * d, m.ln1_b + (size_t)l * d, m.ln_eps, ms,
+                               (fl & BFB200_SITE_ATTN_RESID) ? sb + 1 : -1, (fl & BFB200_SITE_FFN_IN) ? sb + 2 : -1, st,
+                               ws.att16, fmt, y16));
+      BFB_CALL(launch_gemm_tc(ws.att16, d, w16 + img.ff1 + (size_t)l * F * d, m.ff1_b + (size_t)l * F, ws.h16, nullptr, F, R, F, d,
+                              1, fmt, st));
+    }
+    if (lite) {
+      // v2 = x + FFN(LN1(v1)) (both residuals start from the BLOCK INPUT x, transformer.py:231-233) and its row
+      // statistics come out of the FFN2 product; LayerNorm2 + layer-out dropout is a 16-bit read-modify-write
+      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(float2), st);
+      BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+      GemmFusion add;
+      add.resid16 = ws.x16; add.resid_pitch = d; add.stats_out = ws.stats;
+      BFB_CALL(launch_gemm_tc_ex(ws.h16, F, w16 + img.ff2 + (size_t)l * d * F, m.ff2_b + (size_t)l * d, y16, nullptr, d, R, d, F, 0,
+                                 fmt, add, st));
+      BFB_CALL(launch_ln16_apply(y16, ws.stats, ws.x16, R, len, d, m.ln2_w + (size_t)l * d, m.ln2_b + (size_t)l * d, m.ln_eps, ms,
+                                 (fl & BFB200_SITE_LAYER_OUT) ? sb + 0 : -1, fmt, st));
+      continue;
+    }
     BFB_CALL(launch_gemm_tc(ws.h16, F, w16 + img.ff2 + (size_t)l * d * F, m.ff2_b + (size_t)l * d, y16, nullptr, d, R, d, F, 0,
                             fmt, st));
     // both residuals start from the BLOCK INPUT x (transformer.py:231-233)
@@ -275,6 +321,8 @@ extern "C" int bfb200_fused_pack(const bfb200_transformer* model, void* image, s
   BFB_CALL(launch_to16(m.ff1_w, w16 + img.ff1, (int64_t)(L * F * d), fmt, st));
   BFB_CALL(launch_to16(m.ff2_w, w16 + img.ff2, (int64_t)(L * d * F), fmt, st));
   BFB_CALL(launch_to16(m.head_w, w16 + img.head, (int64_t)(V * d), fmt, st));
+  BFB_CALL(launch_fold_ln_pack(m.ff1_w, m.ff1_b, m.ln1_w, m.ln1_b, (int)L, (int)F, (int)d, fmt, w16 + img.ff1g,
+                               reinterpret_cast<float*>(w16 + img.col_s), reinterpret_cast<float*>(w16 + img.col_c), st));
   return BFB200_OK;
 }
 

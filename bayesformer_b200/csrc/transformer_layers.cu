@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) embed16_kernel(const int32_t* __restrict_
     if (site >= 0) drop8(e, keep8(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)g), ms.scale);
 #pragma unroll
     for (int c = 0; c < 8; ++c) e[c] = e[c] * sqrt_d + p[c];
-    store8_f32(x + i * 8, e);
+    if (x != nullptr) store8_f32(x + i * 8, e);
     store8_16(x16 + i * 8, fmt, e);
   }
 }
@@ -540,6 +540,55 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
       }
     }
   }
+}
+
+// out16 = dropout_out( LayerNorm(v16) ) with the row statistics already known: the GEMM that produced v (its epilogue
+// added the residual) also accumulated each row's sum and sum of squares (launch_gemm_tc_ex), so this kernel is one
+// 16-bit read and one 16-bit write per element (transformer.py:233, :370).  One warp per row.
+template <int NJ>
+__global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restrict__ v16, const float2* __restrict__ stats,
+                                                         uint16_t* __restrict__ out16, int64_t n_rows, int len, int d,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, MaskSource ms, int out_site, uint32_t fmt) {
+  const int lane = threadIdx.x & 31;
+  const int d8 = d >> 3;
+  const float inv_d = 1.0f / (float)d;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
+    const int64_t s = r / len;
+    const uint32_t t = (uint32_t)(r - s * len);
+    const float2 st = __ldg(stats + r);
+    const float mean = st.x * inv_d;
+    const float rstd = rsqrtf(fmaxf(st.y * inv_d - mean * mean, 0.f) + eps);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int g = lane + 32 * j;
+      if (g < d8) {
+        float v[8], gm[8], bt[8];
+        load8_16(v16 + r * d + 8 * g, fmt, v);
+        load8_f32(gamma + 8 * g, gm);
+        load8_f32(beta + 8 * g, bt);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = (v[c] - mean) * rstd * gm[c] + bt[c];
+        if (out_site >= 0) drop8(v, keep8(ms, s, t, (uint32_t)out_site, (uint32_t)g), ms.scale);
+        store8_16(out16 + r * d + 8 * g, fmt, v);
+      }
+    }
+  }
+}
+
+int launch_ln16_apply(const void* v16, const float2* stats, void* out16, int64_t n_rows, int len, int d, const float* gamma,
+                      const float* beta, float eps, const MaskSource& ms, int out_site, uint32_t fmt, cudaStream_t st) {
+  BFB_REQUIRE((d & 7) == 0 && d <= 2048, BFB200_ERR_UNSUPPORTED, "ln16_apply needs d_model %% 8 == 0 and <= 2048 (got %d)", d);
+  const int grid = stride_grid((n_rows + 7) / 8, 8);
+#define LAUNCH_LNA(NJ) ln16_apply_kernel<NJ><<<grid, 256, 0, st>>>((const uint16_t*)v16, stats, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, out_site, fmt)
+  if (d <= 256) LAUNCH_LNA(1);
+  else if (d <= 512) LAUNCH_LNA(2);
+  else if (d <= 1024) LAUNCH_LNA(4);
+  else LAUNCH_LNA(8);
+#undef LAUNCH_LNA
+  BFB_LAUNCH_CHECK("ln16_apply_kernel", st);
+  return BFB200_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -701,6 +750,55 @@ __global__ void to16_kernel(const float* __restrict__ src, uint16_t* __restrict_
     const uint32_t w = fmt == umma::kFmtF16 ? umma::pack_f16x2(src[i], 0.f) : umma::pack_bf16x2(src[i], 0.f);
     dst[i] = (uint16_t)(w & 0xFFFFu);
   }
+}
+
+// one warp per output row n of layer l
+__global__ void __launch_bounds__(256) fold_ln_pack_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int64_t rows_total, int N, int K, uint32_t fmt,
+                                                           uint16_t* __restrict__ w16g, float* __restrict__ col_s,
+                                                           float* __restrict__ col_c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_total) return;
+  const int64_t l = r / N;
+  const float* w = W + r * K;
+  const float* g = gamma + l * K;
+  const float* be = beta + l * K;
+  float s = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wg = w[k] * g[k];
+    uint16_t h;
+    float back;
+    if (fmt == umma::kFmtF16) {
+      const __half hh = __float2half_rn(fminf(fmaxf(wg, -65504.f), 65504.f));
+      h = *reinterpret_cast<const uint16_t*>(&hh);
+      back = __half2float(hh);
+    } else {
+      const __nv_bfloat16 bb = __float2bfloat16_rn(wg);
+      h = *reinterpret_cast<const uint16_t*>(&bb);
+      back = __bfloat162float(bb);
+    }
+    w16g[r * K + k] = h;
+    s += back;
+    c = fmaf(w[k], be[k], c);
+  }
+  s = warp_sum(s);
+  c = warp_sum(c);
+  if (lane == 0) {
+    col_s[r] = s;
+    col_c[r] = c + b[r];
+  }
+}
+
+int launch_fold_ln_pack(const float* W, const float* b, const float* gamma, const float* beta, int L, int N, int K,
+                        uint32_t fmt, void* w16g, float* col_s, float* col_c, cudaStream_t st) {
+  const int64_t rows = (int64_t)L * N;
+  if (rows == 0) return BFB200_OK;
+  fold_ln_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(W, b, gamma, beta, rows, N, K, fmt, (uint16_t*)w16g, col_s,
+                                                                 col_c);
+  BFB_LAUNCH_CHECK("fold_ln_pack_kernel", st);
+  return BFB200_OK;
 }
 
 int launch_to16(const float* src, void* dst, int64_t n, uint32_t fmt, cudaStream_t st) {

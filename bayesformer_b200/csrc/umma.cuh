@@ -189,5 +189,25 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t packed) {
 __device__ __forceinline__ float bf16_lo(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
+// ------------------------------------------------------------------------------------------
+// Mixed-precision FMA, d = a * b + c with fp16 a, b taken straight from a half of a packed word and fp32 c, d
+// (PTX fma.rn.f32.f16, SASS FHFMA with .H0/.H1 operand selectors): fp16 tiles are multiplied (or, against a packed 1.0, added)
+// without unpacking them.  The product of two fp16 values is exact in fp32, so this is the arithmetic of
+// "unpack, then FFMA" at half the instructions.
+#define BFB_FH(NAME, ASEL, BSEL)                                                                              \
+  __device__ __forceinline__ float NAME(uint32_t a, uint32_t b, float c) {                                    \
+    float d;                                                                                                  \
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"                  \
+        "fma.rn.f32.f16 %0, " ASEL ", " BSEL ", %3;\n\t}"                                                     \
+        : "=f"(d)                                                                                             \
+        : "r"(a), "r"(b), "f"(c));                                                                            \
+    return d;                                                                                                 \
+  }
+BFB_FH(fh_ll, "al", "bl")
+BFB_FH(fh_hh, "ah", "bh")
+BFB_FH(fh_lh, "al", "bh")
+BFB_FH(fh_hl, "ah", "bl")
+#undef BFB_FH
+
 }  // namespace umma
 }  // namespace bfb
