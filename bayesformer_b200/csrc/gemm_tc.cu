@@ -651,7 +651,7 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
     const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
     cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     gemm2_tc_kernel<<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, map_r, g);
-    BFB_LAUNCH_CHECK("gemm_tc_kernel", st);
+    BFB_LAUNCH_CHECK(g.resid ? "gemm_tc_kernel[+residual,+row stats]" : g.stats_in != nullptr ? "gemm_tc_kernel[LayerNorm folded]" : "gemm_tc_kernel", st);
     return BFB200_OK;
   }
   const int64_t n_tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);

@@ -410,21 +410,41 @@ __global__ void __launch_bounds__(256, 4) resid_ln_kernel(const float* __restric
 // eight features) — the float4-per-thread kernels above evaluate every call twice.  Per thread and group: 2 x 128-bit
 // loads of the fp32 residual, one 128-bit load of the 16-bit branch, one 128-bit store of the 16-bit output.
 // ---------------------------------------------------------------------------
-// 8 keep bits (bit j = feature 8 g + j) for (local sequence s, position pos, site)
-__device__ __forceinline__ uint32_t keep8(const MaskSource& m, int64_t s, uint32_t pos, uint32_t site, uint32_t g) {
-  if (m.bits != nullptr) {
-    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + s)) * m.max_len + pos;
-    return (m.bits[row * m.words + (g >> 2)] >> ((g & 3u) * 8u)) & 0xFFu;
-  }
-  const uint64_t item = (uint64_t)(m.item_base + s / m.n_draws);
-  const uint32_t draw = m.draw_base + (uint32_t)(s % m.n_draws);
-  return keep8_of(philox4x32_10(make_uint4((uint32_t)item, draw, (m.step << 16) | pos, (site << 16) | g), m.key), m.threshold);
+// Mask addressing of one token row, computed once per row with 32-bit arithmetic (a chunk never holds 2^31 rows)
+struct RowKey {
+  uint32_t item, draw, seq, pos;
+};
+__device__ __forceinline__ RowKey make_row_key(const MaskSource& m, uint32_t row, uint32_t len) {
+  RowKey k;
+  k.seq = row / len;
+  k.pos = row - k.seq * len;
+  const uint32_t q = k.seq / m.n_draws;
+  k.item = (uint32_t)((uint64_t)m.item_base + q);
+  k.draw = m.draw_base + (k.seq - q * m.n_draws);
+  return k;
 }
 
-__device__ __forceinline__ void drop8(float (&v)[8], uint32_t keep, float scale) {
+// v[0..8) (features 8 g .. 8 g + 7 of the row) through the dropout site: kept values are scaled by 1 / (1 - p).
+// Philox mode decides straight on the 16-bit halves of the four output words (common.cuh: feature j <- half j & 1 of
+// word j >> 1, kept iff half >= threshold); mask-injection mode reads the packed bits.
+__device__ __forceinline__ void drop8_site(float (&v)[8], const MaskSource& m, const RowKey& k, uint32_t site, uint32_t g) {
+  if (m.bits != nullptr) {
+    const int64_t row = (((int64_t)m.step * m.n_sites + site) * m.n_seq + (m.seq_base + k.seq)) * m.max_len + k.pos;
+    const uint32_t keep = (m.bits[row * m.words + (g >> 2)] >> ((g & 3u) * 8u)) & 0xFFu;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * scale : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * m.scale : 0.f;
+    return;
+  }
+  const uint4 r = philox4x32_10(make_uint4(k.item, k.draw, (m.step << 16) | k.pos, (site << 16) | g), m.key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const uint32_t thr_hi = m.threshold << 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = (w[i] << 16) >= thr_hi ? v[2 * i] * m.scale : 0.f;          // low half  >= threshold
+    v[2 * i + 1] = w[i] >= thr_hi ? v[2 * i + 1] * m.scale : 0.f;          // high half >= threshold
+  }
 }
+
 __device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -466,15 +486,14 @@ __global__ void __launch_bounds__(256) embed16_kernel(const int32_t* __restrict_
   const int d8 = d >> 3;
   const int64_t total = n_seq * len * d8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / d8;
-    const int g = (int)(i - r * d8);
-    const int64_t s = r / len;
-    const int t = (int)(r - s * len);
-    const int tok = tokens[s * tok_stride + t];
+    const uint32_t r = (uint32_t)(i / d8);
+    const int g = (int)(i - (int64_t)r * d8);
+    const RowKey rk = make_row_key(ms, r, (uint32_t)len);
+    const int tok = tokens[(int64_t)rk.seq * tok_stride + rk.pos];
     float e[8], p[8];
     load8_f32(emb + (int64_t)tok * d + 8 * g, e);
-    load8_f32(pe + (int64_t)t * d + 8 * g, p);
-    if (site >= 0) drop8(e, keep8(ms, s, (uint32_t)t, (uint32_t)site, (uint32_t)g), ms.scale);
+    load8_f32(pe + (int64_t)rk.pos * d + 8 * g, p);
+    if (site >= 0) drop8_site(e, ms, rk, (uint32_t)site, (uint32_t)g);
 #pragma unroll
     for (int c = 0; c < 8; ++c) e[c] = e[c] * sqrt_d + p[c];
     if (x != nullptr) store8_f32(x + i * 8, e);
@@ -493,8 +512,7 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
   const int d8 = d >> 3;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
-    const int64_t s = r / len;
-    const uint32_t t = (uint32_t)(r - s * len);
+    const RowKey rk = make_row_key(ms, (uint32_t)r, (uint32_t)len);
     float v[NJ][8];
     float sum = 0.f;
 #pragma unroll
@@ -506,7 +524,7 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
         float b[8];
         load8_f32(x + r * d + 8 * g, v[j]);
         load8_16(y16 + r * d + 8 * g, fmt, b);
-        if (branch_site >= 0) drop8(b, keep8(ms, s, t, (uint32_t)branch_site, (uint32_t)g), ms.scale);
+        if (branch_site >= 0) drop8_site(b, ms, rk, (uint32_t)branch_site, (uint32_t)g);
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[j][c] += b[c];
         sum += ((v[j][0] + v[j][1]) + (v[j][2] + v[j][3])) + ((v[j][4] + v[j][5]) + (v[j][6] + v[j][7]));
@@ -534,7 +552,7 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
         load8_f32(beta + 8 * g, bt);
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] = (v[j][c] - mean) * rstd * gm[c] + bt[c];
-        if (out_site >= 0) drop8(o, keep8(ms, s, t, (uint32_t)out_site, (uint32_t)g), ms.scale);
+        if (out_site >= 0) drop8_site(o, ms, rk, (uint32_t)out_site, (uint32_t)g);
         if (out != nullptr) store8_f32(out + r * d + 8 * g, o);
         if (out16 != nullptr) store8_16(out16 + r * d + 8 * g, fmt, o);
       }
@@ -555,8 +573,7 @@ __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restr
   const float inv_d = 1.0f / (float)d;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
-    const int64_t s = r / len;
-    const uint32_t t = (uint32_t)(r - s * len);
+    const RowKey rk = make_row_key(ms, (uint32_t)r, (uint32_t)len);
     const float2 st = __ldg(stats + r);
     const float mean = st.x * inv_d;
     const float rstd = rsqrtf(fmaxf(st.y * inv_d - mean * mean, 0.f) + eps);
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restr
         load8_f32(beta + 8 * g, bt);
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = (v[c] - mean) * rstd * gm[c] + bt[c];
-        if (out_site >= 0) drop8(v, keep8(ms, s, t, (uint32_t)out_site, (uint32_t)g), ms.scale);
+        if (out_site >= 0) drop8_site(v, ms, rk, (uint32_t)out_site, (uint32_t)g);
         store8_16(out16 + r * d + 8 * g, fmt, v);
       }
     }
@@ -580,6 +597,7 @@ __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restr
 int launch_ln16_apply(const void* v16, const float2* stats, void* out16, int64_t n_rows, int len, int d, const float* gamma,
                       const float* beta, float eps, const MaskSource& ms, int out_site, uint32_t fmt, cudaStream_t st) {
   BFB_REQUIRE((d & 7) == 0 && d <= 2048, BFB200_ERR_UNSUPPORTED, "ln16_apply needs d_model %% 8 == 0 and <= 2048 (got %d)", d);
+  BFB_REQUIRE(n_rows < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");
   const int grid = stride_grid((n_rows + 7) / 8, 8);
 #define LAUNCH_LNA(NJ) ln16_apply_kernel<NJ><<<grid, 256, 0, st>>>((const uint16_t*)v16, stats, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, out_site, fmt)
   if (d <= 256) LAUNCH_LNA(1);
@@ -824,6 +842,7 @@ int launch_init_tokens(const int64_t* prompts, int64_t n_items_total, int64_t it
 int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const float* pe, int64_t n_seq,
                  int len, int d, const MaskSource& ms, int site, float* x, cudaStream_t st, void* x16, uint32_t fmt) {
   if (x16 != nullptr && (d & 7) == 0) {
+    BFB_REQUIRE(n_seq * len < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");
     const int64_t total8 = n_seq * len * (d >> 3);
     embed16_kernel<<<stride_grid((total8 + 255) / 256, 8), 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d,
                                                                         sqrtf((float)d), ms, site, x, (uint16_t*)x16, fmt);
@@ -886,6 +905,7 @@ int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, 
   BFB_REQUIRE(d <= 4096, BFB200_ERR_UNSUPPORTED, "d_model %d > 4096", d);
   const int grid = stride_grid((n_rows + 7) / 8, 8);
   if (y16 != nullptr && (d & 7) == 0 && d <= 2048) {   // tensor-core path: eight features per thread
+    BFB_REQUIRE(n_rows < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");
 #define LAUNCH_LN16(NJ) resid_ln16_kernel<NJ><<<grid, 256, 0, st>>>(x, (const uint16_t*)y16, out, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, branch_site, out_site, fmt)
     if (d <= 256) LAUNCH_LN16(1);
     else if (d <= 512) LAUNCH_LN16(2);
