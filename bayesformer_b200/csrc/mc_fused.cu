@@ -1,5 +1,5 @@
 // Fused MC-forward kernel for the notebook-default model class (d_model = 64, 8 heads of 8, F <= 64,
-// V <= 128, sequences of at most 16 tokens): ONE kernel runs the whole forward pass of a decode step —
+// V <= 128, sequences of at most 40 tokens): ONE kernel runs the whole forward pass of a decode step —
 // embedding + MC dropout + positional encoding, every TransformerBlock (QKV / W_out / FFN contractions on
 // tcgen05 tensor cores with fp16 operands and fp32 TMEM accumulators, causal attention, both
 // residual + LayerNorm pairs, the always-on dropout sites), the last-position vocabulary head, log-softmax,
@@ -11,7 +11,7 @@
 //   * row phases    — thread = token row: reads its fp32 accumulator row from TMEM (tcgen05.ld 32x32b), does
 //                     bias / ReLU / residual / LayerNorm / dropout in registers, writes the next operand row as
 //                     fp16 into the 128-byte-swizzled K-major tile the next tcgen05.mma consumes;
-//   * pair phase    — thread = (sequence, head): causal softmax(QK^T / sqrt(dh)) V over <= 16 keys from the
+//   * pair phase    — thread = (sequence, head) (or (query, sequence, head) beyond 16 tokens): causal softmax(QK^T / sqrt(dh)) V from the
 //                     fp16 Q/K/V tiles (a head's 8 values are exactly one 16-byte swizzle chunk);
 //   * score phase   — 4 or 8 threads per sequence: log-softmax over the vocabulary, probabilities, max /
 //                     margin / entropy, greedy arg-max or inverse-CDF sample.
@@ -35,7 +35,7 @@ constexpr int FROWS = 128;      // token rows per group tile (UMMA M)
 constexpr int FGROUPS = 2;      // independent groups per CTA, one tile of 128 token rows each
 constexpr int FGROUP_THREADS = 256;   // two threads per token row (32 features each)
 constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
-constexpr int FMAXLEN = 16;     // longest sequence the fused path takes
+constexpr int FMAXLEN = 40;     // longest sequence the fused path takes (rows of the positional table in the image)
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
 constexpr int PARAMS_PER_LAYER = 6 * 64;      // ln1_w, ln1_b, b1, b2, ln2_w, ln2_b (floats)
@@ -590,8 +590,53 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       umma::tc_fence_before_sync();
       umma::group_sync(bar_id, FGROUP_THREADS);
 
-      // ---- causal attention (transformer.py:58-65): work item = (sequence, head[, query parity]) ----
-      {
+      // ---- causal attention (transformer.py:58-65) ----
+      if constexpr (MAXLEN > 16) {
+        // Long sequences (the char-level configuration: 32..36 tokens): work item = (query position, sequence, head),
+        // query-major so that the lanes of a warp walk (nearly) the same number of keys.  K and V rows are streamed
+        // from the fp16 tiles, two passes over the keys (row maximum, then weights and the PV sum): no per-key state
+        // survives in registers, whatever the length.
+        const int npairs = nseq * FH;
+        const int nitems = prune ? npairs : npairs * len;
+        for (int it = gt; it < nitems; it += FGROUP_THREADS) {
+          const int t = prune ? len - 1 : it / npairs;
+          const int p = prune ? it : it - t * npairs;
+          const int sl = p >> 3, hd = p & 7;
+          const uint32_t row0 = (uint32_t)sl;
+          uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
+          const uint4 qw = *reinterpret_cast<const uint4*>(qptr);
+          float mx = -INFINITY;
+          for (int j = 0; j <= t; ++j)
+            mx = fmaxf(mx, dot8_f16(qw, *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd))));
+          const float nmx = -mx * qk_scale_log2e;
+          float z = 0.f;
+          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j <= t; ++j) {
+            const float sj = dot8_f16(qw, *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd)));
+            const float e = ex2_approx(fmaf(sj, qk_scale_log2e, nmx));
+            z += e;
+            const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
+            const uint32_t pl = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
+            const uint4 vw = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j * spt, hd));
+            axpy8_f16<false>(ph, vw, o);
+            axpy8_f16<false>(pl, vw, o);
+          }
+          const float inv_z = __fdividef(1.0f, z);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] *= inv_z;
+          if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
+            const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
+            const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
+          }
+          uint4 w;
+          w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
+          w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(qptr) = w;   // in place: other items read only K / V rows, never this Q chunk
+        }
+      } else {
+        // short sequences: work item = (sequence, head[, query parity]), K and V held in registers
         const int npairs = nseq * FH;
         // few pairs: two threads share one, by query parity; in the last layer only the last query is live
         const int nsplit = (!prune && npairs * 2 <= FGROUP_THREADS) ? 2 : 1;
@@ -834,9 +879,12 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   if (len <= 8) {
     cudaFuncSetAttribute(mc_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mc_forward_kernel<8><<<(int)grid, FTHREADS, smem, st>>>(a);
-  } else {
+  } else if (len <= 16) {
     cudaFuncSetAttribute(mc_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mc_forward_kernel<16><<<(int)grid, FTHREADS, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(mc_forward_kernel<FMAXLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mc_forward_kernel<FMAXLEN><<<(int)grid, FTHREADS, smem, st>>>(a);
   }
   BFB_LAUNCH_CHECK("mc_forward_kernel", st);
   return BFB200_OK;

@@ -53,7 +53,7 @@ enum {
                               class.  Operands are IEEE fp16 (saturating): bf16's 8-bit mantissa moves the
                               trained model's mid-range probabilities by up to 5 %, fp16 keeps them within
                               1 % (measured).  Served by the
-                              fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 16
+                              fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 40
                               (the reference notebooks' model).  Other models with heads of width 64 and
                               sequences of at most 256 tokens (the scaled configuration) run the layered
                               tensor-core path: TMA-fed tcgen05 GEMMs + tcgen05 attention, fp32 residual stream */,

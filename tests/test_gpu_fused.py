@@ -4,7 +4,7 @@
 (equivalently |dlogp| <= 1e-2), scores within 1e-2, integer outputs identical wherever the oracle's decision gap
 exceeds that tolerance.  Checked against (1) the golden vectors recorded from the unmodified reference with its own
 dropout masks injected, (2) the CPU oracle under the library's Philox counter scheme, (3) the exact fp32 CUDA path
-under the same seed (same masks), which also covers the latent dropout sites and the 16-token variant.
+under the same seed (same masks), which also covers the latent dropout sites and the 16- and 40-token variants.
 """
 
 import ctypes as C
@@ -166,9 +166,10 @@ def _fused_vs_exact(engine, dev, model, prompts, N, T, scheme, mode, seed, rtol=
 
 
 @pytest.mark.parametrize("P,N,B,T", [(4, 5, 257, 20), (1, 3, 33, 4), (2, 2, 1, 1), (3, 6, 70, 7), (7, 2, 19, 20),
-                                     (9, 4, 45, 5), (12, 5, 23, 3), (16, 1, 9, 2)])
+                                     (9, 4, 45, 5), (12, 5, 23, 3), (16, 1, 9, 2), (17, 3, 11, 3), (32, 5, 29, 4),
+                                     (40, 1, 7, 2), (25, 6, 10, 5)])
 def test_fused_matches_exact_path_all_shapes(engine, dev, c2, P, N, B, T):
-    """Tile tails, 1..16-token sequences (both kernel variants), every mode.  Uniformly random token prompts are
+    """Tile tails, 1..40-token sequences (all three kernel variants), every mode.  Uniformly random token prompts are
     far outside the trained model's input distribution (flatter, less stable logits); fp16 operand rounding then
     reaches 1-2 % on single probabilities and 2e-4 absolute on the smallest ones, so this structural test allows
     2e-2 relative + 5e-4 absolute — the reference-data tests above hold the stated 1e-2."""
@@ -178,6 +179,25 @@ def test_fused_matches_exact_path_all_shapes(engine, dev, c2, P, N, B, T):
     prompts = torch.randint(0, 114, (P, B), generator=g).to(dev)
     for mode in H.MODES:
         _fused_vs_exact(engine, dev, model, prompts, N, T, "dropout", mode, seed=1000 + P, rtol=2e-2, atol=5e-4)
+
+
+def test_fused_serves_the_char_level_configuration(engine, dev):
+    """SURVEY C1 shape: MyTransformer(67, 64, 8, 8, 2), 32-character prompts, 5 decode steps (sequences of 32..36
+    tokens) — the long-sequence variant of the fused kernel, against the exact fp32 path under the same seed, with the
+    latent dropout sites switched on as well."""
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(67)
+    model = MyTransformer(67, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval()
+    prompts = torch.randint(0, 65, (32, 50), generator=torch.Generator().manual_seed(5)).to(dev)
+    assert engine.scoring_pack(model.to(dev), dev, 32, 5, "auto").compute == "fp16"
+    for mode in H.MODES:
+        _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 6, "dropout", mode, seed=4242, rtol=2e-2, atol=5e-4)
+    for layer in model.layers:
+        layer.bayes, layer.bayes_dropout = True, 0.3
+        layer.ff.bayes_dropout = 0.3
+        layer.self_attn.bayes, layer.self_attn.bayes_dropout = True, 0.3
+    _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 4, "sampling", "entropy", seed=77, rtol=2e-2, atol=5e-4)
 
 
 def test_fused_latent_sites_match_exact_path(engine, dev, c2):
@@ -235,9 +255,10 @@ def test_fp16_outside_the_fused_class_is_an_error(engine, dev):
     assert pack.compute == "fp32"
     small = MyTransformer(114, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval().to(dev)
     assert engine.scoring_pack(small, dev, 4, 5, "auto").compute == "fp16"
-    assert engine.scoring_pack(small, dev, 32, 5, "auto").compute == "fp32"   # 36-token sequences
+    assert engine.scoring_pack(small, dev, 32, 5, "auto").compute == "fp16"   # 36-token sequences: long variant
+    assert engine.scoring_pack(small, dev, 40, 5, "auto").compute == "fp32"   # 44-token sequences: outside the class
     with pytest.raises(NotImplementedError):
-        engine.mc_score_transformer(small.native_pack(dev, "fp16"), torch.zeros(32, 4, dtype=torch.int64, device=dev),
+        engine.mc_score_transformer(small.native_pack(dev, "fp16"), torch.zeros(40, 4, dtype=torch.int64, device=dev),
                                     5, 2, "dropout", "max")
 
 

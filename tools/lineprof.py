@@ -45,5 +45,5 @@ def getsrc(f, ln):
             return src[p][ln - 1].strip()[:90] if ln - 1 < len(src[p]) else ""
     return ""
 print(f"total inst {tot[0]:,} samples {tot[1]:,}")
-for (f, ln), (ie, sm, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+for (f, ln), (ie, sm, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("SORTCOL","1"))])[:int(__import__("os").environ.get("TOPN","45"))]:
     print(f"{100*ie/tot[0]:5.1f}% inst {100*sm/max(1,tot[1]):5.1f}% stall  n={cnt:4d}  {f}:{ln}  {getsrc(f, ln)}")
