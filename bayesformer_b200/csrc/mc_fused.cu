@@ -143,6 +143,7 @@ struct FusedArgs {
   int len;                     // tokens per sequence in this step
   int spt;                     // sequences per tile = 128 / len
   int tps;                     // score-phase threads per sequence (4 or 8)
+  uint32_t qsplit;             // pair phase with two threads per (sequence, head): bit t = which of them takes query t
   int64_t n_seq;               // sequences in the chunk
   int64_t n_tiles;
   const int32_t* tokens;       // (n_seq, tok_stride)
@@ -638,7 +639,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       } else {
         // short sequences: work item = (sequence, head[, query parity]), K and V held in registers
         const int npairs = nseq * FH;
-        // few pairs: two threads share one, by query parity; in the last layer only the last query is live
+        // few pairs: two threads share one, queries split so that both walk about the same number of keys (query t
+        // costs t + 1 key visits; a.qsplit is the balanced assignment); in the last layer only the last query is live
         const int nsplit = (!prune && npairs * 2 <= FGROUP_THREADS) ? 2 : 1;
         for (int it = gt; it < npairs * nsplit; it += FGROUP_THREADS) {
           const int p = nsplit == 2 ? it >> 1 : it;
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
           for (int t = 0; t < MAXLEN; ++t) {
-            if (t < len && (qpar < 0 || (t & 1) == qpar) && (!prune || t == len - 1)) {
+            if (t < len && (qpar < 0 || (int)((a.qsplit >> t) & 1u) == qpar) && (!prune || t == len - 1)) {
               uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
               const uint4 qw = *reinterpret_cast<const uint4*>(qptr);
               float sc[MAXLEN];
@@ -859,6 +861,24 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   a.len = len;
   a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 8 threads
   a.tps = (FGROUP_THREADS / a.spt) >= 16 ? 16 : 8;
+  {   // balanced two-way split of the queries 0..len-1 with weights t + 1 (exhaustive, cached per length)
+    static uint32_t cache[17] = {0};
+    static bool have[17] = {false};
+    const int n = len < 16 ? len : 16;
+    if (!have[n]) {
+      uint32_t best = 0xAAAAAAAAu;
+      int best_max = 1 << 30;
+      for (uint32_t m = 0; m < (1u << n); ++m) {
+        int s1 = 0, s0 = 0;
+        for (int t = 0; t < n; ++t) ((m >> t) & 1u ? s1 : s0) += t + 1;
+        const int mx = s1 > s0 ? s1 : s0;
+        if (mx < best_max) { best_max = mx; best = m; }
+      }
+      cache[n] = best;
+      have[n] = true;
+    }
+    a.qsplit = cache[n];
+  }
   a.n_seq = n_seq;
   a.n_tiles = (n_seq + a.spt - 1) / a.spt;
   a.tokens = tokens; a.tokens_out = tokens_out; a.tok_stride = tok_stride;

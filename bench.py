@@ -450,6 +450,27 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
         del big, pk, pr
     except Exception as exc:
         out["scaled_c4_mc_score"] = {"error": repr(exc)}
+    # char-level configuration (SURVEY C1 / BASELINE configs[0]): MyTransformer(67, 64, 8, 8, 2), 32-token prompts, 5 decode
+    # steps (sequences of 32..36 tokens), T = 20, entropy, 10,000 synthetic windows: the fused kernel's long-sequence variant
+    try:
+        from bayesformer_b200.model.transformer import MyTransformer
+        torch.manual_seed(SEED)
+        small = MyTransformer(67, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval().to(dev)
+        n_items = 10_000
+        pr = torch.randint(0, 65, (32, n_items), device=dev)
+        pk = engine.scoring_pack(small, dev, 32, 5, "auto")
+        ms = timed(lambda: engine.mc_score_transformer(pk, pr, 5, T_MC, "dropout", "entropy", seed=SEED), reps=3)
+        flops = T_MC * sum(2 * (8 * ln * 64 * 64 + 4 * ln * 64 * 8 + 2 * ln * (ln + 1) * 64) + 2 * 64 * 67 for ln in range(32, 37))
+        sps = n_items / (ms * 1e-3)
+        out["char_level_c1_mc_score"] = {"pool_items": n_items, "T_mc": T_MC, "prompt_len": 32, "new_tokens": 5, "compute": pk.compute,
+                                         "ms": ms, "pool_samples_per_s": sps, "flops_per_pool_sample": flops, "bound": "tensor",
+                                         "achieved": sps * flops / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                         "frac": sps * flops / 1e12 / peaks["bf16_tflops_sustained"],
+                                         "peak_source": peak_src + " (sustained)",
+                                         "note": "issue-bound like the headline kernel (dh = 8, F = 8)"}
+        del small, pk, pr
+    except Exception as exc:
+        out["char_level_c1_mc_score"] = {"error": repr(exc)}
     # toy classifier, SURVEY C2i
     from bayesformer_b200.model.bayesian_classification import MLP
     torch.manual_seed(SEED)
