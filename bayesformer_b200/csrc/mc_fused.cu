@@ -438,6 +438,17 @@ __device__ __forceinline__ void ln_finish(float (&v)[HW], float2 own, float2 oth
   for (int i = 0; i < HW; ++i) v[i] = fmaf(fmaf(v[i], rstd, shift), gamma[i], beta[i]);
 }
 
+#ifdef BFB_FUSED_TIMING
+// debug build only (make EXTRA=-DBFB_FUSED_TIMING): cycles one observer thread per group spends in the product
+// round trips (barrier -> MMA issue -> completion wait), in the other group barriers, and in total
+__device__ unsigned long long bfb_fused_dbg[8];
+#define BFB_T0() const long long _t0 = clock64()
+#define BFB_T1(slot) do { if ((gt & 31) == 5) dbg[slot] += clock64() - _t0; } while (0)
+#else
+#define BFB_T0() do { } while (0)
+#define BFB_T1(slot) do { } while (0)
+#endif
+
 template <int MAXLEN>
 __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -508,20 +519,50 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const uint32_t img_u32 = umma::smem_u32(img);
 
   // one GEMM phase: operand rows are in shared memory -> accumulators in TMEM columns [tW, tW + N)
+#ifdef BFB_FUSED_TIMING
+  long long dbg[4] = {0, 0, 0, 0};   // observer lanes: round-trip cycles, round trips, cycles after the barrier
+  long long dbi[3] = {0, 0, 0};      // issuing thread: barrier exit -> commit issued, -> completion seen, fence
+  const long long t_begin = clock64();
+#endif
   auto gemm = [&](uint32_t a_addr, uint32_t b_addr, int N, int k_steps) {
+    BFB_T0();
+    // descriptors are built before the barrier: after it, the issuing thread's path to the tensor core is the
+    // critical path of the whole group (measured: ~600 cycles from barrier exit to the commit)
+    const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
+    const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
     umma::fence_async_smem();
     umma::tc_fence_before_sync();
     umma::group_sync(bar_id, FGROUP_THREADS);
+#ifdef BFB_FUSED_TIMING
+    const long long _t_issue = clock64();
+#endif
     if (gt == 0) {
       umma::tc_fence_after_sync();
-      const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
-      const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
+#ifdef BFB_FUSED_TIMING
+      const long long _t1 = clock64();
+#endif
       for (int k = 0; k < k_steps; ++k) umma::mma_bf16_ss(tW_mma, da + 2 * k, db + 2 * k, idesc, k > 0);
+#ifdef BFB_FUSED_TIMING
+      const long long _t2 = clock64();
+#endif
       umma::mma_commit(bar);
+#ifdef BFB_FUSED_TIMING
+      const long long _t3 = clock64();
+      dbi[0] += _t3 - _t_issue;
+      dbi[2] += _t1 - _t_issue;
+      (void)_t2;
+#endif
     }
     umma::mbar_wait(bar, phase);
+#ifdef BFB_FUSED_TIMING
+    if (gt == 0) dbi[1] += clock64() - _t_issue;
+#endif
     phase ^= 1u;
     umma::tc_fence_after_sync();
+    BFB_T1(0);
+#ifdef BFB_FUSED_TIMING
+    if ((gt & 31) == 5) { dbg[1] += 1; dbg[2] += clock64() - _t_issue; }
+#endif
   };
 
   for (int64_t tile = (int64_t)blockIdx.x * FGROUPS + g; tile < a.n_tiles; tile += (int64_t)gridDim.x * FGROUPS) {
@@ -811,12 +852,38 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
+#ifdef BFB_FUSED_TIMING
+  if ((gt & 31) == 5) {
+    atomicAdd(&bfb_fused_dbg[0], (unsigned long long)dbg[0]);
+    atomicAdd(&bfb_fused_dbg[1], (unsigned long long)dbg[1]);
+    atomicAdd(&bfb_fused_dbg[2], (unsigned long long)dbg[2]);
+    atomicAdd(&bfb_fused_dbg[3], (unsigned long long)(clock64() - t_begin));
+    atomicAdd(&bfb_fused_dbg[4], 1ull);
+  }
+  if (gt == 0) {
+    atomicAdd(&bfb_fused_dbg[5], (unsigned long long)dbi[0]);
+    atomicAdd(&bfb_fused_dbg[6], (unsigned long long)dbi[1]);
+    atomicAdd(&bfb_fused_dbg[7], (unsigned long long)dbi[2]);
+  }
+#endif
   umma::tc_fence_before_sync();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
+
+#ifdef BFB_FUSED_TIMING
+extern "C" int bfb200_debug_fused_timing(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, bfb_fused_dbg, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(bfb_fused_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // host side

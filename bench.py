@@ -241,6 +241,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     W, K = max(3, args.warmup), max(1, args.steps)
