@@ -115,16 +115,68 @@ def _encode_addition_pool(prompts: list[str], answers: list[str], tokenizer) -> 
     return (torch.from_numpy(np.ascontiguousarray(X.T)), torch.from_numpy(np.ascontiguousarray(Y.T)), P - 0, A)
 
 
+def _encode_char_pool(prompts: list[str], answers: list[str], tokenizer) -> tuple | None:
+    """Vectorised encoding of a whole pool under a character-level tokenizer (`CharacterLevelTokenizer`, reference
+    `src/libs/tokenizer.py:28-62`, or the char-vocabulary tokenizer of the Shakespeare-window pool): one id per
+    character, characters outside the vocabulary dropped (the reference's `clean`), prompts LEFT padded with PAD,
+    answers + EOS RIGHT padded (`src/libs/preprocessing.py:59-72`).  Ragged and empty strings are fine.  Returns
+    `(X (P,B), Y (A+1,B), P, A)` bit-identical to the per-item path, or None when the vocabulary is not one character
+    per token."""
+    import numpy as np
+
+    t2i = tokenizer.token_to_id
+    single = {ord(k): v for k, v in t2i.items() if len(k) == 1}
+    if not prompts or len(single) != len(t2i) - 2 or max(single) > 0xFFFF:
+        return None
+    pad_id, eos_id = t2i[constants.PAD_TOKEN], t2i[constants.EOS_TOKEN]
+    table = np.full(0x10000, -1, dtype=np.int64)
+    table[np.fromiter(single.keys(), dtype=np.int64)] = np.fromiter(single.values(), dtype=np.int64)
+    B = len(prompts)
+
+    def encode(strings):
+        lens = np.fromiter(map(len, strings), dtype=np.int64, count=B)
+        flat = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
+        if flat.size != int(lens.sum()):
+            return None
+        ids = np.where(flat < 0x10000, table[np.minimum(flat, 0xFFFF)], -1)
+        keep = ids >= 0
+        rows = np.repeat(np.arange(B), lens)[keep]
+        ids = ids[keep]
+        counts = np.bincount(rows, minlength=B)
+        pos = np.arange(ids.size) - (np.cumsum(counts) - counts)[rows]
+        return rows, ids, counts, pos
+
+    ep, ea = encode(prompts), encode(answers)
+    if ep is None or ea is None:
+        return None
+    rows, ids, counts, pos = ep
+    P = int(counts.max())
+    X = np.full((B, P), pad_id, dtype=np.int64)
+    X[rows, P - counts[rows] + pos] = ids
+    rows, ids, counts, pos = ea
+    A = int(counts.max())
+    Y = np.full((B, A + 1), pad_id, dtype=np.int64)
+    Y[rows, pos] = ids
+    Y[np.arange(B), counts] = eos_id
+    return (torch.from_numpy(np.ascontiguousarray(X.T)), torch.from_numpy(np.ascontiguousarray(Y.T)), P, A)
+
+
 def get_batch(dataset: list[tuple[str, str]], tokenizer: Tokenizer, i: int, batch_size: int):
     """Encode `dataset[i : i + batch_size]` → `(X (P,B), Y (A+1,B), P, A, prompts, answers)`.
 
     Pools of canonical addition strings under the `ReversedPairingTokenizer` are encoded by the vectorised
-    `_encode_addition_pool` (identical output, ~100x faster); anything else takes the reference's per-item route."""
+    `_encode_addition_pool`, pools under a character-level tokenizer by `_encode_char_pool` (identical output,
+    ~25-100x faster); anything else takes the reference's per-item route."""
     rows = [dataset[j] for j in range(i, i + batch_size)]
     prompts = [row[0] for row in rows]
     answers = [row[1] for row in rows]
     if batch_size >= 64 and type(tokenizer).__name__ == "ReversedPairingTokenizer":
         fast = _encode_addition_pool(prompts, answers, tokenizer)
+        if fast is not None:
+            X, Y, prompt_length, answers_length = fast
+            return X, Y, prompt_length, answers_length, prompts, answers
+    if batch_size >= 64 and type(tokenizer).__name__ in ("CharacterLevelTokenizer", "CharVocabTokenizer"):
+        fast = _encode_char_pool(prompts, answers, tokenizer)
         if fast is not None:
             X, Y, prompt_length, answers_length = fast
             return X, Y, prompt_length, answers_length, prompts, answers

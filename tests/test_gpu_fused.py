@@ -351,3 +351,28 @@ def test_sharded_selection_equals_single_device_selection(engine, dev, c2):
         keys.append(engine.topk_keys(part.pool_scores, k, index_base=lo))
     _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
     assert torch.equal(got, want)
+
+
+def test_select_samples_on_a_char_level_pool_runs_the_fused_kernel(engine, dev):
+    """SURVEY C1 through the unchanged list-of-pairs API: 32-character windows + 4-character continuations under a
+    character tokenizer (V = 67), MC-dropout entropy acquisition — tokenised by the vectorised char encoder, scored by
+    the long-sequence variant of the fused kernel; the exact fp32 path ranks the same pool consistently."""
+    import random
+    import string
+
+    from bayesformer_b200.libs import active_learning as al
+    from bayesformer_b200.libs.tokenizer import CharVocabTokenizer
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    rnd = random.Random(3)
+    alphabet = (string.ascii_letters + " ,.;:!?'\n-&3$")[:65]
+    tok = CharVocabTokenizer(alphabet)
+    assert tok.ntokens == 67
+    text = "".join(rnd.choice(alphabet) for _ in range(36 * 600))
+    pool = [(text[36 * i:36 * i + 32], text[36 * i + 32:36 * i + 36]) for i in range(600)]
+    torch.manual_seed(1)
+    model = MyTransformer(67, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).to(dev)
+    with engine.profile(dev) as prof:
+        picked = al.select_samples(model, tok, pool, dev, nb_samples=50, compute="dropout", mode="entropy")
+    assert "mc_forward_kernel" in prof.kernels and "sgemm_tn_kernel" not in prof.kernels
+    assert len(set(picked)) == 50 and all(0 <= i < 600 for i in picked)

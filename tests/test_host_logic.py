@@ -208,3 +208,29 @@ def test_repad_prompts_matches_whole_pool_padding():
     assert torch.equal(sharding.repad_prompts(Xa, P, tok.token_to_id["<PAD>"] if "<PAD>" in tok.token_to_id else 112), X[:, :80])
     with pytest.raises(ValueError):
         sharding.repad_prompts(X, Pa, 112)
+
+
+def test_vectorised_char_pool_tokenisation_is_bit_identical():
+    """Character-level tokenizers (the reference's CharacterLevelTokenizer and the 67-symbol tokenizer of the
+    Shakespeare-window pool): ragged and empty strings, characters outside the vocabulary (dropped, as `clean` does)."""
+    import random
+    import string
+
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import CharacterLevelTokenizer, CharVocabTokenizer
+
+    rnd = random.Random(7)
+    alphabet = string.ascii_letters + " ,.;:!?'\n-&3$"
+    for tok, chars in ((CharVocabTokenizer(alphabet), alphabet + "#@é"), (CharacterLevelTokenizer(), "0123456789+= x")):
+        pool = [("".join(rnd.choice(chars) for _ in range(rnd.choice((0, 1, 5, 32, 33)))),
+                 "".join(rnd.choice(chars) for _ in range(rnd.choice((0, 2, 4))))) for _ in range(300)]
+        fast = preprocessing.get_batch(pool, tok, 0, len(pool))
+        slow_p, p_len = preprocessing.pad(tok, [tok.encode(p) for p, _ in pool], "prompts")
+        slow_a, a_len = preprocessing.pad(tok, [tok.encode(a) for _, a in pool], "answers")
+        assert (fast[2], fast[3]) == (p_len, a_len)
+        assert torch.equal(fast[0], torch.tensor(slow_p, dtype=torch.int64).t())
+        assert torch.equal(fast[1], torch.tensor(slow_a, dtype=torch.int64).t())
+        # small batches keep the per-item route and agree as well
+        few = preprocessing.get_batch(pool, tok, 10, 20)
+        sp, _ = preprocessing.pad(tok, [tok.encode(p) for p, _ in pool[10:30]], "prompts")
+        assert torch.equal(few[0], torch.tensor(sp, dtype=torch.int64).t())
