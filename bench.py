@@ -241,8 +241,6 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     W, K = max(3, args.warmup), max(1, args.steps)
@@ -531,4 +529,11 @@ def kernel_roofline(name: str, stat: dict, passes: int, pool: int, P: int, N: in
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (the NCCL banner) are sent to
+    # stderr, and the line itself goes to the original stdout
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w")
     main()
+    sys.stdout.flush()
