@@ -449,6 +449,22 @@ __device__ unsigned long long bfb_fused_dbg[8];
 #define BFB_T1(slot) do { } while (0)
 #endif
 
+// The MMAs of one product, issued by ONE thread of group G.  Every operand is built from kernel-uniform values (the
+// shared-memory window base, kernel parameters, the compile-time group index; the TMEM allocation is the whole
+// 512 columns, so its base is column 0) and therefore lives in uniform registers: with per-thread operands the
+// compiler wraps each UTCHMMA in an ELECT / R2UR.BROADCAST / branch "waterfall" loop, ~140 cycles per instruction
+// on the critical path of the whole group.
+template <int G>
+__device__ __forceinline__ void fused_issue_product(uint32_t tiles_u32, int a_sel, uint32_t b_addr, int N, int k_steps,
+                                                    uint64_t* group_bars) {
+  const uint32_t a_addr = tiles_u32 + (uint32_t)(G * 3 + a_sel) * TILE_BYTES;
+  const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
+  const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
+  const uint32_t d_tmem = (uint32_t)G * 256u + 64u;
+  for (int k = 0; k < k_steps; ++k) umma::mma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0);
+  umma::mma_commit(&group_bars[G]);
+}
+
 template <int MAXLEN>
 __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -498,7 +514,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const uint32_t lane_base = (uint32_t)(gw * 32) << 16;
   const uint32_t tX = tmem_base + (uint32_t)g * 256u + lane_base + (uint32_t)h * HW;  // residual stream (this half)
   const uint32_t tW = tmem_base + (uint32_t)g * 256u + lane_base + 64u;               // accumulators, 192 columns
-  const uint32_t tW_mma = tmem_base + (uint32_t)g * 256u + 64u;                       // same, lane field 0
+  if (tmem_base != 0u) __trap();   // all 512 columns are ours: the MMA issue path relies on base column 0
   uint64_t* bar = &bar_group[g];
   uint32_t phase = 0;
   const int bar_id = 1 + g;
@@ -515,7 +531,6 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const uint32_t fl = a.site_flags;
   const MaskSource& ms = a.ms;
 
-  const uint32_t descA0 = umma::smem_u32(B0), descA1 = umma::smem_u32(B1);
   const uint32_t img_u32 = umma::smem_u32(img);
 
   // one GEMM phase: operand rows are in shared memory -> accumulators in TMEM columns [tW, tW + N)
@@ -524,12 +539,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   long long dbi[3] = {0, 0, 0};      // issuing thread: barrier exit -> commit issued, -> completion seen, fence
   const long long t_begin = clock64();
 #endif
-  auto gemm = [&](uint32_t a_addr, uint32_t b_addr, int N, int k_steps) {
+  const uint32_t tiles_u32 = umma::smem_u32(smem) + lay.image_bytes;   // kernel-uniform
+  auto gemm = [&](int a_sel, uint32_t b_addr, int N, int k_steps) {
     BFB_T0();
-    // descriptors are built before the barrier: after it, the issuing thread's path to the tensor core is the
-    // critical path of the whole group (measured: ~600 cycles from barrier exit to the commit)
-    const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
-    const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
     umma::fence_async_smem();
     umma::tc_fence_before_sync();
     umma::group_sync(bar_id, FGROUP_THREADS);
@@ -541,16 +553,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 #ifdef BFB_FUSED_TIMING
       const long long _t1 = clock64();
 #endif
-      for (int k = 0; k < k_steps; ++k) umma::mma_bf16_ss(tW_mma, da + 2 * k, db + 2 * k, idesc, k > 0);
-#ifdef BFB_FUSED_TIMING
-      const long long _t2 = clock64();
-#endif
-      umma::mma_commit(bar);
+      if (g == 0) fused_issue_product<0>(tiles_u32, a_sel, b_addr, N, k_steps, bar_group);
+      else        fused_issue_product<1>(tiles_u32, a_sel, b_addr, N, k_steps, bar_group);
 #ifdef BFB_FUSED_TIMING
       const long long _t3 = clock64();
       dbi[0] += _t3 - _t_issue;
       dbi[2] += _t1 - _t_issue;
-      (void)_t2;
 #endif
     }
     umma::mbar_wait(bar, phase);
@@ -607,7 +615,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       const bool live = !prune || warp_has_last;
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
-      gemm(descA0, wl, 3 * FD, 4);
+      gemm(0, wl, 3 * FD, 4);
       // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 operand tiles B0, B1, B2
       // (x in B0 is dead once the product has completed); each half copies 96 columns, 16 per trip
 #pragma unroll 1
@@ -750,16 +758,16 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       if (!live) {
         // dead rows of the last layer: take part in the barriers of the three products and the two LayerNorm
         // exchanges (thread 0 of the group still issues the MMAs inside gemm()), compute nothing
-        gemm(descA0, wl + lay.off_out, FD, 4);
+        gemm(0, wl + lay.off_out, FD, 4);
         umma::group_sync(bar_id, FGROUP_THREADS);
-        gemm(descA0, wl + lay.off_w1, (int)lay.fp, 4);
-        gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+        gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
+        gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
         umma::group_sync(bar_id, FGROUP_THREADS);
         continue;
       }
 
       // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
-      gemm(descA0, wl + lay.off_out, FD, 4);
+      gemm(0, wl + lay.off_out, FD, 4);
       {
         const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
         const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
@@ -781,7 +789,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
 
       // ---- FFN: Linear(d -> F) + bias + ReLU (transformer.py:151-155); each half takes fp / 2 columns ----
-      gemm(descA0, wl + lay.off_w1, (int)lay.fp, 4);
+      gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
       {
         const float* b1 = pl + 128;
         const uint32_t half_cols = lay.fp >> 1;   // multiple of 8
@@ -800,7 +808,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
-      gemm(descA1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+      gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (fl & BFB200_SITE_LAYER_OUT) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
@@ -827,7 +835,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     }
 
     // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
-    gemm(descA0, img_u32 + lay.off_head, FMAXV, 4);
+    gemm(0, img_u32 + lay.off_head, FMAXV, 4);
     const int stage_stride = FMAXV + a.tps;
     float* stage = reinterpret_cast<float*>(B1);  // B1 + B2: 32 KB (K / V / FFN hidden are dead)
     {
