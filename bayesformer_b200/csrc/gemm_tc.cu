@@ -73,12 +73,29 @@ struct GemmArgs {
   int vec_ok;              // bias / col_s / col_c are 16-byte aligned: full chunks read them with 128-bit loads
 };
 
+// Compile-time epilogue specialisations of the two-SM kernel: the launcher instantiates the combinations the
+// transformer path uses (so their epilogues carry no dead branches: the K = 512 products are epilogue-paced) and
+// falls back to EPI_DYNAMIC, which consults the runtime fields of GemmArgs for everything.
+constexpr uint32_t EPI_BIAS = 1u, EPI_RELU = 2u, EPI_AFFINE = 4u, EPI_RESID = 8u, EPI_STATS = 16u, EPI_F16 = 32u,
+                   EPI_OUT16_ONLY = 64u, EPI_DYNAMIC = 0x80000000u;
+template <uint32_t F> struct Epi {
+  static constexpr bool dyn = (F & EPI_DYNAMIC) != 0;
+  __device__ static __forceinline__ bool bias(const GemmArgs& g) { return dyn ? g.bias != nullptr : (F & EPI_BIAS) != 0; }
+  __device__ static __forceinline__ bool relu(const GemmArgs& g) { return dyn ? g.relu != 0 : (F & EPI_RELU) != 0; }
+  __device__ static __forceinline__ bool affine(const GemmArgs& g) { return dyn ? g.stats_in != nullptr : (F & EPI_AFFINE) != 0; }
+  __device__ static __forceinline__ bool resid(const GemmArgs& g) { return dyn ? g.resid != 0 : (F & EPI_RESID) != 0; }
+  __device__ static __forceinline__ bool stats(const GemmArgs& g) { return dyn ? g.stats_out != nullptr : (F & EPI_STATS) != 0; }
+  __device__ static __forceinline__ bool f16(const GemmArgs& g) { return dyn ? g.fmt == umma::kFmtF16 : (F & EPI_F16) != 0; }
+  __device__ static __forceinline__ bool out32(const GemmArgs& g) { return (dyn || !(F & EPI_OUT16_ONLY)) ? g.out32 != nullptr : false; }
+  __device__ static __forceinline__ bool out16(const GemmArgs& g) { return (dyn || !(F & EPI_OUT16_ONLY)) ? g.out16 != nullptr : true; }
+};
+
 // The arithmetic of one 32-column chunk of one accumulator row.  FULL: all 32 columns are inside the matrix and the
 // per-column vectors are 16-byte aligned (128-bit broadcast loads, no guards).
 //   plain     : v = acc (+ bias) (ReLU)
 //   affine    : v = rstd (acc - mean col_s) + col_c (ReLU)            LayerNorm folded into this product
 //   residual  : v += R16 row (read from the ring slot TMA filled), and the row's running sum / sum of squares
-template <bool FULL>
+template <bool FULL, uint32_t F>
 __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&acc)[32], float (&v)[32], int n0, float r_mean,
                                            float r_rstd, const uint8_t* box, int resid_row, int half, float& st_sum,
                                            float& st_sq) {
@@ -94,13 +111,13 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
       for (int i = 0; i < 32; ++i) dst[i] = n0 + i < g.N ? __ldg(src + n0 + i) : 0.f;
     }
   };
-  if (g.stats_in != nullptr) {
+  if (Epi<F>::affine(g)) {
     float cs_[32];
     load32(g.col_s, cs_);
     load32(g.col_c, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(r_rstd, fmaf(-r_mean, cs_[i], __uint_as_float(acc[i])), v[i]);
-  } else if (g.bias != nullptr) {
+  } else if (Epi<F>::bias(g)) {
     load32(g.bias, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(acc[i]);
@@ -108,11 +125,11 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   }
-  if (g.relu) {
+  if (Epi<F>::relu(g)) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  if (g.resid) {
+  if (Epi<F>::resid(g)) {
     // chunk = bytes [64 half, +64) of row `resid_row` of a swizzled box of 128 rows x 64 columns
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -120,7 +137,7 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
       const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (g.fmt == umma::kFmtF16) {   // v += x: one mixed-precision FMA against a packed 1.0 per value
+        if (Epi<F>::f16(g)) {   // v += x: one mixed-precision FMA against a packed 1.0 per value
           v[8 * c + 2 * k] = umma::fh_ll(ww[k], 0x3C003C00u, v[8 * c + 2 * k]);
           v[8 * c + 2 * k + 1] = umma::fh_hl(ww[k], 0x3C003C00u, v[8 * c + 2 * k + 1]);
         } else {
@@ -129,7 +146,7 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
         }
       }
     }
-    if (g.stats_out != nullptr) {
+    if (Epi<F>::stats(g)) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float x = (FULL || n0 + i < g.N) ? v[i] : 0.f;
@@ -143,13 +160,13 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
 // Epilogue of one accumulator stage for one warp: columns [c_begin, c_begin + 32 * NCH) of its 32 TMEM lanes ->
 // (+ bias)(ReLU) -> swizzled 32-row slabs -> 2-D TMA stores.  The tcgen05.ld of chunk i + 1 is in flight while chunk
 // i is converted and staged.
-template <int NCH>
+template <int NCH, uint32_t F = EPI_DYNAMIC>
 __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtensorMap* map_c16, const CUtensorMap* map_c32,
                                                  uint32_t tacc, int n_base, int row0,
                                                  int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane,
                                                  const uint8_t* resid_rows, int resid_row) {
   constexpr uint32_t SLAB_BYTES = 32 * 128;
-  const bool affine = g.stats_in != nullptr;
+  const bool affine = Epi<F>::affine(g);
   float r_mean = 0.f, r_rstd = 1.f, st_sum = 0.f, st_sq = 0.f;
   if (affine && row0 + lane < g.M) {   // thread = output row: its LayerNorm statistics
     const float2 st = __ldg(g.stats_in + row0 + lane);
@@ -168,10 +185,10 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
       float v[32];
       const uint8_t* box = resid_rows + (uint32_t)(ch >> 1) * (GM * 128u);
       if (n0 + 32 <= g.N && g.vec_ok)   // warp-uniform: the whole chunk is inside the matrix -> no per-column guards
-        chunk_math<true>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
+        chunk_math<true, F>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
       else
-        chunk_math<false>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
-      if (g.out32 != nullptr) {
+        chunk_math<false, F>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
+      if (Epi<F>::out32(g)) {
         uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
         tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
         __syncwarp();
@@ -187,7 +204,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
         }
         ++slab_i;
       }
-      if (g.out16 != nullptr) {
+      if (Epi<F>::out16(g)) {
         // two 32-column chunks share one 128-byte slab row: even chunk -> bytes [0, 64), odd chunk -> [64, 128)
         uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
         const int half = ch & 1;   // c_begin is a multiple of 64
@@ -221,7 +238,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
       }
     }
   }
-  if (g.resid && g.stats_out != nullptr && row0 + lane < g.M) {
+  if (Epi<F>::resid(g) && Epi<F>::stats(g) && row0 + lane < g.M) {
     atomicAdd(&g.stats_out[row0 + lane].x, st_sum);
     atomicAdd(&g.stats_out[row0 + lane].y, st_sq);
   }
@@ -390,6 +407,7 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
+template <uint32_t F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c16, const __grid_constant__ CUtensorMap map_c32,
@@ -451,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           tma_load_2d_2sm(sa, &map_a, kb * GK, (int)(mb * 2 * GM + rank * GM), bar);
           tma_load_2d_2sm(sa + A_BYTES, &map_w, kb * GK, nb * BN + (int)rank * WROWS, bar);
         }
-        if (g.resid) {
+        if (Epi<F>::resid(g)) {
           // the tile's residual rows of this CTA ride the same ring: one slot per 128 output columns (two swizzled boxes of
           // 128 rows x 64 columns), completion on this CTA's own rfull barrier; the epilogue warps hand the slot back
           const int n_rs = nb * BN + 128 < g.N ? 2 : 1;
@@ -490,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           mma_commit_2sm(&empty_bar[s]);
         }
         mma_commit_2sm(&acc_full[as]);
-        if (g.resid) {   // the residual slots of this tile are not MMA operands
+        if (Epi<F>::resid(g)) {   // the residual slots of this tile are not MMA operands
           const int64_t mb_ = tile / tiles_n;
           const int nb_ = (int)(tile - mb_ * tiles_n);
           it += nb_ * BN + 128 < g.N ? 2u : 1u;
@@ -514,7 +532,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
       const uint8_t* resid_rows = nullptr;
       uint32_t rslot = 0;
       const int n_rs = nb * BN + 128 < g.N ? 2 : 1;
-      if (g.resid) {
+      if (Epi<F>::resid(g)) {
         ring_it += (uint32_t)k_blocks;                 // this tile's operand slots
         for (int rs = 0; rs < n_rs; ++rs) {            // every warp tracks the phase of every residual slot
           const uint32_t sl = (ring_it + (uint32_t)rs) % GSTAGES;
@@ -526,9 +544,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           rphase ^= 1u << sl;
         }
       }
-      epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
-                                my_slabs, slab_i, lane, resid_rows, q * 32 + lane);
-      if (g.resid) {
+      epilogue_columns<BN / 64, F>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
+                                   my_slabs, slab_i, lane, resid_rows, q * 32 + lane);
+      if (Epi<F>::resid(g)) {
         if (chalf < n_rs) {   // the four warps that read this slot hand it back to the producer
           asm volatile("bar.sync %0, 128;" ::"r"(2 + chalf) : "memory");
           if (q == 0 && lane == 0) mbar_arrive(&empty_bar[rslot]);
@@ -649,8 +667,25 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
     const int64_t max_clusters = sms / 2;
     const int grid = 2 * (int)(n_tiles < max_clusters ? n_tiles : max_clusters);
     const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
-    cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm2_tc_kernel<<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, map_r, g);
+    // the specialisations the transformer path launches; anything else takes the dynamic kernel
+    uint32_t want = (bias != nullptr ? EPI_BIAS : 0u) | (relu ? EPI_RELU : 0u) | (g.stats_in != nullptr ? EPI_AFFINE : 0u) |
+                    (g.resid ? EPI_RESID : 0u) | (g.stats_out != nullptr ? EPI_STATS : 0u) | (fmt == umma::kFmtF16 ? EPI_F16 : 0u) |
+                    ((out16 != nullptr && out32 == nullptr) ? EPI_OUT16_ONLY : 0u);
+    if (g.stats_in != nullptr) want &= ~EPI_BIAS;   // the affine epilogue carries its own constant term
+#define G2_LAUNCH(FLAGS)                                                                                               \
+  do {                                                                                                                 \
+    cudaFuncSetAttribute(gemm2_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+    gemm2_tc_kernel<FLAGS><<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, map_r, g);                   \
+  } while (0)
+    constexpr uint32_t kPlain = EPI_OUT16_ONLY, kF = EPI_F16;
+    if (want == (kPlain | kF)) G2_LAUNCH(kPlain | kF);                                                     // QKV
+    else if (want == (kPlain | kF | EPI_RESID | EPI_STATS)) G2_LAUNCH(kPlain | kF | EPI_RESID | EPI_STATS);   // W_out
+    else if (want == (kPlain | kF | EPI_AFFINE | EPI_RELU)) G2_LAUNCH(kPlain | kF | EPI_AFFINE | EPI_RELU);   // FFN1, LN folded
+    else if (want == (kPlain | kF | EPI_BIAS | EPI_RESID | EPI_STATS)) G2_LAUNCH(kPlain | kF | EPI_BIAS | EPI_RESID | EPI_STATS);   // FFN2
+    else if (want == (kPlain | kF | EPI_BIAS | EPI_RELU)) G2_LAUNCH(kPlain | kF | EPI_BIAS | EPI_RELU);       // FFN1, unfused
+    else if (want == (kPlain | kF | EPI_BIAS)) G2_LAUNCH(kPlain | kF | EPI_BIAS);                             // FFN2, unfused
+    else G2_LAUNCH(EPI_DYNAMIC);
+#undef G2_LAUNCH
     BFB_LAUNCH_CHECK(g.resid ? "gemm_tc_kernel[+residual,+row stats]" : g.stats_in != nullptr ? "gemm_tc_kernel[LayerNorm folded]" : "gemm_tc_kernel", st);
     return BFB200_OK;
   }
