@@ -160,7 +160,7 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
 // Epilogue of one accumulator stage for one warp: columns [c_begin, c_begin + 32 * NCH) of its 32 TMEM lanes ->
 // (+ bias)(ReLU) -> swizzled 32-row slabs -> 2-D TMA stores.  The tcgen05.ld of chunk i + 1 is in flight while chunk
 // i is converted and staged.
-template <int NCH, uint32_t F = EPI_DYNAMIC>
+template <int NCH, uint32_t F = EPI_DYNAMIC, int NSLAB = 2>
 __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtensorMap* map_c16, const CUtensorMap* map_c32,
                                                  uint32_t tacc, int n_base, int row0,
                                                  int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane,
@@ -189,8 +189,8 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
       else
         chunk_math<false, F>(g, r[ch & 1], v, n0, r_mean, r_rstd, box, resid_row, ch & 1, st_sum, st_sq);
       if (Epi<F>::out32(g)) {
-        uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
-        tma_store_wait_read<1>();   // the slab used two stores ago has been read by the copy engine
+        uint8_t* slab = my_slabs + (slab_i % NSLAB) * SLAB_BYTES;
+        tma_store_wait_read<NSLAB - 1>();   // the slab used NSLAB stores ago has been read by the copy engine
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -206,10 +206,10 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
       }
       if (Epi<F>::out16(g)) {
         // two 32-column chunks share one 128-byte slab row: even chunk -> bytes [0, 64), odd chunk -> [64, 128)
-        uint8_t* slab = my_slabs + (slab_i & 1u) * SLAB_BYTES;
+        uint8_t* slab = my_slabs + (slab_i % NSLAB) * SLAB_BYTES;
         const int half = ch & 1;   // c_begin is a multiple of 64
         if (half == 0) {
-          tma_store_wait_read<1>();
+          tma_store_wait_read<NSLAB - 1>();
           __syncwarp();
         }
 #pragma unroll
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
 // Each CTA's epilogue drains its own 128 TMEM lanes exactly like the one-SM kernel.
 // ------------------------------------------------------------------------------------------
 constexpr int G2_BN = 256;          // tile columns (UMMA N); each CTA stages G2_BN / 2 rows of W
-constexpr int G2_STAGES = 5;
+constexpr int G2_STAGES = 6;
+constexpr int G2_SLABS = 1;        // store slabs per epilogue warp
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -406,6 +407,16 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+
+#ifdef BFB_GEMM_TIMING
+// debug build only (make EXTRA=-DBFB_GEMM_TIMING, tools/gemm_timing.py): where the two-SM kernel's roles wait
+__device__ unsigned long long bfb_gemm_dbg[16];
+#define GT_BEGIN() const long long _gt0 = clock64()
+#define GT_END(slot) gdbg[slot] += clock64() - _gt0
+#else
+#define GT_BEGIN() do { } while (0)
+#define GT_END(slot) do { } while (0)
+#endif
 
 template <uint32_t F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
@@ -452,6 +463,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
   cluster_sync_all();   // the peer's barriers exist before anything signals them
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+#ifdef BFB_GEMM_TIMING
+  long long gdbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long g_begin = clock64();
+#endif
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own 128 rows of A, own 128 rows of the W tile =====
@@ -462,7 +477,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
         const int nb = (int)(tile - mb * tiles_n);
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
-          umma::mbar_wait(&empty_bar[s], ph ^ 1u);
+          { GT_BEGIN(); umma::mbar_wait(&empty_bar[s], ph ^ 1u); GT_END(0); }
           uint8_t* sa = smem + s * STAGE_BYTES;
           if (rank == 0) umma::mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
           const uint32_t bar = mapa_rank(umma::smem_u32(&full_bar[s]), 0);
@@ -493,12 +508,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
       uint32_t it = 0, tcount = 0, fphase = 0;
       for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
         const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
-        umma::mbar_wait(&acc_empty[as], aph ^ 1u);   // both epilogues have drained this accumulator stage
+        { GT_BEGIN(); umma::mbar_wait(&acc_empty[as], aph ^ 1u); GT_END(1); }   // both epilogues have drained this stage
         umma::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % GSTAGES;
-          umma::mbar_wait(&full_bar[s], (fphase >> s) & 1u);
+          { GT_BEGIN(); umma::mbar_wait(&full_bar[s], (fphase >> s) & 1u); GT_END(2); }
           fphase ^= 1u << s;
           umma::tc_fence_after_sync();
           const uint32_t sa = umma::smem_u32(smem + s * STAGE_BYTES);
@@ -519,7 +534,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     // ===== epilogue (both CTAs): warps 2..9 over this CTA's 128 rows; lane quarter w & 3, column half (w - 2) >> 2 =====
     const int q = warp & 3, chalf = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * 2u * SLAB_BYTES;
+    uint8_t* my_slabs = slabs + (uint32_t)(warp - 2) * (uint32_t)G2_SLABS * SLAB_BYTES;
     const uint32_t acc_empty_leader0 = mapa_rank(umma::smem_u32(&acc_empty[0]), 0);
     uint32_t tcount = 0, slab_i = 0, ring_it = 0, rphase = 0;
     for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tcount) {
@@ -527,8 +542,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
       const int row0 = (int)(mb * 2 * GM) + (int)rank * GM + q * 32;
-      umma::mbar_wait(&acc_full[as], aph);
+      { GT_BEGIN(); umma::mbar_wait(&acc_full[as], aph); GT_END(3); }
       umma::tc_fence_after_sync();
+#ifdef BFB_GEMM_TIMING
+      const long long _ge0 = clock64();
+#endif
       const uint8_t* resid_rows = nullptr;
       uint32_t rslot = 0;
       const int n_rs = nb * BN + 128 < g.N ? 2 : 1;
@@ -544,7 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
           rphase ^= 1u << sl;
         }
       }
-      epilogue_columns<BN / 64, F>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
+      epilogue_columns<BN / 64, F, G2_SLABS>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
                                    my_slabs, slab_i, lane, resid_rows, q * 32 + lane);
       if (Epi<F>::resid(g)) {
         if (chalf < n_rs) {   // the four warps that read this slot hand it back to the producer
@@ -553,6 +571,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
         }
         ring_it += (uint32_t)n_rs;
       }
+#ifdef BFB_GEMM_TIMING
+      gdbg[4] += clock64() - _ge0;
+      gdbg[5] += 1;
+#endif
       umma::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + as * (uint32_t)sizeof(uint64_t));
@@ -561,6 +583,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
+#ifdef BFB_GEMM_TIMING
+  if (lane == 0) {
+    const unsigned long long total = (unsigned long long)(clock64() - g_begin);
+    if (warp == 0) { atomicAdd(&bfb_gemm_dbg[0], (unsigned long long)gdbg[0]); atomicAdd(&bfb_gemm_dbg[1], total); }
+    if (warp == 1 && rank == 0) {
+      atomicAdd(&bfb_gemm_dbg[2], (unsigned long long)gdbg[1]); atomicAdd(&bfb_gemm_dbg[3], (unsigned long long)gdbg[2]);
+      atomicAdd(&bfb_gemm_dbg[4], total);
+    }
+    if (warp == 2) {
+      atomicAdd(&bfb_gemm_dbg[5], (unsigned long long)gdbg[3]); atomicAdd(&bfb_gemm_dbg[6], (unsigned long long)gdbg[4]);
+      atomicAdd(&bfb_gemm_dbg[7], (unsigned long long)gdbg[5]); atomicAdd(&bfb_gemm_dbg[8], total);
+    }
+  }
+#endif
   umma::tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // nobody retires while its peer may still signal its barriers or read its shared memory
@@ -666,7 +702,7 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
     const int64_t n_tiles = ((M + 2 * GM - 1) / (2 * GM)) * ((N + G2_BN - 1) / G2_BN);
     const int64_t max_clusters = sms / 2;
     const int grid = 2 * (int)(n_tiles < max_clusters ? n_tiles : max_clusters);
-    const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + 2 * GEPI_WARPS * 32 * 128;
+    const size_t smem = 1024 + (size_t)G2_STAGES * (GM * GK * 2 + (G2_BN / 2) * GK * 2) + G2_SLABS * GEPI_WARPS * 32 * 128;
     // the specialisations the transformer path launches; anything else takes the dynamic kernel
     uint32_t want = (bias != nullptr ? EPI_BIAS : 0u) | (relu ? EPI_RELU : 0u) | (g.stats_in != nullptr ? EPI_AFFINE : 0u) |
                     (g.resid ? EPI_RESID : 0u) | (g.stats_out != nullptr ? EPI_STATS : 0u) | (fmt == umma::kFmtF16 ? EPI_F16 : 0u) |
@@ -705,6 +741,18 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
 }
 
 }  // namespace bfb
+
+#ifdef BFB_GEMM_TIMING
+extern "C" int bfb200_debug_gemm_timing(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, bfb::bfb_gemm_dbg, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(bfb::bfb_gemm_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // C[M, N] = A[M, K] W[N, K]^T (+ bias)(ReLU); A, W 16-bit (fmt 0 = fp16, 1 = bf16) device pointers, A rows `a_pitch`
 // elements apart; out16 (same format) and/or out32 (fp32) with row pitch `ldc` elements, either may be NULL.
