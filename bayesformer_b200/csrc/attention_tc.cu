@@ -62,9 +62,10 @@ __device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
   return fmt == umma::kFmtF16 ? umma::pack_f16x2(a, b) : umma::pack_bf16x2(a, b);
 }
 
-template <int MAXKV>
+template <int MAXKV, bool F16>
 __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                                   const AttnArgs a) {
+  constexpr uint32_t FMT = F16 ? umma::kFmtF16 : umma::kFmtBF16;   // compile-time: no per-element format branches
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     umma::mbar_wait(&bar_qk, 0);
     umma::tc_fence_after_sync();
     const uint64_t dq = umma::smem_desc_sw128(umma::smem_u32(sQ)), dk = umma::smem_desc_sw128(umma::smem_u32(sK));
-    const uint32_t idesc = umma::instr_desc_16bit(AT_M, kvp, a.fmt);
+    const uint32_t idesc = umma::instr_desc_16bit(AT_M, kvp, FMT);
 #pragma unroll
     for (int k = 0; k < AT_DH / 16; ++k) umma::mma_bf16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
     umma::mma_commit(&bar_s);
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 w;
-      w.x = at_pack2(e[8 * c], e[8 * c + 1], a.fmt); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], a.fmt);
-      w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], a.fmt); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], a.fmt);
+      w.x = at_pack2(e[8 * c], e[8 * c + 1], FMT); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], FMT);
+      w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], FMT); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], FMT);
       *reinterpret_cast<uint4*>(slab + umma::sw128_offset(row, ch0 + c)) = w;
     }
   }
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     umma::tc_fence_after_sync();
     // B = V as loaded (keys x dims): MN-major, 128-byte rows of 64 dims, 8-key groups 1024 bytes apart;
     // one K = 16 step consumes two such groups -> 2048 bytes per step
-    const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, a.fmt) | (1u << 16);
+    const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, FMT) | (1u << 16);
     const uint32_t pP = umma::smem_u32(sP), pV = umma::smem_u32(sV);
     for (int ks = 0; ks < kvp / 16; ++ks) {
       const uint64_t dp = umma::smem_desc_sw128(pP + (ks >> 2) * (AT_M * 128) + (ks & 3) * 32);
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 w;
-        w.x = at_pack2(o[8 * c], o[8 * c + 1], a.fmt); w.y = at_pack2(o[8 * c + 2], o[8 * c + 3], a.fmt);
-        w.z = at_pack2(o[8 * c + 4], o[8 * c + 5], a.fmt); w.w = at_pack2(o[8 * c + 6], o[8 * c + 7], a.fmt);
+        w.x = at_pack2(o[8 * c], o[8 * c + 1], FMT); w.y = at_pack2(o[8 * c + 2], o[8 * c + 3], FMT);
+        w.z = at_pack2(o[8 * c + 4], o[8 * c + 5], FMT); w.w = at_pack2(o[8 * c + 6], o[8 * c + 7], FMT);
         dst[c] = w;
       }
     }
@@ -293,16 +294,26 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   BFB_REQUIRE(grid <= 0x7FFFFFFF, BFB200_ERR_UNSUPPORTED, "too many attention tiles in one launch");
   // one launch per query tile: tile 0 attends to <= 128 keys (48 KB of shared memory, 128 TMEM columns: four CTAs
   // per SM), tile 1 to <= 256 (96 KB, 256 columns: two CTAs per SM)
-  cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<128>::TOTAL);
+  const bool f16 = fmt == umma::kFmtF16;
+#define AT_LAUNCH(KV)                                                                                                   \
+  do {                                                                                                                  \
+    if (f16) {                                                                                                          \
+      cudaFuncSetAttribute(attention_tc_kernel<KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<KV>::TOTAL); \
+      attention_tc_kernel<KV, true><<<(unsigned)grid, 2 * AT_M, AtSmem<KV>::TOTAL, st>>>(map, a);                       \
+    } else {                                                                                                            \
+      cudaFuncSetAttribute(attention_tc_kernel<KV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<KV>::TOTAL); \
+      attention_tc_kernel<KV, false><<<(unsigned)grid, 2 * AT_M, AtSmem<KV>::TOTAL, st>>>(map, a);                      \
+    }                                                                                                                   \
+  } while (0)
   a.m_tile = 0;
-  attention_tc_kernel<128><<<(unsigned)grid, 2 * AT_M, AtSmem<128>::TOTAL, st>>>(map, a);
+  AT_LAUNCH(128);
   BFB_LAUNCH_CHECK("attention_tc_kernel<128>", st);
   if (len > AT_M) {
-    cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<256>::TOTAL);
     a.m_tile = 1;
-    attention_tc_kernel<256><<<(unsigned)grid, 2 * AT_M, AtSmem<256>::TOTAL, st>>>(map, a);
+    AT_LAUNCH(256);
     BFB_LAUNCH_CHECK("attention_tc_kernel<256>", st);
   }
+#undef AT_LAUNCH
   return BFB200_OK;
 }
 

@@ -479,10 +479,12 @@ __device__ __forceinline__ void store8_16(uint16_t* p, uint32_t fmt, const float
 }
 
 // x = dropout_E(embedding[tok]) * sqrt(d) + pe[t], fp32 and 16-bit copies      (transformer.py:355-362, :269-272)
+template <bool F16>
 __global__ void __launch_bounds__(256) embed16_kernel(const int32_t* __restrict__ tokens, int tok_stride,
                                                       const float* __restrict__ emb, const float* __restrict__ pe,
                                                       int64_t n_seq, int len, int d, float sqrt_d, MaskSource ms, int site,
-                                                      float* __restrict__ x, uint16_t* __restrict__ x16, uint32_t fmt) {
+                                                      float* __restrict__ x, uint16_t* __restrict__ x16) {
+  constexpr uint32_t fmt = F16 ? umma::kFmtF16 : umma::kFmtBF16;
   const int d8 = d >> 3;
   const int64_t total = n_seq * len * d8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -563,11 +565,12 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
 // out16 = dropout_out( LayerNorm(v16) ) with the row statistics already known: the GEMM that produced v (its epilogue
 // added the residual) also accumulated each row's sum and sum of squares (launch_gemm_tc_ex), so this kernel is one
 // 16-bit read and one 16-bit write per element (transformer.py:233, :370).  One warp per row.
-template <int NJ>
+template <int NJ, bool F16>
 __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restrict__ v16, const float2* __restrict__ stats,
                                                          uint16_t* __restrict__ out16, int64_t n_rows, int len, int d,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         float eps, MaskSource ms, int out_site, uint32_t fmt) {
+                                                         float eps, MaskSource ms, int out_site) {
+  constexpr uint32_t fmt = F16 ? umma::kFmtF16 : umma::kFmtBF16;   // compile-time: no per-element format branches
   const int lane = threadIdx.x & 31;
   const int d8 = d >> 3;
   const float inv_d = 1.0f / (float)d;
@@ -599,7 +602,13 @@ int launch_ln16_apply(const void* v16, const float2* stats, void* out16, int64_t
   BFB_REQUIRE((d & 7) == 0 && d <= 2048, BFB200_ERR_UNSUPPORTED, "ln16_apply needs d_model %% 8 == 0 and <= 2048 (got %d)", d);
   BFB_REQUIRE(n_rows < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");
   const int grid = stride_grid((n_rows + 7) / 8, 8);
-#define LAUNCH_LNA(NJ) ln16_apply_kernel<NJ><<<grid, 256, 0, st>>>((const uint16_t*)v16, stats, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, out_site, fmt)
+#define LAUNCH_LNA(NJ)                                                                                                         \
+  do {                                                                                                                         \
+    if (fmt == umma::kFmtF16)                                                                                                  \
+      ln16_apply_kernel<NJ, true><<<grid, 256, 0, st>>>((const uint16_t*)v16, stats, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, out_site); \
+    else                                                                                                                       \
+      ln16_apply_kernel<NJ, false><<<grid, 256, 0, st>>>((const uint16_t*)v16, stats, (uint16_t*)out16, n_rows, len, d, gamma, beta, eps, ms, out_site); \
+  } while (0)
   if (d <= 256) LAUNCH_LNA(1);
   else if (d <= 512) LAUNCH_LNA(2);
   else if (d <= 1024) LAUNCH_LNA(4);
@@ -844,8 +853,12 @@ int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const 
   if (x16 != nullptr && (d & 7) == 0) {
     BFB_REQUIRE(n_seq * len < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");
     const int64_t total8 = n_seq * len * (d >> 3);
-    embed16_kernel<<<stride_grid((total8 + 255) / 256, 8), 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d,
-                                                                        sqrtf((float)d), ms, site, x, (uint16_t*)x16, fmt);
+    if (fmt == umma::kFmtF16)
+      embed16_kernel<true><<<stride_grid((total8 + 255) / 256, 8), 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d,
+                                                                                sqrtf((float)d), ms, site, x, (uint16_t*)x16);
+    else
+      embed16_kernel<false><<<stride_grid((total8 + 255) / 256, 8), 256, 0, st>>>(tokens, tok_stride, emb, pe, n_seq, len, d,
+                                                                                 sqrtf((float)d), ms, site, x, (uint16_t*)x16);
     BFB_LAUNCH_CHECK("embed16_kernel", st);
     return BFB200_OK;
   }
