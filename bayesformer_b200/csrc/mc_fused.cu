@@ -240,7 +240,7 @@ __device__ __forceinline__ float sub_sum(float v, int n) {
 // softmax(log-probs) is exp(log-probs) up to rounding, so the un-tempered probabilities reuse the exponentials
 // of the log-softmax, and log(p + 1e-10) is taken as log p (the terms where they differ weigh < 1e-8).
 // ------------------------------------------------------------------------------------------
-template <int TPS>
+template <int TPS, bool NO_SAMPLING>
 __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __restrict__ stage, int stage_stride,
                                             int gt, int nseq, uint32_t s0, int len) {
   constexpr int NPT = FMAXV / TPS;
@@ -279,7 +279,7 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
     if (a.logp_out != nullptr && active && c < V) a.logp_out[(size_t)sq * V + c] = lg[j];
   }
   float ent = 0.f;
-  if (a.scheme != BFB200_SCHEME_SAMPLING) {
+  if (NO_SAMPLING || a.scheme != BFB200_SCHEME_SAMPLING) {
     const float inv_z = __fdividef(1.0f, z);
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
@@ -327,7 +327,7 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
   p2 = sub_max(p2, TPS);
 
   int token = best_i;
-  if (a.scheme == BFB200_SCHEME_SAMPLING) {
+  if (!NO_SAMPLING && a.scheme == BFB200_SCHEME_SAMPLING) {
     // inverse CDF in class order from one Philox word (the library's documented sampling rule)
     const RowRng srr = make_row_rng(a.ms, sq);
     const uint4 rnd = philox4x32_10(
@@ -465,8 +465,18 @@ __device__ __forceinline__ void fused_issue_product(uint32_t tiles_u32, int a_se
   umma::mma_commit(&group_bars[G]);
 }
 
-template <int MAXLEN>
-__global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a) {
+// FAST = the configuration every MC-dropout acquisition round runs (the reference's default dropout sites E +
+// layer-out, Philox masks, greedy per-draw decoding, no log-prob / forced-token side channels): the latent-site,
+// mask-injection, sampling and side-channel branches are compiled out instead of tested at run time.
+template <int MAXLEN, bool FAST>
+__global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a_in) {
+  FusedArgs a = a_in;
+  if (FAST) {
+    a.site_flags = BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT;
+    a.ms.bits = nullptr;
+    a.logp_out = nullptr;
+    a.forced = nullptr;
+  }
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment of the swizzled tiles, computed as an offset so the pointers stay in the shared
   // address space (LDS / STS instead of generic loads)
@@ -855,8 +865,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     umma::group_sync(bar_id, FGROUP_THREADS);
 
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
-    if (a.tps == 16) score_phase<16>(a, stage, stage_stride, gt, nseq, s0, len);
-    else             score_phase<8>(a, stage, stage_stride, gt, nseq, s0, len);
+    if (a.tps == 16) score_phase<16, FAST>(a, stage, stage_stride, gt, nseq, s0, len);
+    else             score_phase<8, FAST>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
@@ -971,16 +981,22 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  if (len <= 8) {
-    cudaFuncSetAttribute(mc_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mc_forward_kernel<8><<<(int)grid, FTHREADS, smem, st>>>(a);
-  } else if (len <= 16) {
-    cudaFuncSetAttribute(mc_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mc_forward_kernel<16><<<(int)grid, FTHREADS, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(mc_forward_kernel<FMAXLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mc_forward_kernel<FMAXLEN><<<(int)grid, FTHREADS, smem, st>>>(a);
-  }
+  const bool fast = a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) && a.ms.bits == nullptr &&
+                    a.logp_out == nullptr && a.forced == nullptr && scheme != BFB200_SCHEME_SAMPLING;
+#define FUSED_LAUNCH(ML)                                                                                       \
+  do {                                                                                                         \
+    if (fast) {                                                                                                \
+      cudaFuncSetAttribute(mc_forward_kernel<ML, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      mc_forward_kernel<ML, true><<<(int)grid, FTHREADS, smem, st>>>(a);                                       \
+    } else {                                                                                                   \
+      cudaFuncSetAttribute(mc_forward_kernel<ML, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      mc_forward_kernel<ML, false><<<(int)grid, FTHREADS, smem, st>>>(a);                                      \
+    }                                                                                                          \
+  } while (0)
+  if (len <= 8) FUSED_LAUNCH(8);
+  else if (len <= 16) FUSED_LAUNCH(16);
+  else FUSED_LAUNCH(FMAXLEN);
+#undef FUSED_LAUNCH
   BFB_LAUNCH_CHECK("mc_forward_kernel", st);
   return BFB200_OK;
 }
