@@ -278,13 +278,23 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
     lg[j] = (lg[j] - mx) - lse;   // log-probabilities (class >= V: -inf)
     if (a.logp_out != nullptr && active && c < V) a.logp_out[(size_t)sq * V + c] = lg[j];
   }
-  float ent = 0.f;
+  float ent = 0.f, p1, p2 = -INFINITY;
   if (NO_SAMPLING || a.scheme != BFB200_SCHEME_SAMPLING) {
+    // un-tempered distribution: p_j = e_j / z with e_j = exp(logit_j - max) already at hand, so only the requested
+    // score is formed (warp-uniform branches): max p = 1 / z; margin needs the runner-up; entropy sum e_j log p_j
     const float inv_z = __fdividef(1.0f, z);
+    p1 = inv_z;
+    if (a.mode == BFB200_MODE_ENTROPY) {
 #pragma unroll
-    for (int j = 0; j < NPT; ++j) {
-      pr[j] *= inv_z;
-      ent = fmaf(pr[j], fmaxf(lg[j], -1e30f), ent);   // 0 * -inf guard for padded / underflowed classes
+      for (int j = 0; j < NPT; ++j) ent = fmaf(pr[j], fmaxf(lg[j], -1e30f), ent);   // 0 * -inf guard (padded classes)
+      ent = -sub_sum(ent, TPS) * inv_z;
+    } else if (a.mode == BFB200_MODE_MARGIN) {
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = sub + j * TPS;
+        if (c != best_i) p2 = fmaxf(p2, pr[j]);
+      }
+      p2 = sub_max(p2, TPS) * inv_z;
     }
   } else {
     // tempered distribution: softmax(log-probs / temperature); its maximum sits at the arg-max class
@@ -303,28 +313,27 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
       pr[j] *= inv_pz;
       ent = fmaf(pr[j], fmaxf(lg[j] - log_pz, -1e30f), ent);
     }
-  }
-  ent = -sub_sum(ent, TPS);
-  float p1 = -INFINITY;
-  int p1_i = 0x7fffffff;
+    ent = -sub_sum(ent, TPS);
+    p1 = -INFINITY;
+    int p1_i = 0x7fffffff;
 #pragma unroll
-  for (int j = 0; j < NPT; ++j) {
-    const int c = sub + j * TPS;
-    if (pr[j] > p1) { p1 = pr[j]; p1_i = c; }
-  }
+    for (int j = 0; j < NPT; ++j) {
+      const int c = sub + j * TPS;
+      if (pr[j] > p1) { p1 = pr[j]; p1_i = c; }
+    }
 #pragma unroll
-  for (int o = TPS >> 1; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, p1, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, p1_i, o);
-    if (ob > p1 || (ob == p1 && oi < p1_i)) { p1 = ob; p1_i = oi; }
-  }
-  float p2 = -INFINITY;
+    for (int o = TPS >> 1; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, p1, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, p1_i, o);
+      if (ob > p1 || (ob == p1 && oi < p1_i)) { p1 = ob; p1_i = oi; }
+    }
 #pragma unroll
-  for (int j = 0; j < NPT; ++j) {
-    const int c = sub + j * TPS;
-    if (c != p1_i) p2 = fmaxf(p2, pr[j]);
+    for (int j = 0; j < NPT; ++j) {
+      const int c = sub + j * TPS;
+      if (c != p1_i) p2 = fmaxf(p2, pr[j]);
+    }
+    p2 = sub_max(p2, TPS);
   }
-  p2 = sub_max(p2, TPS);
 
   int token = best_i;
   if (!NO_SAMPLING && a.scheme == BFB200_SCHEME_SAMPLING) {
@@ -379,6 +388,24 @@ __device__ __forceinline__ uint32_t half_keep_mask(const MaskSource& m, const Ro
     return m.bits[row * m.words + h];
   }
   return philox_keep32(m.key.x, m.key.y, m.threshold, rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h));
+}
+
+// FAST instantiations (two dropout sites): the four Philox calls of a half row are inlined and decide straight on the
+// 16-bit halves of their output words, eight features at a time — no keep-bit packing / unpacking in between
+// (same decisions as philox_keep32 + drop_half: feature j of a call <- half j & 1 of word j >> 1, kept iff >= threshold).
+__device__ __forceinline__ void drop_half_direct(float (&v)[HW], const MaskSource& m, const RowRng& rr, uint32_t pos,
+                                                 uint32_t site, uint32_t h) {
+  const uint32_t thr_hi = m.threshold << 16;
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c) {
+    const uint4 r = philox4x32_10(make_uint4(rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h + c)), m.key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      v[8 * c + 2 * i] = (w[i] << 16) >= thr_hi ? v[8 * c + 2 * i] * m.scale : 0.f;
+      v[8 * c + 2 * i + 1] = w[i] >= thr_hi ? v[8 * c + 2 * i + 1] * m.scale : 0.f;
+    }
+  }
 }
 
 __device__ __forceinline__ void store_half_f16(uint8_t* tile, uint32_t row, uint32_t h, const float (&v)[HW]) {
@@ -465,14 +492,15 @@ __device__ __forceinline__ void fused_issue_product(uint32_t tiles_u32, int a_se
   umma::mma_commit(&group_bars[G]);
 }
 
-// FAST = the configuration every MC-dropout acquisition round runs (the reference's default dropout sites E +
-// layer-out, Philox masks, greedy per-draw decoding, no log-prob / forced-token side channels): the latent-site,
-// mask-injection, sampling and side-channel branches are compiled out instead of tested at run time.
-template <int MAXLEN, bool FAST>
+// FAST != 0 = the configurations every acquisition round runs (the reference's default dropout sites E + layer-out of a
+// BayesFormer, or none for the standard Transformer; Philox masks, greedy decoding, no log-prob / forced-token side
+// channels): the latent-site, mask-injection, sampling and side-channel branches are compiled out instead of tested
+// at run time.
+template <int MAXLEN, int FAST>   // 0: everything at run time; 1: sites E + layer-out (BayesFormer); 2: no site (Transformer)
 __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a_in) {
   FusedArgs a = a_in;
   if (FAST) {
-    a.site_flags = BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT;
+    a.site_flags = FAST == 1 ? (BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) : 0u;
     a.ms.bits = nullptr;
     a.logp_out = nullptr;
     a.forced = nullptr;
@@ -592,7 +620,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 
     // ---- embedding + dropout E + sqrt(d) scale + positional encoding (transformer.py:355-362) ----
     {
-      const uint32_t k_embed = (fl & BFB200_SITE_EMBED) ? half_keep_mask(ms, rr, (uint32_t)pos, 0u, (uint32_t)h) : 0u;
+      const uint32_t k_embed = (!FAST && (fl & BFB200_SITE_EMBED)) ? half_keep_mask(ms, rr, (uint32_t)pos, 0u, (uint32_t)h) : 0u;
       float x[HW];
       if (row_valid) {
         const int tok = a.tokens[(size_t)s * a.tok_stride + pos];
@@ -602,7 +630,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           const float4 v = __ldg(e + i);
           x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        if (fl & BFB200_SITE_EMBED) drop_half(x, k_embed, ms.scale);
+        if (FAST == 1) drop_half_direct(x, ms, rr, (uint32_t)pos, 0u, (uint32_t)h);
+        else if (fl & BFB200_SITE_EMBED) drop_half(x, k_embed, ms.scale);
         const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD + h * HW;
 #pragma unroll
         for (int i = 0; i < HW; ++i) x[i] = x[i] * sqrt_d + pe[i];
@@ -821,7 +850,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
-        const uint32_t k_out = (fl & BFB200_SITE_LAYER_OUT) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
+        const uint32_t k_out = (!FAST && (fl & BFB200_SITE_LAYER_OUT)) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
         float v[HW];
         tmem_load_half(tW + h * HW, v);
         const float* b2 = pl + 192 + h * HW;
@@ -838,7 +867,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         red[h * FROWS + row] = own;
         umma::group_sync(bar_id, FGROUP_THREADS);
         ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + 256 + h * HW, pl + 320 + h * HW, a.ln_eps);
-        if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);   // transformer.py:370
+        if (FAST == 1) drop_half_direct(v, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);   // transformer.py:370
+        else if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);
         if (!prune) tmem_store_half(tX, v);
         store_half_f16(B0, row, h, v);
       }
@@ -865,8 +895,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     umma::group_sync(bar_id, FGROUP_THREADS);
 
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
-    if (a.tps == 16) score_phase<16, FAST>(a, stage, stage_stride, gt, nseq, s0, len);
-    else             score_phase<8, FAST>(a, stage, stage_stride, gt, nseq, s0, len);
+    if (a.tps == 16) score_phase<16, FAST != 0>(a, stage, stage_stride, gt, nseq, s0, len);
+    else             score_phase<8, FAST != 0>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
@@ -981,22 +1011,24 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  const bool fast = a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) && a.ms.bits == nullptr &&
-                    a.logp_out == nullptr && a.forced == nullptr && scheme != BFB200_SCHEME_SAMPLING;
-#define FUSED_LAUNCH(ML)                                                                                       \
-  do {                                                                                                         \
-    if (fast) {                                                                                                \
-      cudaFuncSetAttribute(mc_forward_kernel<ML, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      mc_forward_kernel<ML, true><<<(int)grid, FTHREADS, smem, st>>>(a);                                       \
-    } else {                                                                                                   \
-      cudaFuncSetAttribute(mc_forward_kernel<ML, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      mc_forward_kernel<ML, false><<<(int)grid, FTHREADS, smem, st>>>(a);                                      \
-    }                                                                                                          \
+  const bool plain = a.ms.bits == nullptr && a.logp_out == nullptr && a.forced == nullptr && scheme != BFB200_SCHEME_SAMPLING;
+  const int fast = !plain ? 0 : a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) ? 1 : a.site_flags == 0u ? 2 : 0;
+#define FUSED_LAUNCH_F(ML, FV)                                                                              \
+  do {                                                                                                      \
+    cudaFuncSetAttribute(mc_forward_kernel<ML, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    mc_forward_kernel<ML, FV><<<(int)grid, FTHREADS, smem, st>>>(a);                                        \
+  } while (0)
+#define FUSED_LAUNCH(ML)                  \
+  do {                                    \
+    if (fast == 1) FUSED_LAUNCH_F(ML, 1); \
+    else if (fast == 2) FUSED_LAUNCH_F(ML, 2); \
+    else FUSED_LAUNCH_F(ML, 0);           \
   } while (0)
   if (len <= 8) FUSED_LAUNCH(8);
   else if (len <= 16) FUSED_LAUNCH(16);
   else FUSED_LAUNCH(FMAXLEN);
 #undef FUSED_LAUNCH
+#undef FUSED_LAUNCH_F
   BFB_LAUNCH_CHECK("mc_forward_kernel", st);
   return BFB200_OK;
 }
