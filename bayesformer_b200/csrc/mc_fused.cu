@@ -1024,7 +1024,13 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
     else if (fast == 2) FUSED_LAUNCH_F(ML, 2); \
     else FUSED_LAUNCH_F(ML, 0);           \
   } while (0)
-  if (len <= 8) FUSED_LAUNCH(8);
+  // the pair phase keeps a sequence's K and V rows in registers: one instantiation per length up to 8 (the decode steps
+  // of the reference's addition task run at lengths 4..8), so that the arrays are exactly as long as the sequences
+  if (len <= 4) FUSED_LAUNCH(4);
+  else if (len == 5) FUSED_LAUNCH(5);
+  else if (len == 6) FUSED_LAUNCH(6);
+  else if (len == 7) FUSED_LAUNCH(7);
+  else if (len == 8) FUSED_LAUNCH(8);
   else if (len <= 16) FUSED_LAUNCH(16);
   else FUSED_LAUNCH(FMAXLEN);
 #undef FUSED_LAUNCH
