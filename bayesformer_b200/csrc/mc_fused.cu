@@ -38,7 +38,7 @@ constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
 constexpr int FMAXLEN = 40;     // longest sequence the fused path takes (rows of the positional table in the image)
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
-constexpr int PARAMS_PER_LAYER = 6 * 64;      // ln1_w, ln1_b, b1, b2, ln2_w, ln2_b (floats)
+constexpr int PARAMS_PER_LAYER = 8 * 64;      // ln1_w, ln1_b, b1, b2, ln2_w, ln2_b, col_s, col_c (floats)
 
 struct FusedLayout {
   uint32_t fp;            // F rounded up to 16
@@ -65,7 +65,7 @@ __host__ __device__ inline FusedLayout fused_layout(int L, int F, int V) {
   return lay;
 }
 
-constexpr size_t kFusedStaticSlack = 2048;  // alignment slack + static __shared__ of the kernel
+constexpr size_t kFusedStaticSlack = 4608;  // static __shared__ of the kernel (LayerNorm exchange 4 KB, barriers)
 
 inline size_t fused_smem_bytes(const FusedLayout& lay) {
   return 1024 + (size_t)lay.image_bytes + (size_t)FGROUPS * 3 * TILE_BYTES;
@@ -77,6 +77,9 @@ inline size_t fused_smem_bytes(const FusedLayout& lay) {
 __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t* __restrict__ image) {
   const int L = m.n_layers, F = m.d_ff, V = m.ntoken;
   const int per_layer = 3 * FD * FD + FD * FD + F * FD + FD * F;
+  // LayerNorm1 is folded into the FFN1 product unless a dropout site sits between them (mc_forward_kernel): the W1
+  // slot then holds W1 * diag(gamma1)
+  const bool fold_ln1 = !(m.site_flags & BFB200_SITE_FFN_IN);
   const int n_mat = L * per_layer + V * FD;
   const int n_par = L * PARAMS_PER_LAYER + FMAXV + FMAXLEN * FD;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mat + n_par; i += gridDim.x * blockDim.x) {
@@ -93,6 +96,7 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
           n = j / FD; k = j % FD; w = m.w_out[(size_t)l * FD * FD + j]; base += lay.off_out;
         } else if ((j -= FD * FD) < F * FD) {        // FFN W1 (F, d)
           n = j / FD; k = j % FD; w = m.ff1_w[(size_t)l * F * FD + j]; base += lay.off_w1;
+          if (fold_ln1) w *= m.ln1_w[l * FD + k];
         } else {                                     // FFN W2 (d, F): K = F
           j -= F * FD;
           n = j / F; k = j % F; w = m.ff2_w[(size_t)l * FD * F + j]; base += lay.off_w2;
@@ -114,7 +118,18 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
           case 2: v = c < F ? m.ff1_b[l * F + c] : 0.f; break;
           case 3: v = m.ff2_b[l * FD + c]; break;
           case 4: v = m.ln2_w[l * FD + c]; break;
-          default: v = m.ln2_b[l * FD + c]; break;
+          case 5: v = m.ln2_b[l * FD + c]; break;
+          case 6:    // col_s[n] = sum_k fp16(W1[n, k] gamma1[k]) — of the rounded values the tensor core multiplies
+            if (c < F)
+              for (int k = 0; k < FD; ++k)
+                v += __half2float(__float2half_rn(fminf(fmaxf(m.ff1_w[((size_t)l * F + c) * FD + k] * m.ln1_w[l * FD + k], -65504.f), 65504.f)));
+            break;
+          default:   // col_c[n] = b1[n] + sum_k W1[n, k] beta1[k]
+            if (c < F) {
+              v = m.ff1_b[l * F + c];
+              for (int k = 0; k < FD; ++k) v = fmaf(m.ff1_w[((size_t)l * F + c) * FD + k], m.ln1_b[l * FD + k], v);
+            }
+            break;
         }
       } else if (j < L * PARAMS_PER_LAYER + FMAXV) {
         const int c = j - L * PARAMS_PER_LAYER;
@@ -567,6 +582,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const float sqrt_d = sqrtf((float)FD);
   const float qk_scale_log2e = 1.4426950408889634f / sqrtf((float)FDH);   // scores / sqrt(dh), in base-2 exponent units
   const uint32_t fl = a.site_flags;
+  const bool fold_ln1 = !(fl & BFB200_SITE_FFN_IN);   // the same rule fused_pack_kernel packed the W1 slot by
   const MaskSource& ms = a.ms;
 
   const uint32_t img_u32 = umma::smem_u32(img);
@@ -798,7 +814,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         // dead rows of the last layer: take part in the barriers of the three products and the two LayerNorm
         // exchanges (thread 0 of the group still issues the MMAs inside gemm()), compute nothing
         gemm(0, wl + lay.off_out, FD, 4);
-        umma::group_sync(bar_id, FGROUP_THREADS);
+        if (!fold_ln1) umma::group_sync(bar_id, FGROUP_THREADS);
         gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
         gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
         umma::group_sync(bar_id, FGROUP_THREADS);
@@ -821,9 +837,14 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         }
         const float2 own = ln_partial(v);
         red[h * FROWS + row] = own;
-        umma::group_sync(bar_id, FGROUP_THREADS);
-        ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + h * HW, pl + 64 + h * HW, a.ln_eps);
-        if (fl & BFB200_SITE_FFN_IN) drop_half(v, k_ffn_in, ms.scale);
+        if (!fold_ln1) {
+          umma::group_sync(bar_id, FGROUP_THREADS);
+          ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + h * HW, pl + 64 + h * HW, a.ln_eps);
+          drop_half(v, k_ffn_in, ms.scale);
+        }
+        // Otherwise LayerNorm1 only feeds the FFN1 product with no dropout site in between, so it is folded into that
+        // product (W1 * gamma1 in the image): the UN-normalised row is the operand, the statistics wait in `red` for
+        // the FFN1 epilogue, and the exchange barrier merges with the product's own
         store_half_f16(B0, row, h, v);
       }
 
@@ -831,6 +852,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
       {
         const float* b1 = pl + 128;
+        const float* col_s = pl + 384;
+        const float* col_c = pl + 448;
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (fold_ln1) {   // W1 LN(v) + b1 = rstd (v (W1 gamma)^T - mean col_s) + col_c
+          const float2 own = red[h * FROWS + row], other = red[(h ^ 1) * FROWS + row];
+          const float dm = own.x - other.x;
+          ln_mean = 0.5f * (own.x + other.x);
+          ln_rstd = rsqrtf((own.y + other.y + 16.0f * dm * dm) * (1.0f / FD) + a.ln_eps);
+        }
         const uint32_t half_cols = lay.fp >> 1;   // multiple of 8
         for (uint32_t c0 = half_cols * h; c0 < half_cols * (h + 1); c0 += 8) {
           uint32_t r[8];
@@ -838,7 +868,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           umma::tmem_ld_wait();
           float hc[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) hc[i] = fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
+          for (int i = 0; i < 8; ++i)
+            hc[i] = fold_ln1 ? fmaxf(fmaf(ln_rstd, fmaf(-ln_mean, col_s[c0 + i], __uint_as_float(r[i])), col_c[c0 + i]), 0.f)
+                             : fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
           uint4 w;
           w.x = umma::pack_f16x2(hc[0], hc[1]); w.y = umma::pack_f16x2(hc[2], hc[3]);
           w.z = umma::pack_f16x2(hc[4], hc[5]); w.w = umma::pack_f16x2(hc[6], hc[7]);
