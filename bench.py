@@ -507,14 +507,14 @@ def kernel_roofline(name: str, stat: dict, passes: int, pool: int, P: int, N: in
         flops = passes * pool * flops_per_pool_sample(P, N)
         ach = flops / (ms * 1e-3) / 1e12
         traffic, traffic_note = None, None
-        prof = os.path.join(ROOT, "profiles", "r1n_ncu_mc_forward_bench_size.json")
+        prof = os.path.join(ROOT, "profiles", "r1p_ncu_mc_forward_bench_size.json")
         if os.path.exists(prof) and pool == POOL_PER_GPU:   # dram__bytes_read + write of one `ncu --set full` capture
             traffic = int(json.load(open(prof))["dram_bytes_per_launch_mean"])
             traffic_note = "mean over the 5 launches of a pass (len 4..8), " + os.path.basename(prof)
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "traffic_note": traffic_note, "avg_launch_ms": avg_ms, "peak_source": peak_src,
-                "note": "issue-bound by construction (dh = 8, F = 8, len <= 8): ncu shows 41-44 % of issue slots and 5 % "
+                "note": "issue-bound by construction (dh = 8, F = 8, len <= 8): ncu shows 41-45 % of issue slots and 6 % "
                         "of tensor-pipe cycles busy; algorithmic HBM traffic is 40 B per sequence-step"}
     per_row = {"attention_kernel": 4 * d * 4,            # read q,k,v + write out
                "resid_ln_kernel": 3 * d * 4,             # read x, y + write out
