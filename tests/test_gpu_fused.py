@@ -376,3 +376,22 @@ def test_select_samples_on_a_char_level_pool_runs_the_fused_kernel(engine, dev):
         picked = al.select_samples(model, tok, pool, dev, nb_samples=50, compute="dropout", mode="entropy")
     assert "mc_forward_kernel" in prof.kernels and "sgemm_tn_kernel" not in prof.kernels
     assert len(set(picked)) == 50 and all(0 <= i < 600 for i in picked)
+
+
+@pytest.mark.parametrize("bayes", [True, False])
+def test_specialised_kernels_equal_the_generic_kernel_bit_for_bit(engine, dev, c2, bayes):
+    """The FAST instantiations (default sites / no site, Philox masks, greedy decoding, no side channels) compile the
+    other branches out; asking for the log-probs routes the same call through the generic instantiation.  Same seed
+    => identical masks => the scores and the decoded tokens must agree exactly, for sequence lengths on both sides of
+    the per-length instantiations (4..8, 16, 40)."""
+    z, sd = c2
+    model = H.build_model(sd, float(z["p"]) if bayes else None, bayes).to(dev)
+    pack = model.native_pack(dev, "fp16")
+    for P, N in ((4, 5), (2, 3), (11, 4), (20, 3)):
+        prompts = torch.randint(0, 114, (P, 77), generator=torch.Generator().manual_seed(P)).to(dev)
+        scheme, T = ("dropout", 6) if bayes else ("greedy", 1)
+        for mode in H.MODES:
+            fast = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True)
+            slow = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True, return_logp=True)
+            assert torch.equal(fast.step_scores, slow.step_scores)
+            assert torch.equal(fast.tokens, slow.tokens)
