@@ -410,7 +410,16 @@ _PACKS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 def _param_signature(module, device) -> tuple:
-    return (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + site_flags_of(module)
+    # `_bfb_weights_generation` is bumped by code that updates the weights without going through the dispatcher (a CUDA
+    # graph replay of the optimizer step does not touch `_version`): see mark_weights_changed
+    return ((str(device), getattr(module, "_bfb_weights_generation", 0)) +
+            tuple((p.data_ptr(), p._version) for p in module.parameters()) + site_flags_of(module))
+
+
+def mark_weights_changed(module) -> None:
+    """Invalidate the packed / 16-bit weight images of `module` (weights were updated behind autograd's back, e.g. by
+    replaying a captured optimizer step)."""
+    module._bfb_weights_generation = getattr(module, "_bfb_weights_generation", 0) + 1
 
 
 def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransformer:

@@ -26,25 +26,106 @@ def _batch_loss(model, dataset, tokenizer, start, batch_size, vocab_size, device
     return criterion(pred, answers.view(-1))
 
 
+class _GraphedTrainStep:
+    """One training step (forward, loss, backward, AdamW) of a fixed batch shape as ONE CUDA graph.
+
+    The reference's step is ~600 kernels of a few microseconds each on this model (50 k parameters, 20 x 9 tokens):
+    launch-bound, 4-5 ms in eager mode.  Captured once per (prompt length, answer length, batch) shape and replayed,
+    the same kernels run back to back.  Capturing needs warm-up runs of the step; parameters and optimizer state are
+    saved before and restored IN PLACE after them, so creating a graph never advances the training."""
+
+    def __init__(self, model, optimizer, criterion, p_len: int, a_len: int, batch: int, vocab_size: int, device):
+        self.tokens = torch.zeros(p_len + a_len + 1, batch, dtype=torch.int64, device=device)
+        self.loss = None
+        self.p_len, self.vocab = p_len, vocab_size
+        params = [p for p in model.parameters()]
+        saved_p = [p.detach().clone() for p in params]
+        saved_s = {id(p): {k: v.clone() for k, v in optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params}
+        had_state = {id(p): p in optimizer.state and len(optimizer.state[p]) > 0 for p in params}
+        rng = torch.cuda.get_rng_state(device)
+
+        def step():
+            out = model(self.tokens)
+            pred = out[self.p_len - 1:-1, :, :].reshape(-1, self.vocab)
+            loss = criterion(pred, self.tokens[self.p_len:].reshape(-1))
+            loss.backward()
+            optimizer.step()
+            return loss
+
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                optimizer.zero_grad(set_to_none=True)
+                step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = step()
+        # undo the warm-up steps (capture itself executes nothing)
+        with torch.no_grad():
+            for p, sp in zip(params, saved_p):
+                p.copy_(sp)
+                for k, v in optimizer.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        if had_state[id(p)]:
+                            v.copy_(saved_s[id(p)][k])
+                        else:
+                            v.zero_()
+        torch.cuda.set_rng_state(rng, device)
+
+    def run(self, prompts: torch.Tensor, answers: torch.Tensor) -> torch.Tensor:
+        self.tokens[:self.p_len].copy_(prompts, non_blocking=True)
+        self.tokens[self.p_len:].copy_(answers, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
+def _graphs_enabled(device) -> bool:
+    import os
+
+    return torch.device(device).type == "cuda" and os.environ.get("BFB200_GRAPH_TRAIN", "1") != "0"
+
+
 def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, batch_size: int, lr: float,
           vocab_size: int, tokenizer: Tokenizer, device: str) -> tuple[np.ndarray, np.ndarray]:
     """AdamW + CrossEntropy on the (already log-softmaxed) outputs; returns per-epoch (train, valid) losses.
 
     Reporting quirk kept: epoch losses are sums of batch means divided by the dataset size (:110-111).
+    On a CUDA device every distinct batch shape is captured once as a CUDA graph (`_GraphedTrainStep`; set
+    BFB200_GRAPH_TRAIN=0 for the plain eager loop) and the batch losses are summed on the device, read once per epoch.
     """
-    optimizer = torch.optim.AdamW(model.parameters(), lr=lr)
+    use_graphs = _graphs_enabled(device)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, capturable=True) if use_graphs else \
+        torch.optim.AdamW(model.parameters(), lr=lr)
     criterion = nn.CrossEntropyLoss()
     history_train, history_valid = [], []
     best = float("inf")
+    graphs: dict[tuple[int, int, int], _GraphedTrainStep] = {}
     for epoch in range(1, nb_epochs + 1):
         model.train()
         running = 0.0
+        running_dev = torch.zeros((), device=device) if use_graphs else None
         for start in range(0, len(train_dataset) - 1, batch_size):
+            if use_graphs:
+                prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
+                key = (p_len, a_len, prompts.shape[1])
+                if key not in graphs:
+                    graphs[key] = _GraphedTrainStep(model, optimizer, criterion, p_len, a_len, prompts.shape[1], vocab_size,
+                                                    device)
+                running_dev += graphs[key].run(prompts, answers).detach()
+                continue
             model.zero_grad()
             loss = _batch_loss(model, train_dataset, tokenizer, start, batch_size, vocab_size, device, criterion)
             loss.backward()
             optimizer.step()
             running += loss.item()
+        if use_graphs:
+            running = float(running_dev.item())
+            from bayesformer_b200 import engine
+
+            engine.mark_weights_changed(model)   # graph replays update the weights without bumping tensor versions
         model.eval()
         running_valid = 0.0
         with torch.no_grad():

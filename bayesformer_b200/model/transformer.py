@@ -161,6 +161,19 @@ def generate_subsequent_mask(sz: int) -> torch.Tensor:
     return torch.triu(torch.full((sz, sz), float("-inf")), diagonal=1)
 
 
+_MASK_CACHE: dict[tuple[int, str], torch.Tensor] = {}
+
+
+def _causal_mask_on(sz: int, device: torch.device) -> torch.Tensor:
+    """The same mask, built once per (size, device): the reference rebuilds it on the host and copies it over in every
+    forward (:366), which also cannot be captured in a CUDA graph (utils.train's graphed step)."""
+    key = (sz, str(device))
+    mask = _MASK_CACHE.get(key)
+    if mask is None:
+        mask = _MASK_CACHE[key] = generate_subsequent_mask(sz).to(device)
+    return mask
+
+
 class MyTransformer(nn.Module):
     """Embedding → (+MC dropout) → ×sqrt(d) → +PE → blocks (→ MC dropout each) → vocab head → log-softmax.
 
@@ -226,7 +239,7 @@ class MyTransformer(nn.Module):
         if self.bayes:
             x = _mc_dropout(x, self.bayes_dropout)
         x = self.pos_enc(x * math.sqrt(self.d_model))
-        mask = generate_subsequent_mask(src.shape[0]).to(src.device)
+        mask = _causal_mask_on(src.shape[0], src.device)
         for layer in self.layers:
             x = layer(x, mask=mask)
             if self.bayes:
