@@ -120,11 +120,43 @@ def select_samples_from_tokens(model: MyTransformer, prompts: torch.Tensor, new_
         return picked.tolist()
 
 
-def select_samples(model: MyTransformer, tokenizer: Tokenizer, pool_dataset: list[tuple[str, str]], device: str,
+class TokenizedPool:
+    """A pool tokenised ONCE (the reference re-tokenises the whole pool in every acquisition round,
+    `active_learning.py:191-194`).  Pass it to `select_samples` in place of the list of pairs; it also behaves like
+    that list (`len`, indexing, iteration), so `create_new_train_set(train, pool, indices)` keeps working.  The token
+    matrix stays on the device it was first scored on."""
+
+    def __init__(self, pool_dataset: list[tuple[str, str]], tokenizer: Tokenizer):
+        self.items = list(pool_dataset)
+        prompts, _answers, _p_len, self.answers_length, _, _ = preprocessing.get_batch(self.items, tokenizer, 0, len(self.items))
+        self.prompts = prompts
+        self._on_device: dict[str, torch.Tensor] = {}
+
+    def prompts_on(self, device) -> torch.Tensor:
+        key = str(torch.device(device))
+        if key not in self._on_device:
+            self._on_device[key] = self.prompts.to(device)
+        return self._on_device[key]
+
+    def __len__(self) -> int:
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+    def __iter__(self):
+        return iter(self.items)
+
+
+def select_samples(model: MyTransformer, tokenizer: Tokenizer, pool_dataset, device: str,
                    nb_samples: int = 200, compute: str = "greedy", mode: str = "max") -> list[int]:
-    """Indices of the `nb_samples` pool items with the largest step-averaged score (reference :158-211)."""
+    """Indices of the `nb_samples` pool items with the largest step-averaged score (reference :158-211).
+    `pool_dataset` is the reference's list of (prompt, answer) pairs, or a `TokenizedPool` built from it once."""
     model.eval()
     with torch.no_grad():
+        if isinstance(pool_dataset, TokenizedPool):
+            return select_samples_from_tokens(model, pool_dataset.prompts_on(device), pool_dataset.answers_length + 1, device,
+                                              nb_samples, compute, mode)
         prompts, _answers, _p_len, answers_length, _, _ = preprocessing.get_batch(
             pool_dataset, tokenizer, 0, len(pool_dataset))
         return select_samples_from_tokens(model, prompts, answers_length + 1, device, nb_samples, compute, mode)

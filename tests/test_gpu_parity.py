@@ -565,3 +565,22 @@ def test_generate_and_evaluate_run_natively(engine, dev, c2):
     model.native_compute = "fp32"
     acc32 = utils.evaluate(model, data, tok, 50, dev)
     assert 0.0 <= acc <= 1.0 and abs(acc - acc32) <= 0.03
+
+
+def test_select_samples_accepts_a_pool_tokenised_once(engine, dev, c2):
+    """TokenizedPool (tokenise once per pool instead of once per round) selects exactly what the list of pairs does."""
+    import random
+
+    from bayesformer_b200.libs import active_learning as al, preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    tok = ReversedPairingTokenizer()
+    random.seed(9)
+    pool = preprocessing.create_dataset(500, 3)
+    model = H.build_model(sd, None, False).to(dev)          # deterministic model: greedy scores are reproducible
+    want = al.select_samples(model, tok, pool, dev, nb_samples=40, compute="greedy", mode="margin")
+    tp = al.TokenizedPool(pool, tok)
+    assert al.select_samples(model, tok, tp, dev, nb_samples=40, compute="greedy", mode="margin") == want
+    assert len(tp) == 500 and tp[3] == pool[3]
+    assert al.create_new_train_set([("1+1=", "2")], tp, want[:2]) == [("1+1=", "2"), pool[want[0]], pool[want[1]]]
