@@ -714,13 +714,20 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
     gemm2_tc_kernel<FLAGS><<<grid, GTHREADS, smem, st>>>(map_a, map_w, map_c16, map_c32, map_r, g);                   \
   } while (0)
     constexpr uint32_t kPlain = EPI_OUT16_ONLY, kF = EPI_F16;
-    if (want == (kPlain | kF)) G2_LAUNCH(kPlain | kF);                                                     // QKV
-    else if (want == (kPlain | kF | EPI_RESID | EPI_STATS)) G2_LAUNCH(kPlain | kF | EPI_RESID | EPI_STATS);   // W_out
-    else if (want == (kPlain | kF | EPI_AFFINE | EPI_RELU)) G2_LAUNCH(kPlain | kF | EPI_AFFINE | EPI_RELU);   // FFN1, LN folded
-    else if (want == (kPlain | kF | EPI_BIAS | EPI_RESID | EPI_STATS)) G2_LAUNCH(kPlain | kF | EPI_BIAS | EPI_RESID | EPI_STATS);   // FFN2
-    else if (want == (kPlain | kF | EPI_BIAS | EPI_RELU)) G2_LAUNCH(kPlain | kF | EPI_BIAS | EPI_RELU);       // FFN1, unfused
-    else if (want == (kPlain | kF | EPI_BIAS)) G2_LAUNCH(kPlain | kF | EPI_BIAS);                             // FFN2, unfused
+    const uint32_t mode = want & ~kF;
+#define G2_MODE(M)                                  \
+  if (mode == (M)) {                                \
+    if (want & kF) G2_LAUNCH((M) | kF);             \
+    else G2_LAUNCH(M);                              \
+  }
+    G2_MODE(kPlain)                                              // QKV
+    else G2_MODE(kPlain | EPI_RESID | EPI_STATS)                 // W_out
+    else G2_MODE(kPlain | EPI_AFFINE | EPI_RELU)                 // FFN1, LayerNorm folded
+    else G2_MODE(kPlain | EPI_BIAS | EPI_RESID | EPI_STATS)      // FFN2 (fp16 residual stream)
+    else G2_MODE(kPlain | EPI_BIAS | EPI_RELU)                   // FFN1, unfused
+    else G2_MODE(kPlain | EPI_BIAS)                              // FFN2, unfused
     else G2_LAUNCH(EPI_DYNAMIC);
+#undef G2_MODE
 #undef G2_LAUNCH
     BFB_LAUNCH_CHECK(g.resid ? "gemm_tc_kernel[+residual,+row stats]" : g.stats_in != nullptr ? "gemm_tc_kernel[LayerNorm folded]" : "gemm_tc_kernel", st);
     return BFB200_OK;
