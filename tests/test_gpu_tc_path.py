@@ -85,13 +85,19 @@ def test_tc_path_matches_exact_path(engine, dev, P, N, B, T):
     np.testing.assert_allclose(got.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=1e-2, atol=1e-3)
 
 
-@pytest.mark.parametrize("compute,rtol,atol", [("fp16", 1e-2, 1e-4), ("bf16", 6e-2, 2e-3)])
-def test_tc_path_fused_epilogues_many_tiles_per_cluster(engine, dev, compute, rtol, atol):
+@pytest.mark.parametrize("compute,fp16_residual,rtol,atol", [("fp16", False, 1e-2, 1e-4), ("fp16", True, 1e-2, 1e-4),
+                                                             ("bf16", False, 6e-2, 2e-3)])
+def test_tc_path_fused_epilogues_many_tiles_per_cluster(engine, dev, monkeypatch, compute, fp16_residual, rtol, atol):
     """d_model 256: every product has more than 128 output columns, so the two-SM GEMM with its fused epilogues runs —
-    LayerNorm1 folded into the FFN1 product, residual + row statistics in the W_out / FFN2 epilogues (fp16: fp16
-    residual stream + ln16_apply; bf16: fp32 stream) — on enough rows (31 k) that every cluster walks several tiles
-    and the residual slots wrap around the operand ring.  F = 136 leaves a column tail in the FFN1 product."""
+    LayerNorm1 folded into the FFN1 product, residual + row statistics in the W_out epilogue (and, with
+    BFB200_TC_FP16_RESIDUAL=1, in the FFN2 epilogue + ln16_apply) — on enough rows (31 k) that every cluster walks
+    several tiles and the residual slots wrap around the operand ring.  F = 136 leaves a column tail in FFN1."""
     from bayesformer_b200.model.transformer import MyTransformer
+
+    if fp16_residual:
+        monkeypatch.setenv("BFB200_TC_FP16_RESIDUAL", "1")
+    else:
+        monkeypatch.delenv("BFB200_TC_FP16_RESIDUAL", raising=False)
 
     torch.manual_seed(11)
     model = MyTransformer(50, 256, 4, 136, 2, bayes_dropout=0.2, bayes=True).eval().to(dev)
@@ -106,7 +112,7 @@ def test_tc_path_fused_epilogues_many_tiles_per_cluster(engine, dev, compute, rt
         got = engine.mc_score_transformer(pack, prompts, N, T, "dropout", "entropy", seed=3, forced_tokens=forced,
                                           return_logp=True)
     assert "gemm_tc_kernel[LayerNorm folded]" in prof.kernels and "gemm_tc_kernel[+residual,+row stats]" in prof.kernels
-    assert ("ln16_apply_kernel" in prof.kernels) == (compute == "fp16")
+    assert ("ln16_apply_kernel" in prof.kernels) == fp16_residual
     _probs_close(got.logp.cpu().numpy(), exact.logp.cpu().numpy(), rtol, atol)
     np.testing.assert_allclose(got.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=rtol, atol=1e-3)
 
