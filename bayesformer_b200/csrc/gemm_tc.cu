@@ -157,6 +157,19 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
   }
 }
 
+// LayerNorm statistics of the output row a thread owns (row-affine epilogue): fetched BEFORE the thread waits for the
+// accumulator, so the global-memory latency hides behind the tile's MMAs.
+template <uint32_t F>
+__device__ __forceinline__ void load_row_stats(const GemmArgs& g, int row, float& r_mean, float& r_rstd) {
+  r_mean = 0.f;
+  r_rstd = 1.f;
+  if (Epi<F>::affine(g) && row < g.M) {
+    const float2 st = __ldg(g.stats_in + row);
+    r_mean = st.x * g.stats_inv_width;
+    r_rstd = rsqrtf(fmaxf(st.y * g.stats_inv_width - r_mean * r_mean, 0.f) + g.stats_eps);
+  }
+}
+
 // Epilogue of one accumulator stage for one warp: columns [c_begin, c_begin + 32 * NCH) of its 32 TMEM lanes ->
 // (+ bias)(ReLU) -> swizzled 32-row slabs -> 2-D TMA stores.  The tcgen05.ld of chunk i + 1 is in flight while chunk
 // i is converted and staged.
@@ -164,15 +177,9 @@ template <int NCH, uint32_t F = EPI_DYNAMIC, int NSLAB = 2>
 __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtensorMap* map_c16, const CUtensorMap* map_c32,
                                                  uint32_t tacc, int n_base, int row0,
                                                  int c_begin, uint8_t* my_slabs, uint32_t& slab_i, int lane,
-                                                 const uint8_t* resid_rows, int resid_row) {
+                                                 const uint8_t* resid_rows, int resid_row, float r_mean, float r_rstd) {
   constexpr uint32_t SLAB_BYTES = 32 * 128;
-  const bool affine = Epi<F>::affine(g);
-  float r_mean = 0.f, r_rstd = 1.f, st_sum = 0.f, st_sq = 0.f;
-  if (affine && row0 + lane < g.M) {   // thread = output row: its LayerNorm statistics
-    const float2 st = __ldg(g.stats_in + row0 + lane);
-    r_mean = st.x * g.stats_inv_width;
-    r_rstd = rsqrtf(fmaxf(st.y * g.stats_inv_width - r_mean * r_mean, 0.f) + g.stats_eps);
-  }
+  float st_sum = 0.f, st_sq = 0.f;
   uint32_t r[2][32];
   if (n_base + c_begin < g.N) umma::tmem_ld32(tacc + c_begin, r[0]);
 #pragma unroll
@@ -335,10 +342,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
       const int row0 = (int)(mb * GM) + q * 32;
+      float r_mean, r_rstd;
+      load_row_stats<EPI_DYNAMIC>(g, row0 + lane, r_mean, r_rstd);
       umma::mbar_wait(&acc_full[as], aph);
       umma::tc_fence_after_sync();
       epilogue_columns<BN / 64>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
-                                my_slabs, slab_i, lane, nullptr, 0);
+                                my_slabs, slab_i, lane, nullptr, 0, r_mean, r_rstd);
       umma::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -542,6 +551,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
       const int nb = (int)(tile - mb * tiles_n);
       const uint32_t as = tcount % GACC, aph = (tcount / GACC) & 1u;
       const int row0 = (int)(mb * 2 * GM) + (int)rank * GM + q * 32;
+      float r_mean, r_rstd;
+      load_row_stats<F>(g, row0 + lane, r_mean, r_rstd);
       { GT_BEGIN(); umma::mbar_wait(&acc_full[as], aph); GT_END(3); }
       umma::tc_fence_after_sync();
 #ifdef BFB_GEMM_TIMING
@@ -563,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTHREADS, 1)
         }
       }
       epilogue_columns<BN / 64, F, G2_SLABS>(g, &map_c16, &map_c32, tmem_base + lane_base + as * BN, nb * BN, row0, chalf * (BN / 2),
-                                   my_slabs, slab_i, lane, resid_rows, q * 32 + lane);
+                                   my_slabs, slab_i, lane, resid_rows, q * 32 + lane, r_mean, r_rstd);
       if (Epi<F>::resid(g)) {
         if (chalf < n_rs) {   // the four warps that read this slot hand it back to the producer
           asm volatile("bar.sync %0, 128;" ::"r"(2 + chalf) : "memory");
