@@ -339,7 +339,7 @@ def main() -> None:
         "config": workload_config(P, N, world, weights) | {
             "compute": pack.compute + (" (fused tcgen05 kernel, fp32 accumulate/residual/softmax/LayerNorm)"
                                        if pack.compute == "fp16" else " (layered CUDA-core path)"),
-            "pool_per_gpu": pool,
+            "pool_per_gpu": pool, "pool_total": pool * world,
             "l2": ("fused kernel: activations never leave the chip; per step it touches 80 MB of tokens/scores + the "
                    "29 KB embedding table, so there is no HBM-resident working set to keep warm or to flush"
                    if pack.compute == "fp16" else
