@@ -51,6 +51,7 @@ struct AttnArgs {
   const uint16_t* qkv;   // (R, 3d)
   uint16_t* out;         // (R, d)
   int64_t n_rows;        // R = n_seq * len
+  int64_t n_items;       // n_seq * n_heads (sequence, head) work items per query tile
   int len, d, n_heads, m_tile;   // this launch handles query tile m_tile of every (sequence, head)
   uint32_t fmt;
   float inv_sqrt_dh;
@@ -61,6 +62,15 @@ struct AttnArgs {
 __device__ __forceinline__ uint32_t at_pack2(float a, float b, uint32_t fmt) {
   return fmt == umma::kFmtF16 ? umma::pack_f16x2(a, b) : umma::pack_bf16x2(a, b);
 }
+
+#ifdef BFB_ATTN_TIMING
+// debug build only (make EXTRA=-DBFB_ATTN_TIMING, tools/attn_zoo.py prints it): cycles thread 0 of every CTA of the
+// 256-key variant spends up to each milestone
+__device__ unsigned long long bfb_attn_dbg[8];
+#define AT_MARK(slot) do { if (MAXKV == 256 && tid == 0) atomicAdd(&bfb_attn_dbg[slot], (unsigned long long)(clock64() - at_t0)); } while (0)
+#else
+#define AT_MARK(slot) do { } while (0)
+#endif
 
 template <int MAXKV, bool F16>
 __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
@@ -77,13 +87,13 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   __shared__ float s_max[2][AT_M], s_sum[2][AT_M];
 
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef BFB_ATTN_TIMING
+  long long at_t0 = clock64();
+#endif
   const int row = tid & (AT_M - 1), half = tid >> 7;   // warps w and w + 4 share TMEM lane quarter w & 3
-  const int h = blockIdx.x % a.n_heads;
-  const int64_t s = blockIdx.x / a.n_heads;
   const int m0 = a.m_tile * AT_M;
   const int kv_len = min(a.len, m0 + AT_M);
   const int kvp = (kv_len + 15) & ~15;
-  const int64_t row_base = s * a.len;
 
   if (warp == 0) {
     umma::tmem_alloc(&tmem_slot, MAXKV);
@@ -100,21 +110,37 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  AT_MARK(0);   // TMEM allocated, barriers initialised
 
-  if (tid == 0) {
+  // Persistent over (sequence, head) items: TMEM and the barriers are set up once per CTA, and an item's tiles are
+  // requested as soon as the previous item's PV product has released the shared memory — while that item's output is
+  // still being normalised and stored.
+  auto issue_loads = [&](int64_t item) {
+    const int hh = (int)(item % a.n_heads);
+    const int64_t rb = (item / a.n_heads) * a.len;
     const int k_boxes = (kvp + AT_M - 1) / AT_M;
     umma::mbar_expect_tx(&bar_qk, AT_Q_BYTES + (uint32_t)k_boxes * AT_M * 128u);
-    at_tma_load_2d(sQ, &map_qkv, h * AT_DH, (int)(row_base + m0), &bar_qk);
+    at_tma_load_2d(sQ, &map_qkv, hh * AT_DH, (int)(rb + m0), &bar_qk);
     for (int b = 0; b < k_boxes; ++b)
-      at_tma_load_2d(sK + b * AT_M * 128, &map_qkv, a.d + h * AT_DH, (int)(row_base + b * AT_M), &bar_qk);
+      at_tma_load_2d(sK + b * AT_M * 128, &map_qkv, a.d + hh * AT_DH, (int)(rb + b * AT_M), &bar_qk);
     umma::mbar_expect_tx(&bar_v, (uint32_t)k_boxes * AT_M * 128u);
     for (int b = 0; b < k_boxes; ++b)
-      at_tma_load_2d(sV + b * AT_M * 128, &map_qkv, 2 * a.d + h * AT_DH, (int)(row_base + b * AT_M), &bar_v);
-  }
+      at_tma_load_2d(sV + b * AT_M * 128, &map_qkv, 2 * a.d + hh * AT_DH, (int)(rb + b * AT_M), &bar_v);
+  };
+  if (tid == 0 && (int64_t)blockIdx.x < a.n_items) issue_loads(blockIdx.x);
+
+  uint32_t phase = 0;
+  for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, phase ^= 1u) {
+  const int h = (int)(item % a.n_heads);
+  const int64_t s = item / a.n_heads;
+  const int64_t row_base = s * a.len;
+#ifdef BFB_ATTN_TIMING
+  if (item != (int64_t)blockIdx.x) at_t0 = clock64();   // milestones are per item (the first one includes the set-up)
+#endif
 
   // ---- S = Q K^T ----
   if (tid == 0) {
-    umma::mbar_wait(&bar_qk, 0);
+    umma::mbar_wait(&bar_qk, phase);
     umma::tc_fence_after_sync();
     const uint64_t dq = umma::smem_desc_sw128(umma::smem_u32(sQ)), dk = umma::smem_desc_sw128(umma::smem_u32(sK));
     const uint32_t idesc = umma::instr_desc_16bit(AT_M, kvp, FMT);
@@ -122,8 +148,9 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     for (int k = 0; k < AT_DH / 16; ++k) umma::mma_bf16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
     umma::mma_commit(&bar_s);
   }
-  umma::mbar_wait(&bar_s, 0);
+  umma::mbar_wait(&bar_s, phase);
   umma::tc_fence_after_sync();
+  AT_MARK(1);   // Q / K landed and S = Q K^T complete
 
   // ---- softmax over the keys j <= query position; two threads per query row, alternating 32-key chunks ----
   // A warp's 32 rows are queries m0 + 32 w + lane and a chunk is 32 keys, so every chunk is, for the WHOLE warp,
@@ -160,6 +187,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   s_max[half][row] = mx;
   __syncthreads();
+  AT_MARK(2);   // row maxima
   mx = fmaxf(mx, s_max[half ^ 1][row]);   // finite: key 0 is visible to every query
   const float nmx = -mx * cs;
   float sm0 = 0.f, sm1 = 0.f, sm2 = 0.f, sm3 = 0.f;
@@ -200,11 +228,12 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   umma::fence_async_smem();
   umma::tc_fence_before_sync();
   __syncthreads();
+  AT_MARK(3);   // weights written
   sum += s_sum[half ^ 1][row];
 
   // ---- O = P V ----
   if (tid == 0) {
-    umma::mbar_wait(&bar_v, 0);
+    umma::mbar_wait(&bar_v, phase);
     umma::tc_fence_after_sync();
     // B = V as loaded (keys x dims): MN-major, 128-byte rows of 64 dims, 8-key groups 1024 bytes apart;
     // one K = 16 step consumes two such groups -> 2048 bytes per step
@@ -217,8 +246,10 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     }
     umma::mma_commit(&bar_o);
   }
-  umma::mbar_wait(&bar_o, 0);
+  umma::mbar_wait(&bar_o, phase);
   umma::tc_fence_after_sync();
+  AT_MARK(4);   // O = P V complete
+  if (tid == 0 && item + gridDim.x < a.n_items) issue_loads(item + gridDim.x);   // P and V are dead: next item's tiles
 
   // ---- epilogue: thread (row, half) takes output dims [32 half, 32 half + 32) ----
   {
@@ -249,7 +280,13 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     }
   }
   umma::tc_fence_before_sync();
-  __syncthreads();
+  __syncthreads();   // every O row has been read: the next item's S may overwrite the accumulator columns
+  umma::tc_fence_after_sync();
+  AT_MARK(5);   // output stored
+#ifdef BFB_ATTN_TIMING
+  if (MAXKV == 256 && tid == 0) atomicAdd(&bfb_attn_dbg[6], 1ull);
+#endif
+  }
   if (warp == 0) umma::tmem_dealloc(tmem_base, MAXKV);
 }
 
@@ -290,13 +327,18 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
   a.qkv = (const uint16_t*)qkv16; a.out = (uint16_t*)out16; a.n_rows = R;
   a.len = len; a.d = d; a.n_heads = n_heads;
   a.fmt = fmt; a.inv_sqrt_dh = 1.0f / sqrtf((float)AT_DH); a.site = site; a.ms = ms;
-  const int64_t grid = n_seq * n_heads;
-  BFB_REQUIRE(grid <= 0x7FFFFFFF, BFB200_ERR_UNSUPPORTED, "too many attention tiles in one launch");
+  a.n_items = n_seq * n_heads;
+  int dev_id = 0, sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+  if (sms <= 0) sms = 148;
   // one launch per query tile: tile 0 attends to <= 128 keys (48 KB of shared memory, 128 TMEM columns: four CTAs
   // per SM), tile 1 to <= 256 (96 KB, 256 columns: two CTAs per SM)
   const bool f16 = fmt == umma::kFmtF16;
 #define AT_LAUNCH(KV)                                                                                                   \
   do {                                                                                                                  \
+    const int64_t resident = (int64_t)sms * (KV == 128 ? 3 : 2);   /* persistent CTAs: what fits on the chip at once */ \
+    const int64_t grid = a.n_items < resident ? a.n_items : resident;                                                   \
     if (f16) {                                                                                                          \
       cudaFuncSetAttribute(attention_tc_kernel<KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtSmem<KV>::TOTAL); \
       attention_tc_kernel<KV, true><<<(unsigned)grid, 2 * AT_M, AtSmem<KV>::TOTAL, st>>>(map, a);                       \
@@ -318,6 +360,18 @@ int launch_attention_tc(const void* qkv16, void* out16, int64_t n_seq, int len, 
 }
 
 }  // namespace bfb
+
+#ifdef BFB_ATTN_TIMING
+extern "C" int bfb200_debug_attn_timing(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, bfb::bfb_attn_dbg, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(bfb::bfb_attn_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // causal multi-head attention on a packed 16-bit QKV activation: qkv (n_seq * len, 3 d) -> out (n_seq * len, d);
 // fmt 0 = fp16, 1 = bf16; heads of width 64, len <= 256.

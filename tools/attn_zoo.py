@@ -23,3 +23,16 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 flops = n_seq * 2 * 256 * 257 * 512
 print(f"attention_tc {n_seq}x{length}x{heads}: {ms:.3f} ms per layer, {flops / ms / 1e9:.1f} TFLOP/s causal-algorithmic")
+
+# with a -DBFB_ATTN_TIMING build: average cycles of a 256-key CTA up to each milestone
+import ctypes as C
+from bayesformer_b200 import _lib
+lib = _lib.load()
+if hasattr(lib, "bfb200_debug_attn_timing"):
+    out = (C.c_ulonglong * 8)()
+    lib.bfb200_debug_attn_timing(out, 1)
+    engine.attention_tc(qkv, n_seq, length, heads)
+    lib.bfb200_debug_attn_timing(out, 1)
+    n = max(1, out[6])
+    names = ["TMEM + barriers ready", "Q/K landed, S = QK^T done", "row maxima", "weights written", "O = PV done", "output stored"]
+    print("256-key CTA, average cycles since CTA start:", ", ".join(f"{nm} {out[i] / n:.0f}" for i, nm in enumerate(names)))
