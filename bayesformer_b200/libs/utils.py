@@ -8,6 +8,8 @@ forward via `MyTransformer.forward`.
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -55,7 +57,7 @@ class _GraphedTrainStep:
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for _ in range(2):
                 optimizer.zero_grad(set_to_none=True)
                 step()
         torch.cuda.current_stream(device).wait_stream(side)
@@ -82,6 +84,29 @@ class _GraphedTrainStep:
         return self.loss
 
 
+# model -> (capturable AdamW, {batch shape: graph}, parameter identity).  Captured steps are reused by later `train` calls
+# on the same model (every active-learning round fine-tunes it again): a fresh call only resets the optimizer state in
+# place (zero moments, step 0 — what a new `torch.optim.AdamW` would start from) and sets the learning rate.
+_GRAPH_STATE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _graph_state(model, lr: float, criterion, device):
+    ident = tuple((p.data_ptr(), tuple(p.shape)) for p in model.parameters()) + (str(torch.device(device)),)
+    state = _GRAPH_STATE.get(model)
+    if state is None or state[2] != ident:
+        optimizer = torch.optim.AdamW(model.parameters(), lr=torch.tensor(float(lr), device=device), capturable=True)
+        state = _GRAPH_STATE[model] = (optimizer, {}, ident)
+    optimizer, graphs, _ = state
+    with torch.no_grad():
+        for group in optimizer.param_groups:
+            group["lr"].fill_(float(lr))
+        for st in optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+    return optimizer, graphs
+
+
 def _graphs_enabled(device) -> bool:
     import os
 
@@ -97,19 +122,26 @@ def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, ba
     BFB200_GRAPH_TRAIN=0 for the plain eager loop) and the batch losses are summed on the device, read once per epoch.
     """
     use_graphs = _graphs_enabled(device)
-    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, capturable=True) if use_graphs else \
-        torch.optim.AdamW(model.parameters(), lr=lr)
     criterion = nn.CrossEntropyLoss()
+    if use_graphs:
+        optimizer, graphs = _graph_state(model, lr, criterion, device)
+    else:
+        optimizer, graphs = torch.optim.AdamW(model.parameters(), lr=lr), {}
     history_train, history_valid = [], []
     best = float("inf")
-    graphs: dict[tuple[int, int, int], _GraphedTrainStep] = {}
+    batches: dict[int, tuple] = {}
     for epoch in range(1, nb_epochs + 1):
         model.train()
         running = 0.0
         running_dev = torch.zeros((), device=device) if use_graphs else None
         for start in range(0, len(train_dataset) - 1, batch_size):
             if use_graphs:
-                prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
+                # the reference walks the same slices in the same order every epoch (no shuffling, :60): each batch is
+                # tokenised and copied to the device once per call
+                if start not in batches:
+                    prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
+                    batches[start] = (prompts.to(device), answers.to(device), p_len, a_len)
+                prompts, answers, p_len, a_len = batches[start]
                 key = (p_len, a_len, prompts.shape[1])
                 if key not in graphs:
                     graphs[key] = _GraphedTrainStep(model, optimizer, criterion, p_len, a_len, prompts.shape[1], vocab_size,
