@@ -475,6 +475,38 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
         del small, pk, pr
     except Exception as exc:
         out["char_level_c1_mc_score"] = {"error": repr(exc)}
+    # The strongest EXISTING way to run this path on the same GPU: the reference's algorithm as it is
+    # written — T x N full eager forwards of the nn.Module stack, ~165 PyTorch kernels each — on this B200.  The
+    # reference itself cannot be imported on the box; `MyTransformer._module_forward` is the same eager arithmetic
+    # (it is the training path of the drop-in module), driven by the loop of `dropout_uncertainty`
+    # (active_learning.py:141-155) restated here.  A reported baseline, like cpu_baseline.
+    try:
+        model, _ = build_model()
+        model = model.to(dev)
+        n_items = 100_000
+        pr = torch.from_numpy(synthetic_addition_prompts(n_items, SEED)).to(dev)
+
+        def eager_pass():
+            with torch.no_grad():
+                acc = torch.zeros(5, n_items, device=dev)
+                for _draw in range(T_MC):
+                    seq = pr
+                    for j in range(5):
+                        logp = model._module_forward(seq)[-1]
+                        probs = torch.softmax(logp, dim=-1)
+                        top2 = torch.sort(probs, dim=-1, descending=True).values
+                        acc[j] += top2[:, 0] - top2[:, 1]
+                        seq = torch.cat((seq, torch.argmax(logp, dim=-1).view(1, -1)), 0)
+                scores = (acc / T_MC).mean(0)
+                return torch.topk(scores, K_TOP).indices
+
+        ms = timed(eager_pass, reps=2)
+        out["eager_torch_same_gpu"] = {"pool_items": n_items, "ms": ms, "pool_samples_per_s": n_items / (ms * 1e-3),
+                                       "note": "reference algorithm as written (T x N eager nn.Module forwards, margin, "
+                                               "top-k) on this GPU; reported baseline, not the product path"}
+        del model, pr
+    except Exception as exc:
+        out["eager_torch_same_gpu"] = {"error": repr(exc)}
     # toy classifier, SURVEY C2i
     from bayesformer_b200.model.bayesian_classification import MLP
     torch.manual_seed(SEED)
