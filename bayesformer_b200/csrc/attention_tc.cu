@@ -33,12 +33,32 @@ constexpr uint32_t AT_Q_BYTES = AT_M * 128;
 // shared memory of the variant that attends to at most MAXKV keys (128: the first query tile of a sequence, four
 // CTAs per SM; 256: the second tile, two CTAs per SM):  [ P slabs over Q | K ][ V ]
 template <int MAXKV> struct AtSmem {
+  // The 256-key variant keeps the softmax weights P in TENSOR memory (A operand of the PV product read from TMEM,
+  // "TS" form of tcgen05.mma) and needs no P region; the 128-key variant writes P over the dead Q / K tiles.
+  static constexpr bool TS = MAXKV == 256;
   static constexpr uint32_t K_BYTES = MAXKV * 128;
   static constexpr uint32_t V_BYTES = MAXKV * 128;                   // keys x 64 dims as delivered by TMA
-  static constexpr uint32_t P_BYTES = (MAXKV / 64) * AT_M * 128;     // slabs of 128 rows x 64 keys
+  static constexpr uint32_t P_BYTES = TS ? AT_Q_BYTES + K_BYTES : (MAXKV / 64) * AT_M * 128;   // slabs of 128 rows x 64 keys
   static constexpr uint32_t TOTAL = 1024 + P_BYTES + V_BYTES;
   static_assert(P_BYTES >= AT_Q_BYTES + K_BYTES, "P must cover the Q and K tiles it overwrites");
 };
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit, two elements per 32-bit column, lane = row) comes from tensor memory
+__device__ __forceinline__ void at_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void at_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 
 __device__ __forceinline__ void at_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -115,7 +135,10 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   // Persistent over (sequence, head) items: TMEM and the barriers are set up once per CTA, and an item's tiles are
   // requested as soon as the previous item's PV product has released the shared memory — while that item's output is
   // still being normalised and stored.
-  auto issue_loads = [&](int64_t item) {
+  constexpr bool TS = AtSmem<MAXKV>::TS;
+  constexpr uint32_t o_col = TS ? MAXKV / 4 : 0;   // first accumulator column of O
+  constexpr int HK = MAXKV / 2;   // TS: thread `half` of a row owns the CONTIGUOUS keys [half HK, half HK + HK)
+  auto issue_qk = [&](int64_t item) {
     const int hh = (int)(item % a.n_heads);
     const int64_t rb = (item / a.n_heads) * a.len;
     const int k_boxes = (kvp + AT_M - 1) / AT_M;
@@ -123,10 +146,16 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     at_tma_load_2d(sQ, &map_qkv, hh * AT_DH, (int)(rb + m0), &bar_qk);
     for (int b = 0; b < k_boxes; ++b)
       at_tma_load_2d(sK + b * AT_M * 128, &map_qkv, a.d + hh * AT_DH, (int)(rb + b * AT_M), &bar_qk);
+  };
+  auto issue_v = [&](int64_t item) {
+    const int hh = (int)(item % a.n_heads);
+    const int64_t rb = (item / a.n_heads) * a.len;
+    const int k_boxes = (kvp + AT_M - 1) / AT_M;
     umma::mbar_expect_tx(&bar_v, (uint32_t)k_boxes * AT_M * 128u);
     for (int b = 0; b < k_boxes; ++b)
       at_tma_load_2d(sV + b * AT_M * 128, &map_qkv, 2 * a.d + hh * AT_DH, (int)(rb + b * AT_M), &bar_v);
   };
+  auto issue_loads = [&](int64_t item) { issue_qk(item); issue_v(item); };
   if (tid == 0 && (int64_t)blockIdx.x < a.n_items) issue_loads(blockIdx.x);
 
   uint32_t phase = 0;
@@ -151,6 +180,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   umma::mbar_wait(&bar_s, phase);
   umma::tc_fence_after_sync();
   AT_MARK(1);   // Q / K landed and S = Q K^T complete
+  if (TS && tid == 0 && item + gridDim.x < a.n_items) issue_qk(item + gridDim.x);   // Q / K tiles are dead already
 
   // ---- softmax over the keys j <= query position; two threads per query row, alternating 32-key chunks ----
   // A warp's 32 rows are queries m0 + 32 w + lane and a chunk is 32 keys, so every chunk is, for the WHOLE warp,
@@ -164,7 +194,10 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   const int warp_first = m0 + (warp & 3) * 32;   // first query row of this warp = its diagonal chunk
   const float cs = a.inv_sqrt_dh * 1.4426950408889634f;   // scores / sqrt(dh), as a base-2 exponent
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-  for (int c0 = 32 * half; c0 <= warp_first && c0 < kvp; c0 += 64) {
+  const int c_begin = TS ? half * HK : 32 * half;            // first chunk of this thread
+  const int c_end = TS ? min(kvp, half * HK + HK) : kvp;     // one past its last key
+  const int c_step = TS ? 32 : 64;
+  for (int c0 = c_begin; c0 <= warp_first && c0 < c_end; c0 += c_step) {
     uint32_t r[32];
     umma::tmem_ld32(tmem_base + lane_base + c0, r);
     umma::tmem_ld_wait();
@@ -191,7 +224,7 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
   mx = fmaxf(mx, s_max[half ^ 1][row]);   // finite: key 0 is visible to every query
   const float nmx = -mx * cs;
   float sm0 = 0.f, sm1 = 0.f, sm2 = 0.f, sm3 = 0.f;
-  for (int c0 = 32 * half; c0 < kvp; c0 += 64) {
+  for (int c0 = c_begin; c0 < c_end; c0 += c_step) {
     float e[32];
     if (c0 <= warp_first) {
       uint32_t r[32];
@@ -213,19 +246,30 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
 #pragma unroll
       for (int i = 0; i < 32; ++i) e[i] = 0.f;
     }
-    uint8_t* slab = sP + (c0 >> 6) * (AT_M * 128);
-    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+    if constexpr (TS) {
+      // P stays in tensor memory: the 32 weights of this chunk, packed two per column, go to the 16 columns
+      // half HK + (c0 - half HK) / 2 — inside the S columns this very thread has already consumed (its own chunks
+      // up to the current one), so neither thread of a row can overwrite a score the other still has to read
+      uint32_t pk[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 w;
-      w.x = at_pack2(e[8 * c], e[8 * c + 1], FMT); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], FMT);
-      w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], FMT); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], FMT);
-      *reinterpret_cast<uint4*>(slab + umma::sw128_offset(row, ch0 + c)) = w;
+      for (int i = 0; i < 16; ++i) pk[i] = at_pack2(e[2 * i], e[2 * i + 1], FMT);
+      at_tmem_st16(tmem_base + lane_base + (uint32_t)(half * HK + ((c0 - half * HK) >> 1)), pk);
+    } else {
+      uint8_t* slab = sP + (c0 >> 6) * (AT_M * 128);
+      const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 w;
+        w.x = at_pack2(e[8 * c], e[8 * c + 1], FMT); w.y = at_pack2(e[8 * c + 2], e[8 * c + 3], FMT);
+        w.z = at_pack2(e[8 * c + 4], e[8 * c + 5], FMT); w.w = at_pack2(e[8 * c + 6], e[8 * c + 7], FMT);
+        *reinterpret_cast<uint4*>(slab + umma::sw128_offset(row, ch0 + c)) = w;
+      }
     }
   }
   float sum = (sm0 + sm1) + (sm2 + sm3);
   s_sum[half][row] = sum;
-  umma::fence_async_smem();
+  if constexpr (TS) umma::tmem_st_wait();
+  else umma::fence_async_smem();
   umma::tc_fence_before_sync();
   __syncthreads();
   AT_MARK(3);   // weights written
@@ -240,21 +284,32 @@ __global__ void __launch_bounds__(2 * AT_M, MAXKV == 128 ? 3 : 2) attention_tc_k
     const uint32_t idesc = umma::instr_desc_16bit(AT_M, AT_DH, FMT) | (1u << 16);
     const uint32_t pP = umma::smem_u32(sP), pV = umma::smem_u32(sV);
     for (int ks = 0; ks < kvp / 16; ++ks) {
-      const uint64_t dp = umma::smem_desc_sw128(pP + (ks >> 2) * (AT_M * 128) + (ks & 3) * 32);
       const uint64_t dv = umma::smem_desc_sw128(pV + ks * 2048);
-      umma::mma_bf16_ss(tmem_base, dp, dv, idesc, ks > 0);
+      if constexpr (TS) {
+        // 16 keys = 8 packed columns of P; keys [HK, 2 HK) start at column HK.  O accumulates into the 64 columns
+        // [HK / 2, HK / 2 + 64): scores of the first thread's later chunks, all consumed
+        const int k0 = 16 * ks;
+        const uint32_t pa = tmem_base + (uint32_t)(k0 < HK ? k0 >> 1 : HK + ((k0 - HK) >> 1));
+        at_mma_ts(tmem_base + o_col, pa, dv, idesc, ks > 0);
+      } else {
+        const uint64_t dp = umma::smem_desc_sw128(pP + (ks >> 2) * (AT_M * 128) + (ks & 3) * 32);
+        umma::mma_bf16_ss(tmem_base, dp, dv, idesc, ks > 0);
+      }
     }
     umma::mma_commit(&bar_o);
   }
   umma::mbar_wait(&bar_o, phase);
   umma::tc_fence_after_sync();
   AT_MARK(4);   // O = P V complete
-  if (tid == 0 && item + gridDim.x < a.n_items) issue_loads(item + gridDim.x);   // P and V are dead: next item's tiles
+  if (tid == 0 && item + gridDim.x < a.n_items) {   // V (and, in the 128-key variant, P over Q / K) is dead: next item's tiles
+    if (TS) issue_v(item + gridDim.x);
+    else issue_loads(item + gridDim.x);
+  }
 
   // ---- epilogue: thread (row, half) takes output dims [32 half, 32 half + 32) ----
   {
     uint32_t r0[32];
-    umma::tmem_ld32(tmem_base + lane_base + 32 * half, r0);
+    umma::tmem_ld32(tmem_base + lane_base + o_col + 32 * half, r0);
     umma::tmem_ld_wait();
     if (q_ok) {
       const float inv = 1.0f / sum;
