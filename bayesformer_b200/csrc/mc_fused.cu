@@ -511,11 +511,13 @@ __device__ __forceinline__ void fused_issue_product(uint32_t tiles_u32, int a_se
 // BayesFormer, or none for the standard Transformer; Philox masks, greedy decoding, no log-prob / forced-token side
 // channels): the latent-site, mask-injection, sampling and side-channel branches are compiled out instead of tested
 // at run time.
-template <int MAXLEN, int FAST>   // 0: everything at run time; 1: sites E + layer-out (BayesFormer); 2: no site (Transformer)
+template <int MAXLEN, int FAST>   // 0: everything at run time; 1: sites E + layer-out (BayesFormer); 2: no site (Transformer);
+                                  // 3: no site, temperature sampling (Transformer, sampling_uncertainty)
 __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a_in) {
   FusedArgs a = a_in;
   if (FAST) {
     a.site_flags = FAST == 1 ? (BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) : 0u;
+    a.scheme = FAST == 3 ? BFB200_SCHEME_SAMPLING : a.scheme;
     a.ms.bits = nullptr;
     a.logp_out = nullptr;
     a.forced = nullptr;
@@ -927,8 +929,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     umma::group_sync(bar_id, FGROUP_THREADS);
 
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
-    if (a.tps == 16) score_phase<16, FAST != 0>(a, stage, stage_stride, gt, nseq, s0, len);
-    else             score_phase<8, FAST != 0>(a, stage, stage_stride, gt, nseq, s0, len);
+    if (a.tps == 16) score_phase<16, FAST == 1 || FAST == 2>(a, stage, stage_stride, gt, nseq, s0, len);
+    else             score_phase<8, FAST == 1 || FAST == 2>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
   }
 
@@ -1043,8 +1045,11 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  const bool plain = a.ms.bits == nullptr && a.logp_out == nullptr && a.forced == nullptr && scheme != BFB200_SCHEME_SAMPLING;
-  const int fast = !plain ? 0 : a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT) ? 1 : a.site_flags == 0u ? 2 : 0;
+  const bool plain = a.ms.bits == nullptr && a.logp_out == nullptr && a.forced == nullptr;
+  const bool sampling = scheme == BFB200_SCHEME_SAMPLING;
+  const int fast = !plain ? 0
+                   : (!sampling && a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT)) ? 1
+                   : (a.site_flags == 0u) ? (sampling ? 3 : 2) : 0;
 #define FUSED_LAUNCH_F(ML, FV)                                                                              \
   do {                                                                                                      \
     cudaFuncSetAttribute(mc_forward_kernel<ML, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1054,6 +1059,7 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   do {                                    \
     if (fast == 1) FUSED_LAUNCH_F(ML, 1); \
     else if (fast == 2) FUSED_LAUNCH_F(ML, 2); \
+    else if (fast == 3) FUSED_LAUNCH_F(ML, 3); \
     else FUSED_LAUNCH_F(ML, 0);           \
   } while (0)
   // the pair phase keeps a sequence's K and V rows in registers: one instantiation per length up to 8 (the decode steps

@@ -389,9 +389,10 @@ def test_specialised_kernels_equal_the_generic_kernel_bit_for_bit(engine, dev, c
     pack = model.native_pack(dev, "fp16")
     for P, N in ((4, 5), (2, 3), (11, 4), (20, 3)):
         prompts = torch.randint(0, 114, (P, 77), generator=torch.Generator().manual_seed(P)).to(dev)
-        scheme, T = ("dropout", 6) if bayes else ("greedy", 1)
-        for mode in H.MODES:
-            fast = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True)
-            slow = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True, return_logp=True)
-            assert torch.equal(fast.step_scores, slow.step_scores)
-            assert torch.equal(fast.tokens, slow.tokens)
+        for scheme, T in ((("dropout", 6),) if bayes else (("greedy", 1), ("sampling", 4))):
+            for mode in H.MODES:
+                fast = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True)
+                slow = engine.mc_score_transformer(pack, prompts, N, T, scheme, mode, seed=123, return_tokens=True,
+                                                   return_logp=True)
+                assert torch.equal(fast.step_scores, slow.step_scores)
+                assert torch.equal(fast.tokens, slow.tokens)
