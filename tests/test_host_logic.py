@@ -234,3 +234,27 @@ def test_vectorised_char_pool_tokenisation_is_bit_identical():
         few = preprocessing.get_batch(pool, tok, 10, 20)
         sp, _ = preprocessing.pad(tok, [tok.encode(p) for p, _ in pool[10:30]], "prompts")
         assert torch.equal(few[0], torch.tensor(sp, dtype=torch.int64).t())
+
+
+def test_weight_image_signature_tracks_versions_sites_and_explicit_marks():
+    """The packed / 16-bit weight images are keyed on every parameter's (data_ptr, _version), the dropout-site
+    configuration and an explicit generation counter (graph replays of an optimizer step update weights without
+    touching `_version`: utils.train bumps the counter)."""
+    from bayesformer_b200 import engine
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(0)
+    m = MyTransformer(20, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True)
+    dev = torch.device("cpu")
+    s0 = engine._param_signature(m, dev)
+    assert engine._param_signature(m, dev) == s0
+    with torch.no_grad():
+        m.linear_out.bias.add_(1.0)                     # in-place update through the dispatcher bumps _version
+    s1 = engine._param_signature(m, dev)
+    assert s1 != s0
+    engine.mark_weights_changed(m)                       # an update behind autograd's back
+    s2 = engine._param_signature(m, dev)
+    assert s2 != s1
+    for layer in m.layers:
+        layer.ff.bayes_dropout = 0.3                     # a latent dropout site switched on (in every layer)
+    assert engine._param_signature(m, dev) != s2
