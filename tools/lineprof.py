@@ -16,6 +16,8 @@ hdr = rows[start + 1]
 body = [dict(zip(hdr, r)) for r in rows[start + 2:end] if len(r) == len(hdr)]
 # nvdisasm with line info
 out = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.splitlines()
+# "kernel<(int)8, (int)1>" -> "kernelILi8ELi1EE"; MANGLED=... overrides
+mangled = __import__("os").environ.get("MANGLED") or ksub.replace("<(int)", "ILi").replace(", (int)", "ELi").replace(">", "EE")
 fn = None; line = None; file = None; seq = []
 for l in out:
     if l.startswith(".text."):
@@ -23,7 +25,7 @@ for l in out:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         file, line = m.group(1).split("/")[-1], int(m.group(2)); continue
-    if re.match(r"\s+/\*[0-9a-f]+\*/", l) and fn and ksub.replace("<(int)", "ILi").replace(">", "E") in fn:
+    if re.match(r"\s+/\*[0-9a-f]+\*/", l) and fn and mangled in fn:
         seq.append((file, line, l.split("*/")[1].strip()))
 print("ncu sass rows", len(body), "nvdisasm rows", len(seq), file=sys.stderr)
 n = min(len(body), len(seq))
