@@ -28,6 +28,18 @@ def stats(prompts, N, T, seed):
     d = (a - b)[keep]
     p, q = np.exp(a), np.exp(b)
     ratio = np.abs(p - q) / (1e-2 * q + 1e-4)
+    if os.environ.get("ROWS"):   # per-row view: is the tail a few bad rows (amplification) or spread out?
+        dd = np.where(keep, a - b, 0.0)                      # (steps, sequences, classes)
+        row_rms = np.sqrt((dd * dd).mean(axis=2))
+        qs = np.quantile(row_rms, [0.5, 0.9, 0.99, 0.999, 1.0])
+        print("   per-row rms dlogp quantiles 50/90/99/99.9/100 %:", " ".join(f"{x:.2e}" for x in qs))
+        flat = np.argsort(row_rms, axis=None)[::-1][:6]
+        for f in flat:
+            st, sq = np.unravel_index(f, row_rms.shape)
+            top = np.sort(q[st, sq])[::-1][:3]
+            ent = -(q[st, sq] * np.log(q[st, sq] + 1e-30)).sum()
+            print(f"   worst row: step {st} seq {sq} (item {sq // T}, draw {sq % T}) row rms {row_rms[st, sq]:.2e} "
+                  f"max |dlogp| {np.abs(dd[st, sq]).max():.2e} top-3 p {top.round(3)} entropy {ent:.2f}")
     return np.sqrt(np.mean(d * d)), np.abs(d).max(), ratio.max(), np.sqrt(np.mean(ratio * ratio))
 
 
