@@ -353,6 +353,49 @@ def test_sharded_selection_equals_single_device_selection(engine, dev, c2):
     assert torch.equal(got, want)
 
 
+def test_full_size_pool_properties(engine, dev, c2):
+    """BASELINE configs[1] at its full size (100,000 pool items, T = 20, N = 5 decode steps, margin and max scores),
+    through properties that need no oracle run: a re-run is bit-identical, eight shards with their global index bases
+    reproduce the unsharded scores bit for bit and acquire the same 200 items, scores stay in their range, the
+    acquired list is sorted (descending score, ties by lowest index) and holds the 200 largest scores."""
+    import random
+
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    random.seed(42)
+    pool = preprocessing.create_dataset(100000, 3)
+    X, _, P, A, _, _ = preprocessing.get_batch(pool, ReversedPairingTokenizer(), 0, len(pool))
+    X = X.to(dev)
+    n, k, T, seed, G = X.shape[1], 200, 20, 42, 8
+    assert n == 100000
+    model = H.build_model(sd, float(z["p"]), True).to(dev)
+    pack = engine.scoring_pack(model, dev, P, A + 1)
+    for mode in ("margin", "max"):
+        whole = engine.mc_score_transformer(pack, X, A + 1, T, "dropout", mode, seed=seed).pool_scores
+        again = engine.mc_score_transformer(pack, X, A + 1, T, "dropout", mode, seed=seed).pool_scores
+        assert torch.equal(whole, again)
+        assert bool(torch.isfinite(whole).all()) and float(whole.min()) >= 0.0 and float(whole.max()) <= 1.0
+        vals, idx = engine.unpack_keys(engine.topk_keys(whole, k))
+        v, i = vals.cpu().numpy(), idx.cpu().numpy()
+        assert len(set(i.tolist())) == k
+        assert all(v[j] > v[j + 1] or (v[j] == v[j + 1] and i[j] < i[j + 1]) for j in range(k - 1))
+        np.testing.assert_array_equal(v, whole[idx].cpu().numpy())
+        rest = whole.clone()
+        rest[idx] = -1.0
+        assert float(rest.max()) <= float(v[-1])
+        keys = []
+        for g in range(G):
+            lo, hi = n * g // G, n * (g + 1) // G
+            part = engine.mc_score_transformer(pack, X[:, lo:hi].contiguous(), A + 1, T, "dropout", mode, seed=seed,
+                                               index_base=lo).pool_scores
+            assert torch.equal(part, whole[lo:hi])
+            keys.append(engine.topk_keys(part, k, index_base=lo))
+        _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
+        assert torch.equal(got, idx)
+
+
 def test_select_samples_on_a_char_level_pool_runs_the_fused_kernel(engine, dev):
     """SURVEY C1 through the unchanged list-of-pairs API: 32-character windows + 4-character continuations under a
     character tokenizer (V = 67), MC-dropout entropy acquisition — tokenised by the vectorised char encoder, scored by
