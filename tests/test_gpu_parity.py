@@ -156,6 +156,37 @@ def test_mlp_mc_golden_masks(engine, dev):
     np.testing.assert_allclose(out.mean_of_scores.cpu().numpy(), want["mean_of_scores"].numpy(), rtol=1e-3, atol=1e-5)
 
 
+def test_mlp_full_size_pool_properties(engine, dev):
+    """BASELINE configs[2] size for the classifier (1,000,000 items, T = 20), through properties that hold at any size:
+    a re-run is bit-identical, eight shards with global index bases reproduce the unsharded draws bit for bit and
+    acquire the same items, the predictive mean is the mean of the draws, and the two-class scores follow
+    compute_uncertainty (active_learning.py:26-31) applied to [1 - p, p]."""
+    z = H.load("classifiers.npz")
+    w = [torch.from_numpy(z["mlp.sd." + k]).to(dev) for k in
+         ("hidden_layer.weight", "hidden_layer.bias", "output_layer.weight", "output_layer.bias")]
+    n, T, p, seed, G, k = 1000000, 20, 0.5, 42, 8, 200
+    x = (torch.randn(n, 2, generator=torch.Generator().manual_seed(42)) * 0.8).to(dev)
+    full = engine.mlp_mc_score(x, *w, p, T, seed=seed)
+    again = engine.mlp_mc_score(x, *w, p, T, seed=seed)
+    assert torch.equal(full.probs, again.probs) and torch.equal(full.mean_of_scores, again.mean_of_scores)
+    assert float(full.probs.min()) >= 0.0 and float(full.probs.max()) <= 1.0
+    pm = full.probs.double().mean(0)
+    assert float((full.mean_p.double() - pm).abs().max()) < 1e-6
+    two = torch.stack([1.0 - pm, pm], dim=1)
+    want = torch.stack([two.max(1).values, (two[:, 0] - two[:, 1]).abs(), -(two * (two + 1e-10).log()).sum(1)])
+    assert float((full.score_of_mean.double() - want).abs().max()) < 2e-6
+    keys = []
+    for g in range(G):
+        lo, hi = n * g // G, n * (g + 1) // G
+        part = engine.mlp_mc_score(x[lo:hi], *w, p, T, seed=seed, index_base=lo)
+        assert torch.equal(part.probs, full.probs[:, lo:hi])
+        assert torch.equal(part.mean_of_scores, full.mean_of_scores[:, lo:hi])
+        keys.append(engine.topk_keys(part.mean_of_scores[1].contiguous(), k, index_base=lo))
+    _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
+    _, idx = engine.unpack_keys(engine.topk_keys(full.mean_of_scores[1].contiguous(), k))
+    assert torch.equal(got, idx)
+
+
 def test_mlp_mc_philox_matches_oracle_and_is_shard_invariant(engine, dev):
     z = H.load("classifiers.npz")
     w_cpu = [torch.from_numpy(z["mlp.sd." + k]) for k in
