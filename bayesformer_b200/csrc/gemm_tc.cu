@@ -65,8 +65,8 @@ struct GemmArgs {
   // fused epilogues of the tensor-core transformer path (launch_gemm_tc_ex):
   int resid;               // two-SM kernel: out16 = acc (+ bias) + R16, a 16-bit matrix shaped like the output whose tiles the
                            // TMA producer streams through the operand ring (map_r)
-  float2* stats_out;       // with resid: per-row (sum, sum of squares) of the fp32 result, accumulated atomically
-  const float2* stats_in;  // row-affine mode: out = rstd_r * (acc - mean_r * col_s[n]) + col_c[n], (mean, rstd) from the
+  RowStats* stats_out;     // with resid: per-row (sum, sum of squares) of the fp32 result, accumulated atomically
+  const RowStats* stats_in;  // row-affine mode: out = rstd_r * (acc - mean_r * col_s[n]) + col_c[n], (mean, rstd) from the
   const float* col_s;      //   (sum, sum of squares) of a row of `stats_width` values — LayerNorm folded into this product
   const float* col_c;
   float stats_inv_width, stats_eps;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void load_row_stats(const GemmArgs& g, int row, float
   r_mean = 0.f;
   r_rstd = 1.f;
   if (Epi<F>::affine(g) && row < g.M) {
-    const float2 st = __ldg(g.stats_in + row);
+    const float2 st = row_stats_load(g.stats_in + row);
     r_mean = st.x * g.stats_inv_width;
     r_rstd = rsqrtf(fmaxf(st.y * g.stats_inv_width - r_mean * r_mean, 0.f) + g.stats_eps);
   }
@@ -246,8 +246,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmArgs& g, const CUtens
     }
   }
   if (Epi<F>::resid(g) && Epi<F>::stats(g) && row0 + lane < g.M) {
-    atomicAdd(&g.stats_out[row0 + lane].x, st_sum);
-    atomicAdd(&g.stats_out[row0 + lane].y, st_sq);
+    row_stats_add(&g.stats_out[row0 + lane], st_sum, st_sq);
   }
 }
 

@@ -25,7 +25,7 @@ struct Workspace {
   uint16_t* att16;  // (R, d) attention output, then LayerNorm1 output
   uint16_t* h16;    // (R, F)
   float* x2;        // (R, d) next block input
-  float2* stats;    // (R) per-row (sum, sum of squares) of LayerNorm1's input
+  RowStats* stats;  // (R) per-row (sum, sum of squares) of a LayerNorm's input, fixed point (kernels.cuh)
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -78,7 +78,7 @@ static size_t workspace_bytes(const bfb200_transformer& m, int64_t n_seq, int ma
   if (use_tc(m)) {
     const size_t Vp = (size_t)logits_pitch(m);
     return 256 + align256((size_t)n_seq * max_len * sizeof(int32_t)) + 3 * align256(R * d * 4) +
-           2 * align256(R * d * 2) + align256(R * 3 * d * 2) + align256(R * F * 2) + align256(R * 8) +
+           2 * align256(R * d * 2) + align256(R * 3 * d * 2) + align256(R * F * 2) + align256(R * sizeof(RowStats)) +
            align256((full_logits ? R : (size_t)n_seq) * Vp * 4) + align256((size_t)n_seq * 4);
   }
   size_t b = 256;
@@ -113,7 +113,7 @@ static Workspace carve(void* base, const bfb200_transformer& m, int64_t n_seq, i
     w.att16 = (uint16_t*)take(R * d * 2);
     w.qkv16 = (uint16_t*)take(R * 3 * d * 2);
     w.h16 = (uint16_t*)take(R * F * 2);
-    w.stats = (float2*)take(R * 8);
+    w.stats = (RowStats*)take(R * sizeof(RowStats));
     w.logits = (float*)take((full_logits ? R : (size_t)n_seq) * Vp * 4);
     w.seq_scores = (float*)take((size_t)n_seq * 4);
     w.att = w.x1 = w.qkv = w.h = nullptr;
@@ -243,7 +243,7 @@ static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t 
       // running as a kernel.  W_out's epilogue adds the block input (its 16-bit copy), writes v = x + attn W_out^T
       // as the next A operand and accumulates each row's sum / sum of squares; the FFN1 product runs on v with
       // W1 * gamma1 and its epilogue applies rstd (acc - mean col_s) + col_c, ReLU.
-      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(float2), st);
+      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(RowStats), st);
       BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
       GemmFusion add;
       add.resid16 = ws.x16; add.resid_pitch = d; add.stats_out = ws.stats;
@@ -265,7 +265,7 @@ static int forward_chunk_tc(const bfb200_transformer& m, Workspace& ws, int64_t 
     if (lite) {
       // v2 = x + FFN(LN1(v1)) (both residuals start from the BLOCK INPUT x, transformer.py:231-233) and its row
       // statistics come out of the FFN2 product; LayerNorm2 + layer-out dropout is a 16-bit read-modify-write
-      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(float2), st);
+      const cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)R * sizeof(RowStats), st);
       BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
       GemmFusion add;
       add.resid16 = ws.x16; add.resid_pitch = d; add.stats_out = ws.stats;

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256, 4) resid_ln16_kernel(const float* __restr
 // added the residual) also accumulated each row's sum and sum of squares (launch_gemm_tc_ex), so this kernel is one
 // 16-bit read and one 16-bit write per element (transformer.py:233, :370).  One warp per row.
 template <int NJ, bool F16>
-__global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restrict__ v16, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restrict__ v16, const RowStats* __restrict__ stats,
                                                          uint16_t* __restrict__ out16, int64_t n_rows, int len, int d,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float eps, MaskSource ms, int out_site) {
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restr
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
     const RowKey rk = make_row_key(ms, (uint32_t)r, (uint32_t)len);
-    const float2 st = __ldg(stats + r);
+    const float2 st = row_stats_load(stats + r);
     const float mean = st.x * inv_d;
     const float rstd = rsqrtf(fmaxf(st.y * inv_d - mean * mean, 0.f) + eps);
 #pragma unroll
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) ln16_apply_kernel(const uint16_t* __restr
   }
 }
 
-int launch_ln16_apply(const void* v16, const float2* stats, void* out16, int64_t n_rows, int len, int d, const float* gamma,
+int launch_ln16_apply(const void* v16, const RowStats* stats, void* out16, int64_t n_rows, int len, int d, const float* gamma,
                       const float* beta, float eps, const MaskSource& ms, int out_site, uint32_t fmt, cudaStream_t st) {
   BFB_REQUIRE((d & 7) == 0 && d <= 2048, BFB200_ERR_UNSUPPORTED, "ln16_apply needs d_model %% 8 == 0 and <= 2048 (got %d)", d);
   BFB_REQUIRE(n_rows < 0x7FFFFFFFLL, BFB200_ERR_UNSUPPORTED, "more than 2^31 token rows in one chunk");

@@ -155,3 +155,30 @@ def test_auto_picks_the_tensor_core_path_for_width_64_heads(engine, dev):
     pack = engine.scoring_pack(big, dev, 256, 1, "auto")
     assert pack.compute == "fp16" and pack.path == 2
     assert engine.scoring_pack(big, dev, 300, 1, "auto").compute == "fp32"
+
+
+def test_scaled_c4_full_size_properties(engine, dev):
+    """BASELINE configs[3] per-GPU size (8,192 items x 50 draws x 256 tokens, d = 512, F = 2048, 6 layers, entropy
+    score), through properties that need no oracle run: two shards with their global index bases reproduce the
+    unsharded scores bit for bit (whatever the chunking) and acquire the same 200 items; scores lie in [0, ln V]."""
+    import math
+
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(4)
+    V, B, T, k = 114, 8192, 50, 200
+    model = MyTransformer(V, 512, 8, 2048, 6, bayes_dropout=0.3, bayes=True).eval().to(dev)
+    prompts = torch.randint(0, V, (256, B), generator=torch.Generator().manual_seed(4)).to(dev)
+    pack = engine.scoring_pack(model, dev, 256, 1, "auto")
+    assert pack.path == 2
+    whole = engine.mc_score_transformer(pack, prompts, 1, T, "dropout", "entropy", seed=42).pool_scores
+    assert bool(torch.isfinite(whole).all()) and float(whole.min()) >= 0.0 and float(whole.max()) <= math.log(V) + 1e-4
+    keys = []
+    for lo, hi in ((0, 3000), (3000, B)):
+        part = engine.mc_score_transformer(pack, prompts[:, lo:hi].contiguous(), 1, T, "dropout", "entropy", seed=42,
+                                           index_base=lo).pool_scores
+        assert torch.equal(part, whole[lo:hi])
+        keys.append(engine.topk_keys(part, k, index_base=lo))
+    _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
+    _, want = engine.unpack_keys(engine.topk_keys(whole, k))
+    assert torch.equal(got, want)
