@@ -396,6 +396,34 @@ def test_full_size_pool_properties(engine, dev, c2):
         assert torch.equal(got, idx)
 
 
+def test_char_level_full_size_pool_properties(engine, dev):
+    """BASELINE configs[0] size (10,000 windows of 32 characters, 5 decode steps, T = 20, entropy; V = 67): the
+    long-sequence variant of the fused kernel is deterministic and invariant to sharding, bit for bit."""
+    import math
+
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(67)
+    model = MyTransformer(67, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval().to(dev)
+    n, k = 10000, 200
+    prompts = torch.randint(0, 65, (32, n), generator=torch.Generator().manual_seed(6)).to(dev)
+    pack = engine.scoring_pack(model, dev, 32, 5, "auto")
+    assert pack.compute == "fp16"
+    whole = engine.mc_score_transformer(pack, prompts, 5, 20, "dropout", "entropy", seed=42).pool_scores
+    again = engine.mc_score_transformer(pack, prompts, 5, 20, "dropout", "entropy", seed=42).pool_scores
+    assert torch.equal(whole, again)
+    assert bool(torch.isfinite(whole).all()) and float(whole.min()) >= 0.0 and float(whole.max()) <= math.log(67) + 1e-4
+    keys = []
+    for lo, hi in ((0, 1), (1, 2500), (2500, 7777), (7777, n)):
+        part = engine.mc_score_transformer(pack, prompts[:, lo:hi].contiguous(), 5, 20, "dropout", "entropy", seed=42,
+                                           index_base=lo).pool_scores
+        assert torch.equal(part, whole[lo:hi])
+        keys.append(engine.topk_keys(part, min(k, hi - lo), index_base=lo))
+    _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
+    _, want = engine.unpack_keys(engine.topk_keys(whole, k))
+    assert torch.equal(got, want)
+
+
 def test_select_samples_on_a_char_level_pool_runs_the_fused_kernel(engine, dev):
     """SURVEY C1 through the unchanged list-of-pairs API: 32-character windows + 4-character continuations under a
     character tokenizer (V = 67), MC-dropout entropy acquisition — tokenised by the vectorised char encoder, scored by
