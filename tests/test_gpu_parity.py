@@ -212,6 +212,25 @@ def test_vmlp_mc_golden(engine, dev):
     np.testing.assert_allclose(out.mean_p.cpu().numpy(), z["vmlp.mean"], rtol=1e-3, atol=1e-5)
 
 
+def test_vmlp_full_size_is_shard_invariant(engine, dev):
+    """VariationalMLP at 1,000,000 items: every shard uses the same weight draws (bayesian_classification.py:76 samples
+    once per call for the whole batch), so shards reproduce the unsharded probabilities bit for bit."""
+    z = H.load("classifiers.npz")
+    args = [torch.from_numpy(z["vmlp.sd." + k]).to(dev) for k in
+            ("hidden_layer.w_mu", "hidden_layer.w_rho", "hidden_layer.b_mu", "output_layer.w_mu",
+             "output_layer.w_rho", "output_layer.b_mu")]
+    eps = torch.from_numpy(z["vmlp.eps"]).to(dev)
+    n = 1000000
+    x = (torch.randn(n, 2, generator=torch.Generator().manual_seed(7)) * 0.8).to(dev)
+    full = engine.vmlp_mc_score(x, *args, eps)
+    assert torch.equal(full.probs, engine.vmlp_mc_score(x, *args, eps).probs)
+    assert float(full.probs.min()) >= 0.0 and float(full.probs.max()) <= 1.0
+    assert float((full.mean_p.double() - full.probs.double().mean(0)).abs().max()) < 1e-6
+    for lo, hi in ((0, 333333), (333333, 333334), (333334, n)):
+        part = engine.vmlp_mc_score(x[lo:hi], *args, eps)
+        assert torch.equal(part.probs, full.probs[:, lo:hi]) and torch.equal(part.mean_p, full.mean_p[lo:hi])
+
+
 def test_classifier_modules_route_to_native(engine, dev):
     from bayesformer_b200.model.bayesian_classification import MLP
 
