@@ -396,6 +396,34 @@ def test_full_size_pool_properties(engine, dev, c2):
         assert torch.equal(got, idx)
 
 
+def test_full_size_greedy_and_sampling_are_shard_invariant(engine, dev, c2):
+    """The standard Transformer's two schemes (greedy_uncertainty, sampling_uncertainty: active_learning.py:38-115) on the
+    100,000-item pool: deterministic, and shards with global index bases reproduce the unsharded scores bit for bit
+    (sampling draws its uniforms from the Philox stream keyed by the global item index)."""
+    import random
+
+    from bayesformer_b200.libs import preprocessing
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+
+    z, sd = c2
+    random.seed(43)
+    pool = preprocessing.create_dataset(100000, 3)
+    X, _, P, A, _, _ = preprocessing.get_batch(pool, ReversedPairingTokenizer(), 0, len(pool))
+    X = X.to(dev)
+    n = X.shape[1]
+    model = H.build_model(sd, None, False).to(dev)
+    pack = engine.scoring_pack(model, dev, P, A + 1)
+    for scheme, T, kw in (("greedy", 1, {}), ("sampling", 20, {"temperature": 0.8})):
+        whole = engine.mc_score_transformer(pack, X, A + 1, T, scheme, "entropy", seed=7, **kw).pool_scores
+        again = engine.mc_score_transformer(pack, X, A + 1, T, scheme, "entropy", seed=7, **kw).pool_scores
+        assert torch.equal(whole, again)
+        assert bool(torch.isfinite(whole).all()) and float(whole.min()) >= 0.0
+        for lo, hi in ((0, 12345), (12345, 70001), (70001, n)):
+            part = engine.mc_score_transformer(pack, X[:, lo:hi].contiguous(), A + 1, T, scheme, "entropy", seed=7,
+                                               index_base=lo, **kw).pool_scores
+            assert torch.equal(part, whole[lo:hi])
+
+
 def test_char_level_full_size_pool_properties(engine, dev):
     """BASELINE configs[0] size (10,000 windows of 32 characters, 5 decode steps, T = 20, entropy; V = 67): the
     long-sequence variant of the fused kernel is deterministic and invariant to sharding, bit for bit."""
