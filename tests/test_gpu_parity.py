@@ -91,6 +91,41 @@ def test_acquire_matches_oracle(engine, dev, is_logp, shape):
     np.testing.assert_allclose(got.mean_of_scores.cpu().numpy(), want["mean_of_scores"].numpy(), rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("is_logp", [False, True])
+def test_acquire_full_size_properties(engine, dev, is_logp):
+    """(T, B, C) = (20, 100000, 114) — one decode step of BASELINE configs[1]: tile-aligned slices of the pool reproduce the
+    whole reduction bit for bit, arbitrary slices to rounding, the predictive mean is a distribution, scores stay in range, and the torch expression of
+    compute_uncertainty (active_learning.py:26-31) on the device agrees."""
+    import math
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    T, B, Cn = 20, 100000, 114
+    logp = torch.log_softmax(torch.randn(T, B, Cn, generator=g, device=dev) * 2.0, -1)
+    x = logp if is_logp else logp.exp()
+    whole = engine.acquire(x, is_logp=is_logp)
+    assert float((whole.mean_p.sum(-1) - 1.0).abs().max()) < 1e-5
+    p = logp.exp()
+    ent = -(p * (p + 1e-10).log()).sum(-1).mean(0)
+    top2 = p.topk(2, dim=-1).values
+    want = torch.stack([top2[..., 0].mean(0), (top2[..., 0] - top2[..., 1]).mean(0), ent])
+    assert float((whole.mean_of_scores - want).abs().max()) < 2e-5
+    assert float(whole.mean_of_scores[2].max()) <= math.log(Cn) + 1e-4 and float(whole.mean_of_scores.min()) >= 0.0
+    # slices that start on a 128-item tile boundary: bit for bit
+    for lo, hi in ((0, 768), (768, 50048), (50048, B)):
+        part = engine.acquire(x[:, lo:hi].contiguous(), is_logp=is_logp)
+        assert torch.equal(part.mean_of_scores, whole.mean_of_scores[:, lo:hi])
+        assert torch.equal(part.mean_p, whole.mean_p[lo:hi])
+        assert torch.equal(part.score_of_mean, whole.score_of_mean[:, lo:hi])
+    # any other slice: the class sums of an item are taken in an order that depends on its place in the tile (the
+    # bank-conflict-free rotation of the staged rows) or by the warp-per-item tail kernel — equal to rounding only
+    # (DESIGN.md section 10; the scoring paths reduce per sequence and ARE slice-invariant bit for bit)
+    for lo, hi in ((0, 777), (777, 50001), (50001, B)):
+        part = engine.acquire(x[:, lo:hi].contiguous(), is_logp=is_logp)
+        assert float((part.mean_of_scores - whole.mean_of_scores[:, lo:hi]).abs().max()) < 2e-6
+        assert float((part.mean_p - whole.mean_p[lo:hi]).abs().max()) < 1e-7
+        assert float((part.score_of_mean - whole.score_of_mean[:, lo:hi]).abs().max()) < 2e-6
+
+
 # ----------------------------------------------------------------------------------------------
 # top-k: bit-exact
 # ----------------------------------------------------------------------------------------------
