@@ -182,3 +182,23 @@ def test_scaled_c4_full_size_properties(engine, dev):
     _, got = engine.unpack_keys(engine.merge_topk_keys(torch.cat(keys), k))
     _, want = engine.unpack_keys(engine.topk_keys(whole, k))
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "fp16", "bf16"])
+def test_layered_paths_are_deterministic_and_shard_invariant(engine, dev, compute):
+    """A model outside the fused kernel's class (d = 128, two heads of width 64) on a 20,000-item pool: the layered
+    fp32 path and the layered tensor-core path are deterministic and reproduce the unsharded scores bit for bit from
+    shards with their global index bases (chunk boundaries, GEMM tile tails and acquisition differ between the runs)."""
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    torch.manual_seed(12)
+    model = MyTransformer(50, 128, 2, 72, 2, bayes_dropout=0.2, bayes=True).eval().to(dev)
+    n = 20000
+    prompts = torch.randint(0, 50, (12, n), generator=torch.Generator().manual_seed(12)).to(dev)
+    pack = model.native_pack(dev, compute)
+    whole = engine.mc_score_transformer(pack, prompts, 3, 10, "dropout", "margin", seed=5).pool_scores
+    assert torch.equal(whole, engine.mc_score_transformer(pack, prompts, 3, 10, "dropout", "margin", seed=5).pool_scores)
+    for lo, hi in ((0, 4097), (4097, 13000), (13000, n)):
+        part = engine.mc_score_transformer(pack, prompts[:, lo:hi].contiguous(), 3, 10, "dropout", "margin", seed=5,
+                                           index_base=lo).pool_scores
+        assert torch.equal(part, whole[lo:hi])
