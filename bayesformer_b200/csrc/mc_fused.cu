@@ -1,22 +1,35 @@
-// Fused MC-forward kernel for the notebook-default model class (d_model = 64, 8 heads of 8, F <= 64,
-// V <= 128, sequences of at most 40 tokens): ONE kernel runs the whole forward pass of a decode step —
-// embedding + MC dropout + positional encoding, every TransformerBlock (QKV / W_out / FFN contractions on
-// tcgen05 tensor cores with fp16 operands and fp32 TMEM accumulators, causal attention, both
-// residual + LayerNorm pairs, the always-on dropout sites), the last-position vocabulary head, log-softmax,
-// the per-draw uncertainty score and the next token — with every activation resident on chip.
+// Fused MC-forward kernel for the notebook-default model class (d_model = 64, 8 heads of 8, small F, V <= 128):
+// ONE kernel runs the whole forward pass of a decode step — embedding + MC dropout + positional encoding, every
+// TransformerBlock (QKV / W_out / FFN contractions on tcgen05 tensor cores, fp32 TMEM accumulators, causal attention,
+// both residual + LayerNorm pairs, the always-on dropout sites), the last-position vocabulary head, log-softmax, the
+// per-draw uncertainty score and the next token — with every activation resident on chip.
 //
-// Layout.  A CTA holds the complete fp16 weight image (pre-swizzled by fused_pack_kernel, fetched with 1-D
-// bulk TMA copies) in shared memory and runs two independent 128-thread groups.  A group owns a tile of
-// floor(128 / len) whole sequences = up to 128 token rows:
-//   * row phases    — thread = token row: reads its fp32 accumulator row from TMEM (tcgen05.ld 32x32b), does
-//                     bias / ReLU / residual / LayerNorm / dropout in registers, writes the next operand row as
-//                     fp16 into the 128-byte-swizzled K-major tile the next tcgen05.mma consumes;
-//   * pair phase    — thread = (sequence, head) (or (query, sequence, head) beyond 16 tokens): causal softmax(QK^T / sqrt(dh)) V from the
-//                     fp16 Q/K/V tiles (a head's 8 values are exactly one 16-byte swizzle chunk);
-//   * score phase   — 4 or 8 threads per sequence: log-softmax over the vocabulary, probabilities, max /
+// Layout.  A CTA holds the fp16 weight image (pre-swizzled by fused_pack_kernel, fetched with 1-D bulk TMA copies) in
+// shared memory and runs two independent 256-thread groups.  A group owns a tile of floor(128 / len) whole sequences
+// = up to 128 token rows, two threads per row (32 features each):
+//   * row phases    — read the fp32 accumulator row from TMEM (tcgen05.ld 32x32b), do bias / ReLU / residual /
+//                     LayerNorm / dropout in registers and leave the next product's A operand IN TENSOR MEMORY
+//                     (tcgen05.st; the "TS" form of tcgen05.mma reads it from there) as fp16 hi + lo parts;
+//   * pair phase    — thread = (sequence, head[, query subset]): causal softmax(QK^T / sqrt(dh)) V from the fp16
+//                     Q / K / V tiles in shared memory (a head's 8 values are exactly one 16-byte swizzle chunk);
+//   * score phase   — 8 or 16 threads per sequence: log-softmax over the vocabulary, probabilities, max /
 //                     margin / entropy, greedy arg-max or inverse-CDF sample.
-// The residual stream x stays in fp32 in 64 TMEM columns of the group.  HBM traffic per sequence and step:
-// len token ids in, one score and one token out.
+//
+// Precision (the 16-bit class with margin; tools/emulate_fused_rounding.py).  The tensor pipe is
+// idle most of the time here, so operands whose fp16 rounding matters are given as TWO fp16 numbers, hi + lo, and
+// multiplied twice into the same fp32 accumulator:
+//   - the residual stream x lives in TMEM as fp16 hi + lo (64 columns, 2^-22 relative): it is at once the residual and
+//     the A operand of the QKV, FFN1 and vocabulary-head products;
+//   - the FFN hidden row and the attention output likewise; W_qkv and W2 have a lo image too (W_qkv's is streamed per
+//     layer from L2 into the dead V tiles by bulk copies);
+//   - Q, K and V reach the pair phase as fp16 + an 8-bit (e5m2) remainder; the score and PV products take the cross
+//     terms with packed-half FMAs (the remainders' products need no fp32 accumulation).
+// What stays single fp16: W_out, W1, the vocabulary head's weights.
+//
+// With the reference's default dropout sites W_out and FFN1 are ONE product (`merged`): FFN1(LN1(v)), v = x + attn W_out^T,
+// needs v only through its row statistics and through v (W1 g1)^T = x (W1 g1)^T + attn ((W1 g1) W_out)^T.
+//
+// HBM traffic per sequence and step: len token ids in, one score and one token out.
 //
 // Reference arithmetic: src/model/transformer.py:349-375 (forward), :211-234 (block), :37-65 (head),
 // :151-170 (FFN); src/libs/active_learning.py:62-68 / :103-112 / :146-152 (per-step scoring).
@@ -35,53 +48,82 @@ constexpr int FROWS = 128;      // token rows per group tile (UMMA M)
 constexpr int FGROUPS = 2;      // independent groups per CTA, one tile of 128 token rows each
 constexpr int FGROUP_THREADS = 256;   // two threads per token row (32 features each)
 constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
-constexpr int FMAXLEN = 40;     // longest sequence the fused path takes (rows of the positional table in the image)
+constexpr int FMAXLEN = 40;     // longest sequence the fused path takes
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
-constexpr int PARAMS_PER_LAYER = 8 * 64;      // ln1_w, ln1_b, b1, b2, ln2_w, ln2_b, col_s, col_c (floats)
+// shared-memory tiles of a group: Q (then the attention output), K, the 8-bit remainders of Q and K, V (between the
+// pair phases: landing zone of the next QKV product's W_lo rows)
+constexpr int T_Q = 0, T_K = 1, T_L = 2, T_V = 3, FTILES = 4;
+constexpr uint32_t VLO_BYTES = FROWS * FD;    // per group: V's 8-bit remainders (then landing zone of W_qkv's lo V rows)
+constexpr uint32_t WLO_QK_BYTES = 2 * FD * 128, WLO_V_BYTES = FD * 128;   // lo image of one layer's W_qkv: Q and K rows, V rows
+constexpr uint32_t WLO_BYTES = WLO_QK_BYTES + WLO_V_BYTES;
+constexpr uint32_t HEAD_BYTES = FMAXV * 128;  // vocabulary head: streamed per tile into the dead Q tile
+// TMEM columns of a group's 256-column window
+constexpr uint32_t C_XHI = 0, C_XLO = 32, C_ACC = 64;
+constexpr size_t kFusedSmemMax = 227 * 1024;
+constexpr uint32_t kBarrierBytes = 64;
+constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)FGROUPS * VLO_BYTES;
 
 struct FusedLayout {
   uint32_t fp;            // F rounded up to 16
-  uint32_t vp;            // V rounded up to 16
-  uint32_t layer_bytes;   // matrices of one layer
-  uint32_t off_out, off_w1, off_w2;  // inside a layer (qkv at 0)
-  uint32_t off_head;      // absolute
-  uint32_t off_params;    // absolute
-  uint32_t image_bytes;   // multiple of 1024
+  uint32_t merged;        // W_out + FFN1 as one product (no dropout site between attention and FFN1)
+  uint32_t om_rows;       // rows of the [W_out ; (W1 g1) W_out] slot: 64 (+ fp when merged)
+  uint32_t layer_bytes;   // per layer: W_qkv | [W_out ; M] | W1
+  uint32_t off_om, off_w1;  // inside a layer (qkv at 0)
+  uint32_t off_w2;        // absolute: tiles of 64 rows x 128 bytes; a layer's K = fp columns sit at K offset (l % w2_per_tile) * fp,
+  uint32_t w2_per_tile;   //   their lo parts 32 columns further (fp <= 32; wider FFNs have no W2 lo part)
+  uint32_t w2_lo;
+  uint32_t off_params;    // absolute: fp32 vectors, params_per_layer floats per layer
+  uint32_t params_per_layer;
+  uint32_t smem_image_bytes;   // what the kernel keeps in shared memory
+  uint32_t off_head;      // absolute (global memory only from here on): vocabulary head, HEAD_BYTES
+  uint32_t off_wlo;       // absolute: n_layers x WLO_BYTES
+  uint32_t total_bytes;
 };
 
-__host__ __device__ inline FusedLayout fused_layout(int L, int F, int V) {
+// parameter vectors of a layer (floats from the layer's base): merged flow b2, ln2_w, ln2_b, col_s, col_c;
+// otherwise b2, ln2_w, ln2_b, ln1_w, ln1_b, b1
+constexpr uint32_t P_B2 = 0, P_LN2W = 64, P_LN2B = 128, P_COLS = 192, P_LN1W = 192, P_LN1B = 256, P_B1 = 320;
+
+__host__ __device__ inline FusedLayout fused_layout(int L, int F, uint32_t site_flags) {
   FusedLayout lay;
   lay.fp = (uint32_t)((F + 15) / 16 * 16);
-  lay.vp = FMAXV;   // the head product always spans 128 classes; classes >= V carry zero weights and bias -inf
-  lay.off_out = 3 * FD * 128;
-  lay.off_w1 = lay.off_out + FD * 128;
-  lay.off_w2 = lay.off_w1 + lay.fp * 128;
-  lay.layer_bytes = lay.off_w2 + FD * 128;
-  lay.off_head = (uint32_t)L * lay.layer_bytes;
-  lay.off_params = lay.off_head + lay.vp * 128;
-  const uint32_t n_param_floats = (uint32_t)L * PARAMS_PER_LAYER + FMAXV + FMAXLEN * FD;
-  lay.image_bytes = (lay.off_params + n_param_floats * 4 + 1023u) & ~1023u;
+  lay.merged = (site_flags & (BFB200_SITE_ATTN_RESID | BFB200_SITE_FFN_IN)) ? 0u : 1u;
+  lay.om_rows = FD + (lay.merged ? lay.fp : 0u);
+  lay.off_om = 3 * FD * 128;
+  lay.off_w1 = lay.off_om + lay.om_rows * 128;
+  lay.layer_bytes = lay.off_w1 + lay.fp * 128;
+  lay.off_w2 = (uint32_t)L * lay.layer_bytes;
+  lay.w2_lo = lay.fp <= 32u ? 1u : 0u;
+  lay.w2_per_tile = lay.w2_lo ? 32u / lay.fp : 1u;
+  const uint32_t w2_tiles = ((uint32_t)L + lay.w2_per_tile - 1) / lay.w2_per_tile;
+  lay.off_params = lay.off_w2 + w2_tiles * (FD * 128);
+  lay.params_per_layer = lay.merged ? P_COLS + 2 * lay.fp : P_B1 + lay.fp;
+  lay.smem_image_bytes = (lay.off_params + (uint32_t)L * lay.params_per_layer * 4 + 15u) & ~15u;
+  lay.off_head = (lay.smem_image_bytes + 1023u) & ~1023u;
+  lay.off_wlo = lay.off_head + HEAD_BYTES;
+  lay.total_bytes = lay.off_wlo + (uint32_t)L * WLO_BYTES;
   return lay;
 }
 
-constexpr size_t kFusedStaticSlack = 4608;  // static __shared__ of the kernel (LayerNorm exchange 4 KB, barriers)
-
-inline size_t fused_smem_bytes(const FusedLayout& lay) {
-  return 1024 + (size_t)lay.image_bytes + (size_t)FGROUPS * 3 * TILE_BYTES;
+inline size_t fused_smem_bytes(const FusedLayout& lay) {   // tiles + image + barriers, before the alignment pad
+  return (size_t)kTilesBytes + lay.smem_image_bytes + kBarrierBytes;
 }
 
 // ------------------------------------------------------------------------------------------
-// weight image: fp16 matrices in the swizzled K-major layout + fp32 vectors
+// weight image: fp16 matrices in the swizzled K-major layout + fp32 vectors (+ the global-only W_lo part)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sat16(float w) { return fminf(fmaxf(w, -65504.f), 65504.f); }
+__device__ __forceinline__ float round16(float w) { return __half2float(__float2half_rn(sat16(w))); }
+
 __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t* __restrict__ image) {
   const int L = m.n_layers, F = m.d_ff, V = m.ntoken;
-  const int per_layer = 3 * FD * FD + FD * FD + F * FD + FD * F;
-  // LayerNorm1 is folded into the FFN1 product unless a dropout site sits between them (mc_forward_kernel): the W1
-  // slot then holds W1 * diag(gamma1)
-  const bool fold_ln1 = !(m.site_flags & BFB200_SITE_FFN_IN);
+  const bool merged = lay.merged != 0;
+  // element counts per layer: W_qkv, W_out, M (merged), W1, W2, W_qkv lo
+  const int n_qkv = 3 * FD * FD, n_out = FD * FD, n_m = merged ? F * FD : 0, n_w1 = F * FD, n_w2 = FD * F, n_lo = 3 * FD * FD;
+  const int per_layer = n_qkv + n_out + n_m + n_w1 + n_w2 + n_lo;
   const int n_mat = L * per_layer + V * FD;
-  const int n_par = L * PARAMS_PER_LAYER + FMAXV + FMAXLEN * FD;
+  const int n_par = L * (int)lay.params_per_layer;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mat + n_par; i += gridDim.x * blockDim.x) {
     if (i < n_mat) {
       float w;
@@ -90,55 +132,60 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
         const int l = i / per_layer;
         int j = i - l * per_layer;
         base = (uint32_t)l * lay.layer_bytes;
-        if (j < 3 * FD * FD) {                       // W_qkv (3d, d)
-          n = j / FD; k = j % FD; w = m.w_qkv[(size_t)l * 3 * FD * FD + j];
-        } else if ((j -= 3 * FD * FD) < FD * FD) {   // W_out (d, d)
-          n = j / FD; k = j % FD; w = m.w_out[(size_t)l * FD * FD + j]; base += lay.off_out;
-        } else if ((j -= FD * FD) < F * FD) {        // FFN W1 (F, d)
-          n = j / FD; k = j % FD; w = m.ff1_w[(size_t)l * F * FD + j]; base += lay.off_w1;
-          if (fold_ln1) w *= m.ln1_w[l * FD + k];
-        } else {                                     // FFN W2 (d, F): K = F
-          j -= F * FD;
-          n = j / F; k = j % F; w = m.ff2_w[(size_t)l * FD * F + j]; base += lay.off_w2;
+        if (j < n_qkv) {                             // W_qkv (3d, d)
+          n = j / FD; k = j % FD; w = m.w_qkv[(size_t)l * n_qkv + j];
+        } else if ((j -= n_qkv) < n_out) {           // W_out (d, d)
+          n = j / FD; k = j % FD; w = m.w_out[(size_t)l * n_out + j]; base += lay.off_om;
+        } else if ((j -= n_out) < n_m) {             // M = fp16(W1 g1) W_out (F, d): the attention rows' share of the
+          n = j / FD; k = j % FD;                    // merged product, right behind W_out (rows 64 .. 64 + F)
+          w = 0.f;
+          for (int q = 0; q < FD; ++q)
+            w = fmaf(round16(m.ff1_w[((size_t)l * F + n) * FD + q] * m.ln1_w[l * FD + q]), m.w_out[((size_t)l * FD + q) * FD + k], w);
+          n += FD; base += lay.off_om;
+        } else if ((j -= n_m) < n_w1) {              // FFN W1 (F, d), times gamma1 when LayerNorm1 is folded into it
+          n = j / FD; k = j % FD; w = m.ff1_w[(size_t)l * n_w1 + j]; base += lay.off_w1;
+          if (merged) w *= m.ln1_w[l * FD + k];
+        } else if ((j -= n_w1) < n_w2) {             // FFN W2 (d, F): K = F, layer l at K offset (l % w2_per_tile) * fp,
+          n = j / F; k = j % F + (l % lay.w2_per_tile) * lay.fp; w = m.ff2_w[(size_t)l * n_w2 + j];   // lo part 32 further
+          base = lay.off_w2 + (uint32_t)(l / lay.w2_per_tile) * (FD * 128);
+          if (lay.w2_lo) {
+            const uint32_t off_lo = base + umma::sw128_offset(n, (k + 32u) >> 3) + (k & 7u) * 2u;
+            *reinterpret_cast<__half*>(image + off_lo) = __float2half_rn(sat16(w - round16(w)));
+          }
+        } else {                                     // lo parts of W_qkv (global memory only): Q and K rows, then the V rows
+          j -= n_w2;                                 // as a tile of their own (they land in different shared-memory tiles)
+          n = j / FD; k = j % FD;
+          const float full = m.w_qkv[(size_t)l * n_qkv + j];
+          w = full - round16(full);
+          base = lay.off_wlo + (uint32_t)l * WLO_BYTES;
+          if (n >= 2u * FD) { n -= 2u * FD; base += WLO_QK_BYTES; }
         }
       } else {                                       // vocabulary head (V, d)
         const int j = i - L * per_layer;
         n = j / FD; k = j % FD; w = m.head_w[j]; base = lay.off_head;
       }
       const uint32_t off = base + umma::sw128_offset(n, k >> 3) + (k & 7u) * 2u;
-      *reinterpret_cast<__half*>(image + off) = __float2half_rn(fminf(fmaxf(w, -65504.f), 65504.f));
+      *reinterpret_cast<__half*>(image + off) = __float2half_rn(sat16(w));
     } else {
       const int j = i - n_mat;
+      const int l = j / (int)lay.params_per_layer, q = j % (int)lay.params_per_layer;
       float v = 0.f;
-      if (j < L * PARAMS_PER_LAYER) {
-        const int l = j / PARAMS_PER_LAYER, q = j % PARAMS_PER_LAYER, which = q >> 6, c = q & 63;
-        switch (which) {
-          case 0: v = m.ln1_w[l * FD + c]; break;
-          case 1: v = m.ln1_b[l * FD + c]; break;
-          case 2: v = c < F ? m.ff1_b[l * F + c] : 0.f; break;
-          case 3: v = m.ff2_b[l * FD + c]; break;
-          case 4: v = m.ln2_w[l * FD + c]; break;
-          case 5: v = m.ln2_b[l * FD + c]; break;
-          case 6:    // col_s[n] = sum_k fp16(W1[n, k] gamma1[k]) — of the rounded values the tensor core multiplies
-            if (c < F)
-              for (int k = 0; k < FD; ++k)
-                v += __half2float(__float2half_rn(fminf(fmaxf(m.ff1_w[((size_t)l * F + c) * FD + k] * m.ln1_w[l * FD + k], -65504.f), 65504.f)));
-            break;
-          default:   // col_c[n] = b1[n] + sum_k W1[n, k] beta1[k]
-            if (c < F) {
-              v = m.ff1_b[l * F + c];
-              for (int k = 0; k < FD; ++k) v = fmaf(m.ff1_w[((size_t)l * F + c) * FD + k], m.ln1_b[l * FD + k], v);
-            }
-            break;
+      if (q < (int)P_LN2W) v = m.ff2_b[l * FD + q];
+      else if (q < (int)P_LN2B) v = m.ln2_w[l * FD + q - P_LN2W];
+      else if (q < (int)P_COLS) v = m.ln2_b[l * FD + q - P_LN2B];
+      else if (merged) {
+        const int c = (q - (int)P_COLS) % (int)lay.fp;
+        if (c < F) {
+          if (q < (int)(P_COLS + lay.fp)) {   // col_s[n] = sum_k fp16(W1[n, k] g1[k]) — of the rounded values the tensor core multiplies
+            for (int k = 0; k < FD; ++k) v += round16(m.ff1_w[((size_t)l * F + c) * FD + k] * m.ln1_w[l * FD + k]);
+          } else {                            // col_c[n] = b1[n] + sum_k W1[n, k] beta1[k]
+            v = m.ff1_b[l * F + c];
+            for (int k = 0; k < FD; ++k) v = fmaf(m.ff1_w[((size_t)l * F + c) * FD + k], m.ln1_b[l * FD + k], v);
+          }
         }
-      } else if (j < L * PARAMS_PER_LAYER + FMAXV) {
-        const int c = j - L * PARAMS_PER_LAYER;
-        v = c < V ? m.head_b[c] : -INFINITY;   // padded classes vanish from every softmax
-      } else {
-        const int q = j - L * PARAMS_PER_LAYER - FMAXV;  // pe[pos][c], pos < FMAXLEN
-        const int pos = q >> 6;
-        v = pos < m.pe_len ? m.pe[(size_t)pos * FD + (q & 63)] : 0.f;
-      }
+      } else if (q < (int)P_LN1B) v = m.ln1_w[l * FD + q - P_LN1W];
+      else if (q < (int)P_B1) v = m.ln1_b[l * FD + q - P_LN1B];
+      else v = (q - (int)P_B1) < F ? m.ff1_b[l * F + q - P_B1] : 0.f;
       reinterpret_cast<float*>(image + lay.off_params)[j] = v;
     }
   }
@@ -150,14 +197,17 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
 struct FusedArgs {
   const uint8_t* image;
   const float* embedding;      // (V, 64) fp32
+  const float* pe;             // (pe_len, 64) fp32
+  const float* head_b;         // (V) fp32
   FusedLayout lay;
   int n_layers, d_ff, vocab;
   uint32_t site_flags;
   float ln_eps;
+  uint32_t smem_bytes;         // dynamic shared memory of the launch
   // this launch
   int len;                     // tokens per sequence in this step
   int spt;                     // sequences per tile = 128 / len
-  int tps;                     // score-phase threads per sequence (4 or 8)
+  int tps;                     // score-phase threads per sequence (8 or 16)
   uint32_t qsplit;             // pair phase with two threads per (sequence, head): bit t = which of them takes query t
   int64_t n_seq;               // sequences in the chunk
   int64_t n_tiles;
@@ -188,10 +238,8 @@ __device__ __forceinline__ RowRng make_row_rng(const MaskSource& m, uint32_t s) 
 }
 
 // 32 keep bits of one half row from the Philox stream: features [8 * c3_call, 8 * c3_call + 32) of the (row, site)
-// encoded in (c2, c3): four calls of eight 16-bit decisions each.  Deliberately NOT inlined: the seven dropout
-// sites of the kernel share this one copy of the rounds (the kernel is instruction-fetch sensitive); arguments are
-// scalars so nothing spills to local memory at the call; the four counters advance together so the rounds of
-// independent streams interleave.
+// encoded in (c2, c3): four calls of eight 16-bit decisions each.  Deliberately NOT inlined: the dropout
+// sites of the generic instantiation share this one copy of the rounds (the kernel is instruction-fetch sensitive).
 __device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, uint32_t threshold, uint32_t item,
                                                uint32_t draw, uint32_t c2, uint32_t c3) {
   const uint2 key = make_uint2(key_x, key_y);
@@ -203,14 +251,14 @@ __device__ __noinline__ uint32_t philox_keep32(uint32_t key_x, uint32_t key_y, u
          (keep8_of(r3, threshold) << 24);
 }
 
-
 using umma::fh_ll;
 using umma::fh_hh;
 using umma::fh_lh;
 using umma::fh_hl;
 
-__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b) {
-  float d = fh_ll(a.x, b.x, 0.f);
+// d + a . b over the 8 fp16 values of two packed words (fp32 accumulation; products of halves are exact)
+__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b, float d) {
+  d = fh_ll(a.x, b.x, d);
   d = fh_hh(a.x, b.x, d);
   d = fh_ll(a.y, b.y, d);
   d = fh_hh(a.y, b.y, d);
@@ -219,16 +267,62 @@ __device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b) {
   d = fh_ll(a.w, b.w, d);
   return fh_hh(a.w, b.w, d);
 }
-// o[0..8) += p * v[0..8), p = half `HI` of pp
+// the 8-bit remainders of a Q or K head row (8 bytes) as packed fp16
+__device__ __forceinline__ uint4 widen_lo8(const uint2& w) {
+  return make_uint4(umma::e5m2x4_to_f16x2_lo(w.x), umma::e5m2x4_to_f16x2_hi(w.x), umma::e5m2x4_to_f16x2_lo(w.y),
+                    umma::e5m2x4_to_f16x2_hi(w.y));
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+constexpr uint32_t kOneOne = 0x3C003C00u;   // (1.0h, 1.0h)
+// q . k with q = qh + ql, k = kh + kl (fp16 + 8-bit remainders): qh . kh with fp32 accumulation, the cross terms
+// ql . kh + qh . kl (2^-11 of the result) as packed-half FMAs; the ql . kl term is below 2^-22 of |q||k|.  The clamp
+// keeps an overflowing cross term (|q||k| beyond 1e8) from turning the row into NaNs.
+__device__ __forceinline__ float score_hilo(const uint4& qh, const uint4& ql, const uint4& kh, const uint4& kl) {
+  uint32_t c = hfma2(ql.x, kh.x, 0u);
+  c = hfma2(qh.x, kl.x, c);
+  c = hfma2(ql.y, kh.y, c);
+  c = hfma2(qh.y, kl.y, c);
+  c = hfma2(ql.z, kh.z, c);
+  c = hfma2(qh.z, kl.z, c);
+  c = hfma2(ql.w, kh.w, c);
+  c = hfma2(qh.w, kl.w, c);
+  const float s = fh_hl(c, kOneOne, fh_ll(c, kOneOne, dot8_f16(qh, kh, 0.f)));
+  return fminf(fmaxf(s, -3.0e38f), 3.0e38f);
+}
+// One key of the PV product with weight p = ph + pw (halves `HI` of the packed words) and value row v = vh + vl:
+// o += ph * vh in fp32; the cross terms pw * vh + ph * vl accumulate in the packed halves c2 (folded into o at the end)
 template <bool HI>
-__device__ __forceinline__ void axpy8_f16(uint32_t pp, const uint4& v, float (&o)[8]) {
+__device__ __forceinline__ void pv_step(uint32_t ph, uint32_t pw, const uint4& vh, const uint4& vl, float (&o)[8],
+                                        uint32_t (&c2)[4]) {
+  const uint32_t phd = __byte_perm(ph, 0u, HI ? 0x3232u : 0x1010u), pwd = __byte_perm(pw, 0u, HI ? 0x3232u : 0x1010u);
   if (HI) {
-    o[0] = fh_hl(pp, v.x, o[0]); o[1] = fh_hh(pp, v.x, o[1]); o[2] = fh_hl(pp, v.y, o[2]); o[3] = fh_hh(pp, v.y, o[3]);
-    o[4] = fh_hl(pp, v.z, o[4]); o[5] = fh_hh(pp, v.z, o[5]); o[6] = fh_hl(pp, v.w, o[6]); o[7] = fh_hh(pp, v.w, o[7]);
+    o[0] = fh_hl(ph, vh.x, o[0]); o[1] = fh_hh(ph, vh.x, o[1]); o[2] = fh_hl(ph, vh.y, o[2]); o[3] = fh_hh(ph, vh.y, o[3]);
+    o[4] = fh_hl(ph, vh.z, o[4]); o[5] = fh_hh(ph, vh.z, o[5]); o[6] = fh_hl(ph, vh.w, o[6]); o[7] = fh_hh(ph, vh.w, o[7]);
   } else {
-    o[0] = fh_ll(pp, v.x, o[0]); o[1] = fh_lh(pp, v.x, o[1]); o[2] = fh_ll(pp, v.y, o[2]); o[3] = fh_lh(pp, v.y, o[3]);
-    o[4] = fh_ll(pp, v.z, o[4]); o[5] = fh_lh(pp, v.z, o[5]); o[6] = fh_ll(pp, v.w, o[6]); o[7] = fh_lh(pp, v.w, o[7]);
+    o[0] = fh_ll(ph, vh.x, o[0]); o[1] = fh_lh(ph, vh.x, o[1]); o[2] = fh_ll(ph, vh.y, o[2]); o[3] = fh_lh(ph, vh.y, o[3]);
+    o[4] = fh_ll(ph, vh.z, o[4]); o[5] = fh_lh(ph, vh.z, o[5]); o[6] = fh_ll(ph, vh.w, o[6]); o[7] = fh_lh(ph, vh.w, o[7]);
   }
+  c2[0] = hfma2(phd, vl.x, hfma2(pwd, vh.x, c2[0]));
+  c2[1] = hfma2(phd, vl.y, hfma2(pwd, vh.y, c2[1]));
+  c2[2] = hfma2(phd, vl.z, hfma2(pwd, vh.z, c2[2]));
+  c2[3] = hfma2(phd, vl.w, hfma2(pwd, vh.w, c2[3]));
+}
+// o = (o + c2) * inv_z -> fp16 hi + lo words (the attention output of one (row, head): A operand of the W_out product)
+__device__ __forceinline__ void pv_finish(float (&o)[8], const uint32_t (&c2)[4], float inv_z) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = fh_ll(c2[i], kOneOne, o[2 * i]) * inv_z;
+    o[2 * i + 1] = fh_hl(c2[i], kOneOne, o[2 * i + 1]) * inv_z;
+  }
+}
+// shared-memory offset of V's 8-bit remainders of (row, head): rows of 64 bytes, 16-byte pieces rotated so that the
+// 128-bit stores of eight consecutive rows hit eight different bank groups
+__device__ __forceinline__ uint32_t vlo_offset(uint32_t row, uint32_t head) {
+  return row * 64u + ((((head >> 1) ^ (row >> 1)) & 3u) << 4) + ((head & 1u) << 3);
 }
 __device__ __forceinline__ float ex2_approx(float v) {
   float r;
@@ -384,7 +478,6 @@ __device__ __forceinline__ void score_phase(const FusedArgs& a, const float* __r
     if (a.tokens_out != nullptr && len < a.tok_stride) a.tokens_out[(size_t)sq * a.tok_stride + len] = token;
   }
 }
-
 // ------------------------------------------------------------------------------------------
 // half-row helpers: a token row's 64 features are split between two threads (features [32h, 32h + 32))
 // ------------------------------------------------------------------------------------------
@@ -423,18 +516,6 @@ __device__ __forceinline__ void drop_half_direct(float (&v)[HW], const MaskSourc
   }
 }
 
-__device__ __forceinline__ void store_half_f16(uint8_t* tile, uint32_t row, uint32_t h, const float (&v)[HW]) {
-#pragma unroll
-  for (uint32_t c = 0; c < 4; ++c) {
-    uint4 w;
-    w.x = umma::pack_f16x2(v[8 * c + 0], v[8 * c + 1]);
-    w.y = umma::pack_f16x2(v[8 * c + 2], v[8 * c + 3]);
-    w.z = umma::pack_f16x2(v[8 * c + 4], v[8 * c + 5]);
-    w.w = umma::pack_f16x2(v[8 * c + 6], v[8 * c + 7]);
-    *reinterpret_cast<uint4*>(tile + umma::sw128_offset(row, 4 * h + c)) = w;
-  }
-}
-
 __device__ __forceinline__ void tmem_load_half(uint32_t taddr, float (&v)[HW]) {
   uint32_t r[32];
   umma::tmem_ld32(taddr, r);
@@ -443,12 +524,26 @@ __device__ __forceinline__ void tmem_load_half(uint32_t taddr, float (&v)[HW]) {
   for (int i = 0; i < HW; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void tmem_store_half(uint32_t taddr, const float (&v)[HW]) {
-  uint32_t r[32];
+// v += x for this thread's 32 features of the residual stream (fp16 hi + lo words in TMEM: 16 + 16 columns)
+__device__ __forceinline__ void add_residual_half(uint32_t t_hi, uint32_t t_lo, float (&v)[HW]) {
+  uint32_t hi[16], lo[16];
+  umma::tmem_ld16(t_hi, hi);
+  umma::tmem_ld16(t_lo, lo);
+  umma::tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < HW; ++i) r[i] = __float_as_uint(v[i]);
-  umma::tmem_st32(taddr, r);
-  umma::tmem_st_wait();
+  for (int i = 0; i < 16; ++i) {
+    v[2 * i] = umma::add_hilo_l(hi[i], lo[i], v[2 * i]);
+    v[2 * i + 1] = umma::add_hilo_h(hi[i], lo[i], v[2 * i + 1]);
+  }
+}
+
+// this thread's 32 features as the fp16 hi + lo words of a TS-form A operand (and of the residual stream)
+__device__ __forceinline__ void store_hilo_half(uint32_t t_hi, uint32_t t_lo, const float (&v)[HW]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) umma::split_f16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  umma::tmem_st16(t_hi, hi);
+  umma::tmem_st16(t_lo, lo);
 }
 
 // LayerNorm over a 64-feature row held as two 32-feature halves in two threads (biased variance, eps inside the
@@ -469,12 +564,15 @@ __device__ __forceinline__ float2 ln_partial(const float (&v)[HW]) {
   }
   return make_float2(m_own, q0 + q1);
 }
+__device__ __forceinline__ void ln_combine(float2 own, float2 other, float eps, float& mean, float& rstd) {
+  const float dm = own.x - other.x;
+  mean = 0.5f * (own.x + other.x);
+  rstd = rsqrtf((own.y + other.y + 16.0f * dm * dm) * (1.0f / FD) + eps);
+}
 __device__ __forceinline__ void ln_finish(float (&v)[HW], float2 own, float2 other, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, float eps) {
-  const float dm = own.x - other.x;
-  const float mean = 0.5f * (own.x + other.x);
-  const float var = (own.y + other.y + 16.0f * dm * dm) * (1.0f / FD);
-  const float rstd = rsqrtf(var + eps);
+  float mean, rstd;
+  ln_combine(own, other, eps, mean, rstd);
   const float shift = -mean * rstd;
 #pragma unroll
   for (int i = 0; i < HW; ++i) v[i] = fmaf(fmaf(v[i], rstd, shift), gamma[i], beta[i]);
@@ -482,29 +580,90 @@ __device__ __forceinline__ void ln_finish(float (&v)[HW], float2 own, float2 oth
 
 #ifdef BFB_FUSED_TIMING
 // debug build only (make EXTRA=-DBFB_FUSED_TIMING): cycles one observer thread per group spends in the product
-// round trips (barrier -> MMA issue -> completion wait), in the other group barriers, and in total
+// round trips (barrier -> MMA issue -> completion wait), and in total
 __device__ unsigned long long bfb_fused_dbg[8];
-#define BFB_T0() const long long _t0 = clock64()
-#define BFB_T1(slot) do { if ((gt & 31) == 5) dbg[slot] += clock64() - _t0; } while (0)
-#else
-#define BFB_T0() do { } while (0)
-#define BFB_T1(slot) do { } while (0)
 #endif
 
+// ------------------------------------------------------------------------------------------
 // The MMAs of one product, issued by ONE thread of group G.  Every operand is built from kernel-uniform values (the
 // shared-memory window base, kernel parameters, the compile-time group index; the TMEM allocation is the whole
-// 512 columns, so its base is column 0) and therefore lives in uniform registers: with per-thread operands the
-// compiler wraps each UTCHMMA in an ELECT / R2UR.BROADCAST / branch "waterfall" loop, ~140 cycles per instruction
-// on the critical path of the whole group.
+// 512 columns, so its base is column 0) and therefore lives in uniform registers.
+// ------------------------------------------------------------------------------------------
+enum { PR_QKV = 0, PR_MERGED, PR_WOUT, PR_FFN1, PR_FFN2, PR_HEAD };
+
+struct IssueCtx {
+  uint32_t tiles_u32;   // shared-memory address of group 0's first tile
+  uint32_t img_u32;     // shared-memory address of the weight image
+  uint32_t fp;
+  uint32_t merged;
+  uint32_t w2_per_tile;
+  uint32_t w2_lo;
+  uint32_t attn_lo;     // the pair phase left the attention output's lo parts in the L tile
+  uint32_t off_om, off_w1, off_w2, layer_bytes;
+};
+
 template <int G>
-__device__ __forceinline__ void fused_issue_product(uint32_t tiles_u32, int a_sel, uint32_t b_addr, int N, int k_steps,
-                                                    uint64_t* group_bars) {
-  const uint32_t a_addr = tiles_u32 + (uint32_t)(G * 3 + a_sel) * TILE_BYTES;
-  const uint64_t da = umma::smem_desc_sw128(a_addr), db = umma::smem_desc_sw128(b_addr);
-  const uint32_t idesc = umma::instr_desc_f16(FROWS, N);
-  const uint32_t d_tmem = (uint32_t)G * 256u + 64u;
-  for (int k = 0; k < k_steps; ++k) umma::mma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0);
-  umma::mma_commit(&group_bars[G]);
+__device__ __forceinline__ void fused_issue(const IssueCtx& c, int kind, int layer, uint64_t* group_bar) {
+  const uint32_t tile0 = c.tiles_u32 + (uint32_t)(G * FTILES) * TILE_BYTES;
+  const uint32_t gb = (uint32_t)G * 256u;       // TMEM window of the group
+  const uint32_t wl = c.img_u32 + (uint32_t)layer * c.layer_bytes;
+  const uint32_t fp = c.fp;
+  if (kind == PR_QKV) {
+    // [Q | K | V] = x W_qkv^T with x = hi + lo from TMEM, W_qkv = hi + lo (lo rows of Q, K in the V tile, of V in the
+    // V-remainder tile; the x_lo W_lo term is dropped)
+    const uint64_t dw = umma::smem_desc_sw128(wl), dl = umma::smem_desc_sw128(tile0 + T_V * TILE_BYTES);
+    const uint64_t dlv = umma::smem_desc_sw128(c.tiles_u32 + (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)G * VLO_BYTES);
+    const uint32_t id192 = umma::instr_desc_f16(FROWS, 3 * FD), id128 = umma::instr_desc_f16(FROWS, 2 * FD);
+    const uint32_t id64 = umma::instr_desc_f16(FROWS, FD);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XHI + 8u * k, dw + 2 * k, id192, k > 0);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XLO + 8u * k, dw + 2 * k, id192, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XHI + 8u * k, dl + 2 * k, id128, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + 2u * FD, gb + C_XHI + 8u * k, dlv + 2 * k, id64, 1u);
+  } else if (kind == PR_MERGED) {
+    // columns [0, 64) = attn W_out^T ; [64, 64 + fp) = attn ((W1 g1) W_out)^T + x (W1 g1)^T
+    const uint64_t da = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES), dom = umma::smem_desc_sw128(wl + c.off_om);
+    const uint64_t dal = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES);
+    const uint64_t dw1 = umma::smem_desc_sw128(wl + c.off_w1);
+    const uint32_t id_om = umma::instr_desc_f16(FROWS, FD + fp), id_fp = umma::instr_desc_f16(FROWS, fp);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, da + 2 * k, dom + 2 * k, id_om, k > 0);
+    if (c.attn_lo)
+      for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, dal + 2 * k, dom + 2 * k, id_om, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + FD, gb + C_XHI + 8u * k, dw1 + 2 * k, id_fp, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + FD, gb + C_XLO + 8u * k, dw1 + 2 * k, id_fp, 1u);
+  } else if (kind == PR_WOUT) {
+    const uint64_t da = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES), dom = umma::smem_desc_sw128(wl + c.off_om);
+    const uint64_t dal = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES);
+    const uint32_t id64 = umma::instr_desc_f16(FROWS, FD);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, da + 2 * k, dom + 2 * k, id64, k > 0);
+    if (c.attn_lo)
+      for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, dal + 2 * k, dom + 2 * k, id64, 1u);
+  } else if (kind == PR_FFN1) {
+    // unmerged flow: LayerNorm1 output (hi at columns [64, 96), lo at [96, 128) of the accumulator window) times W1
+    const uint64_t dw1 = umma::smem_desc_sw128(wl + c.off_w1);
+    const uint32_t id_fp = umma::instr_desc_f16(FROWS, fp);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + 128u, gb + C_ACC + 64u + 8u * k, dw1 + 2 * k, id_fp, k > 0);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + 128u, gb + C_ACC + 96u + 8u * k, dw1 + 2 * k, id_fp, 1u);
+  } else if (kind == PR_FFN2) {
+    // FFN hidden row (hi + lo, 32 columns each, at accumulator-window column 128 in the merged flow — the FFN1
+    // accumulator still occupies [64, 64 + fp) — and at 64 otherwise) times W2 -> columns [0, 64)
+    const uint32_t w2 = c.img_u32 + c.off_w2 + ((uint32_t)layer / c.w2_per_tile) * (FD * 128u) +
+                        ((uint32_t)layer % c.w2_per_tile) * fp * 2u;
+    const uint64_t dw2 = umma::smem_desc_sw128(w2);
+    const uint32_t id64 = umma::instr_desc_f16(FROWS, FD);
+    const int ks = (int)(fp >> 4);
+    const uint32_t hcol = gb + C_ACC + (c.merged ? 128u : 64u);
+    for (int k = 0; k < ks; ++k) umma::mma_f16_ts(gb + C_ACC, hcol + 8u * k, dw2 + 2 * k, id64, k > 0);
+    for (int k = 0; k < ks; ++k) umma::mma_f16_ts(gb + C_ACC, hcol + 32u + 8u * k, dw2 + 2 * k, id64, 1u);
+    if (c.w2_lo)   // W2's lo columns sit 32 K-columns (64 bytes) behind the hi ones
+      for (int k = 0; k < ks; ++k) umma::mma_f16_ts(gb + C_ACC, hcol + 8u * k, dw2 + 4 + 2 * k, id64, 1u);
+  } else {
+    // vocabulary head on x = hi + lo: 128 classes; its weights were streamed into the (dead) Q tile
+    const uint64_t dh = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES);
+    const uint32_t id128 = umma::instr_desc_f16(FROWS, FMAXV);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XHI + 8u * k, dh + 2 * k, id128, k > 0);
+    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XLO + 8u * k, dh + 2 * k, id128, 1u);
+  }
+  umma::mma_commit(group_bar);
 }
 
 // FAST != 0 = the configurations every acquisition round runs (the reference's default dropout sites E + layer-out of a
@@ -522,56 +681,70 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     a.logp_out = nullptr;
     a.forced = nullptr;
   }
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment of the swizzled tiles, computed as an offset so the pointers stay in the shared
-  // address space (LDS / STS instead of generic loads)
-  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t bar_image;
-  __shared__ uint64_t bar_group[FGROUPS];
-  __shared__ uint32_t tmem_slot;
-  __shared__ float2 ln_red[FGROUPS][2 * FROWS];
+  // Everything lives in dynamic shared memory (no static allocation in front of it, so its base is 1024-byte aligned
+  // in practice; the pad is computed as an offset so that the pointers stay in the shared address space):
+  //   [FGROUPS x FTILES tiles of 16 KB][FGROUPS V-remainder tiles of 8 KB][weight image][mbarriers, TMEM slot]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const FusedLayout lay = a.lay;
+  if (pad + kTilesBytes + lay.smem_image_bytes + kBarrierBytes > a.smem_bytes) __trap();
+  uint8_t* img = smem + kTilesBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(img + lay.smem_image_bytes);
+  uint64_t* bar_image = bars;          // weight image landed
+  uint64_t* bar_group = bars + 1;      // [FGROUPS] product of the group complete
+  uint64_t* bar_wlo = bars + 3;        // [FGROUPS] W_qkv lo rows of the next QKV product landed in the V tiles
+  uint64_t* bar_head = bars + 5;       // [FGROUPS] vocabulary head landed in the Q tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x;
   const int g = tid / FGROUP_THREADS, gt = tid % FGROUP_THREADS;   // group, thread in group
   const int h = gt >> 7, row = gt & 127;                           // feature half, token row
   const int gw = row >> 5;                                         // TMEM lane quarter (= CTA warp % 4)
-  const FusedLayout lay = a.lay;
-  uint8_t* img = smem;
-  uint8_t* B0 = smem + lay.image_bytes + (uint32_t)g * 3u * TILE_BYTES;
-  uint8_t* B1 = B0 + TILE_BYTES;
-  uint8_t* B2 = B1 + TILE_BYTES;
+  uint8_t* TQ = smem + (uint32_t)(g * FTILES + T_Q) * TILE_BYTES;
+  uint8_t* TK = smem + (uint32_t)(g * FTILES + T_K) * TILE_BYTES;
+  uint8_t* TL = smem + (uint32_t)(g * FTILES + T_L) * TILE_BYTES;
+  uint8_t* TV = smem + (uint32_t)(g * FTILES + T_V) * TILE_BYTES;
+  uint8_t* TVL = smem + (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)g * VLO_BYTES;
   const float* params = reinterpret_cast<const float*>(img + lay.off_params);
-  float2* red = ln_red[g];
+  float2* red = reinterpret_cast<float2*>(TK);   // LayerNorm exchange: K is dead whenever it is in use
 
   if (tid < 32) {
-    umma::tmem_alloc(&tmem_slot, 512);
+    umma::tmem_alloc(tmem_slot, 512);
     umma::tmem_relinquish();
   }
   if (tid == 0) {
-    umma::mbar_init(&bar_image, 1);
-    umma::mbar_init(&bar_group[0], 1);
-    umma::mbar_init(&bar_group[1], 1);
+    for (int i = 0; i < 7; ++i) umma::mbar_init(&bars[i], 1);
     umma::fence_mbar_init();
   }
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
   if (tid == 0) {
-    umma::mbar_expect_tx(&bar_image, lay.image_bytes);
-    for (uint32_t off = 0; off < lay.image_bytes; off += 16384u) {
-      const uint32_t n = lay.image_bytes - off < 16384u ? lay.image_bytes - off : 16384u;
-      umma::bulk_g2s(img + off, a.image + off, n, &bar_image);
+    umma::mbar_expect_tx(bar_image, lay.smem_image_bytes);
+    for (uint32_t off = 0; off < lay.smem_image_bytes; off += 16384u) {
+      const uint32_t n = lay.smem_image_bytes - off < 16384u ? lay.smem_image_bytes - off : 16384u;
+      umma::bulk_g2s(img + off, a.image + off, n, bar_image);
     }
   }
-  umma::mbar_wait(&bar_image, 0);
+  const int64_t tile_first = (int64_t)blockIdx.x * FGROUPS + g, tile_step = (int64_t)gridDim.x * FGROUPS;
+  const uint8_t* wlo_src = a.image + lay.off_wlo;
+  auto stream_wlo = [&](int layer) {   // one thread: W_qkv lo rows of `layer` -> V tile (Q, K rows) and V-remainder tile (V rows)
+    umma::mbar_expect_tx(&bar_wlo[g], WLO_BYTES);
+    umma::bulk_g2s(TV, wlo_src + (uint32_t)layer * WLO_BYTES, WLO_QK_BYTES, &bar_wlo[g]);
+    umma::bulk_g2s(TVL, wlo_src + (uint32_t)layer * WLO_BYTES + WLO_QK_BYTES, WLO_V_BYTES, &bar_wlo[g]);
+  };
+  if (gt == 0 && tile_first < a.n_tiles) stream_wlo(0);   // for the first QKV product
+  umma::mbar_wait(bar_image, 0);
 
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(gw * 32) << 16;
-  const uint32_t tX = tmem_base + (uint32_t)g * 256u + lane_base + (uint32_t)h * HW;  // residual stream (this half)
-  const uint32_t tW = tmem_base + (uint32_t)g * 256u + lane_base + 64u;               // accumulators, 192 columns
+  const uint32_t tG = tmem_base + (uint32_t)g * 256u + lane_base;
+  const uint32_t tXh = tG + C_XHI + 16u * (uint32_t)h, tXl = tG + C_XLO + 16u * (uint32_t)h;   // residual stream (this half)
+  const uint32_t tA = tG + C_ACC;                                                              // accumulators, 192 columns
   if (tmem_base != 0u) __trap();   // all 512 columns are ours: the MMA issue path relies on base column 0
   uint64_t* bar = &bar_group[g];
-  uint32_t phase = 0;
+  uint32_t phase = 0, wlo_phase = 0, head_phase = 0;
   const int bar_id = 1 + g;
 
   const int len = a.len, spt = a.spt;
@@ -584,57 +757,63 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const float sqrt_d = sqrtf((float)FD);
   const float qk_scale_log2e = 1.4426950408889634f / sqrtf((float)FDH);   // scores / sqrt(dh), in base-2 exponent units
   const uint32_t fl = a.site_flags;
-  const bool fold_ln1 = !(fl & BFB200_SITE_FFN_IN);   // the same rule fused_pack_kernel packed the W1 slot by
+  const bool merged = lay.merged != 0;   // the same rule fused_pack_kernel laid the image out by
   const MaskSource& ms = a.ms;
 
-  const uint32_t img_u32 = umma::smem_u32(img);
+  IssueCtx ic;
+  ic.tiles_u32 = umma::smem_u32(smem);
+  ic.img_u32 = umma::smem_u32(img);
+  ic.fp = lay.fp; ic.merged = lay.merged; ic.w2_per_tile = lay.w2_per_tile; ic.w2_lo = lay.w2_lo;
+  ic.attn_lo = MAXLEN <= 16 ? 1u : 0u;
+  ic.off_om = lay.off_om; ic.off_w1 = lay.off_w1; ic.off_w2 = lay.off_w2;
+  ic.layer_bytes = lay.layer_bytes;
 
-  // one GEMM phase: operand rows are in shared memory -> accumulators in TMEM columns [tW, tW + N)
 #ifdef BFB_FUSED_TIMING
-  long long dbg[4] = {0, 0, 0, 0};   // observer lanes: round-trip cycles, round trips, cycles after the barrier
-  long long dbi[3] = {0, 0, 0};      // issuing thread: barrier exit -> commit issued, -> completion seen, fence
+  long long dbg[3] = {0, 0, 0};   // observer lanes: round-trip cycles, round trips
   const long long t_begin = clock64();
 #endif
-  const uint32_t tiles_u32 = umma::smem_u32(smem) + lay.image_bytes;   // kernel-uniform
-  auto gemm = [&](int a_sel, uint32_t b_addr, int N, int k_steps) {
-    BFB_T0();
-    umma::fence_async_smem();
+  // One product: operands are in TMEM (tcgen05.st of this group's threads) or shared memory -> accumulators in TMEM.
+  // next_wlo >= 0: the V tiles are dead from here on, so the issuing thread starts the bulk copies of that layer's
+  // W_qkv lo rows into them (consumed by the next PR_QKV product, which waits for them).  stage_head: likewise the Q
+  // tile is dead and receives the vocabulary head's weights (consumed by PR_HEAD).
+  auto product = [&](int kind, int layer, int next_wlo, bool stage_head = false) {
+#ifdef BFB_FUSED_TIMING
+    const long long _t0 = clock64();
+#endif
+    if (kind == PR_MERGED || kind == PR_WOUT) umma::fence_async_smem();
+    __syncwarp();   // the pair phase leaves the lanes of a warp at different trip counts; tcgen05.wait is warp-aligned
+    umma::tmem_st_wait();
     umma::tc_fence_before_sync();
     umma::group_sync(bar_id, FGROUP_THREADS);
-#ifdef BFB_FUSED_TIMING
-    const long long _t_issue = clock64();
-#endif
     if (gt == 0) {
       umma::tc_fence_after_sync();
-#ifdef BFB_FUSED_TIMING
-      const long long _t1 = clock64();
-#endif
-      if (g == 0) fused_issue_product<0>(tiles_u32, a_sel, b_addr, N, k_steps, bar_group);
-      else        fused_issue_product<1>(tiles_u32, a_sel, b_addr, N, k_steps, bar_group);
-#ifdef BFB_FUSED_TIMING
-      const long long _t3 = clock64();
-      dbi[0] += _t3 - _t_issue;
-      dbi[2] += _t1 - _t_issue;
-#endif
+      if (next_wlo >= 0) stream_wlo(next_wlo);
+      if (stage_head) {
+        umma::mbar_expect_tx(&bar_head[g], HEAD_BYTES);
+        umma::bulk_g2s(TQ, a.image + lay.off_head, HEAD_BYTES, &bar_head[g]);
+      }
+      if (kind == PR_QKV) umma::mbar_wait(&bar_wlo[g], wlo_phase);
+      if (kind == PR_HEAD) umma::mbar_wait(&bar_head[g], head_phase);
+      if (g == 0) fused_issue<0>(ic, kind, layer, &bar_group[0]);
+      else        fused_issue<1>(ic, kind, layer, &bar_group[1]);
     }
+    if (kind == PR_QKV) wlo_phase ^= 1u;
+    if (kind == PR_HEAD) head_phase ^= 1u;
     umma::mbar_wait(bar, phase);
-#ifdef BFB_FUSED_TIMING
-    if (gt == 0) dbi[1] += clock64() - _t_issue;
-#endif
     phase ^= 1u;
     umma::tc_fence_after_sync();
-    BFB_T1(0);
 #ifdef BFB_FUSED_TIMING
-    if ((gt & 31) == 5) { dbg[1] += 1; dbg[2] += clock64() - _t_issue; }
+    if ((gt & 31) == 5) { dbg[0] += clock64() - _t0; dbg[1] += 1; }
 #endif
   };
 
-  for (int64_t tile = (int64_t)blockIdx.x * FGROUPS + g; tile < a.n_tiles; tile += (int64_t)gridDim.x * FGROUPS) {
+  for (int64_t tile = tile_first; tile < a.n_tiles; tile += tile_step) {
     const uint32_t s0 = (uint32_t)tile * (uint32_t)spt;   // n_seq < 2^31 per launch (checked on the host)
     const int nseq = (int)(((uint32_t)a.n_seq - s0) < (uint32_t)spt ? ((uint32_t)a.n_seq - s0) : (uint32_t)spt);
     const bool row_valid = pos < len && seq_l < nseq;
     const uint32_t s = s0 + (row_valid ? (uint32_t)seq_l : 0u);
     const RowRng rr = make_row_rng(ms, s);
+    const bool more_tiles = tile + tile_step < a.n_tiles;
 
     // ---- embedding + dropout E + sqrt(d) scale + positional encoding (transformer.py:355-362) ----
     {
@@ -643,56 +822,66 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       if (row_valid) {
         const int tok = a.tokens[(size_t)s * a.tok_stride + pos];
         const float4* e = reinterpret_cast<const float4*>(a.embedding + (size_t)tok * FD + h * HW);
+        const float4* pe = reinterpret_cast<const float4*>(a.pe + (size_t)pos * FD + h * HW);
+        float pv[HW];
 #pragma unroll
         for (int i = 0; i < HW / 4; ++i) {
-          const float4 v = __ldg(e + i);
+          const float4 v = __ldg(e + i), q = __ldg(pe + i);
           x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+          pv[4 * i] = q.x; pv[4 * i + 1] = q.y; pv[4 * i + 2] = q.z; pv[4 * i + 3] = q.w;
         }
         if (FAST == 1) drop_half_direct(x, ms, rr, (uint32_t)pos, 0u, (uint32_t)h);
         else if (fl & BFB200_SITE_EMBED) drop_half(x, k_embed, ms.scale);
-        const float* pe = params + a.n_layers * PARAMS_PER_LAYER + FMAXV + pos * FD + h * HW;
 #pragma unroll
-        for (int i = 0; i < HW; ++i) x[i] = x[i] * sqrt_d + pe[i];
+        for (int i = 0; i < HW; ++i) x[i] = fmaf(x[i], sqrt_d, pv[i]);
       } else {
 #pragma unroll
         for (int i = 0; i < HW; ++i) x[i] = 0.f;
       }
-      tmem_store_half(tX, x);
-      store_half_f16(B0, row, h, x);
+      store_hilo_half(tXh, tXl, x);
     }
 
     for (int l = 0; l < a.n_layers; ++l) {
-      const uint32_t wl = img_u32 + (uint32_t)l * lay.layer_bytes;
-      const float* pl = params + l * PARAMS_PER_LAYER;
+      const float* pl = params + (uint32_t)l * lay.params_per_layer;
       const uint32_t sb = 1u + BFB200_SITES_PER_LAYER * (uint32_t)l;
       // Last layer: only the last position's output is read (vocabulary head, active_learning.py:146), so its
       // queries, W_out / LayerNorm / FFN rows and layer-out masks for the other positions are dead work; K and V of
       // every position are still needed.  `live` is warp-uniform.
       const bool prune = l + 1 == a.n_layers;
       const bool live = !prune || warp_has_last;
+      const int next_wlo = !prune ? l + 1 : (more_tiles ? 0 : -1);
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
-      gemm(0, wl, 3 * FD, 4);
-      // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 operand tiles B0, B1, B2
-      // (x in B0 is dead once the product has completed); each half copies 96 columns, 16 per trip
+      product(PR_QKV, l, -1);
+      // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 tiles, and their fp16 rounding remainders
+      // as e5m2 bytes: Q and K in the L tile (chunk of (row, head): 8 bytes of Q, 8 of K), V in the V-remainder tile.
+      // This half takes heads [4h, 4h + 4) of each matrix, 16 columns = 2 heads per trip.
 #pragma unroll 1
-      for (uint32_t c0 = 96u * h; c0 < 96u * h + 96u; c0 += 16) {
+      for (uint32_t trip = 0; trip < 6; ++trip) {
+        const uint32_t mat = trip >> 1;                                  // 0 Q, 1 K, 2 V
+        const uint32_t c0 = 64u * mat + 32u * (uint32_t)h + 16u * (trip & 1u);
         uint32_t r[16];
-        umma::tmem_ld16(tW + c0, r);
+        umma::tmem_ld16(tA + c0, r);
         umma::tmem_ld_wait();
-        uint8_t* dst = B0 + (c0 >> 6) * TILE_BYTES;   // B0, B1, B2 are contiguous
+        uint8_t* dst = mat == 0 ? TQ : (mat == 1 ? TK : TV);
         const uint32_t ch = (c0 & 63u) >> 3;
-        uint4 w0, w1;
-        w0.x = umma::pack_f16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
-        w0.y = umma::pack_f16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
-        w0.z = umma::pack_f16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
-        w0.w = umma::pack_f16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
-        w1.x = umma::pack_f16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
-        w1.y = umma::pack_f16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
-        w1.z = umma::pack_f16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
-        w1.w = umma::pack_f16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch)) = w0;
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch + 1)) = w1;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = umma::pack_f16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+        constexpr uint32_t kNegOne = 0xBC00BC00u;
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          e[i] = umma::pack_e5m2x2(fh_ll(w[i], kNegOne, __uint_as_float(r[2 * i])), fh_hl(w[i], kNegOne, __uint_as_float(r[2 * i + 1])));
+        const uint4 lo8 = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+        if (mat < 2) {
+          *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch) + 8u * mat) = make_uint2(lo8.x, lo8.y);
+          *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch + 1) + 8u * mat) = make_uint2(lo8.z, lo8.w);
+        } else {
+          *reinterpret_cast<uint4*>(TVL + vlo_offset(row, ch)) = lo8;   // heads ch (even) and ch + 1 share a 16-byte piece
+        }
       }
       umma::tc_fence_before_sync();
       umma::group_sync(bar_id, FGROUP_THREADS);
@@ -710,27 +899,31 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           const int p = prune ? it : it - t * npairs;
           const int sl = p >> 3, hd = p & 7;
           const uint32_t row0 = (uint32_t)sl;
-          uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
-          const uint4 qw = *reinterpret_cast<const uint4*>(qptr);
+          const uint32_t qoff = umma::sw128_offset(row0 + t * spt, hd);
+          const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
+          const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
           float mx = -INFINITY;
-          for (int j = 0; j <= t; ++j)
-            mx = fmaxf(mx, dot8_f16(qw, *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd))));
+          for (int j = 0; j <= t; ++j) {
+            const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
+            mx = fmaxf(mx, score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
+                                      widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u))));
+          }
           const float nmx = -mx * qk_scale_log2e;
           float z = 0.f;
           float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          uint32_t c2[4] = {0u, 0u, 0u, 0u};
           for (int j = 0; j <= t; ++j) {
-            const float sj = dot8_f16(qw, *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd)));
+            const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
+            const float sj = score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
+                                        widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u)));
             const float e = ex2_approx(fmaf(sj, qk_scale_log2e, nmx));
             z += e;
             const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
-            const uint32_t pl = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
-            const uint4 vw = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j * spt, hd));
-            axpy8_f16<false>(ph, vw, o);
-            axpy8_f16<false>(pl, vw, o);
+            const uint32_t pw = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
+            pv_step<false>(ph, pw, *reinterpret_cast<const uint4*>(TV + koff),
+                           widen_lo8(*reinterpret_cast<const uint2*>(TVL + vlo_offset(row0 + j * spt, hd))), o, c2);
           }
-          const float inv_z = __fdividef(1.0f, z);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] *= inv_z;
+          pv_finish(o, c2, __fdividef(1.0f, z));
           if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
             const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
             const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
@@ -740,45 +933,51 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           uint4 w;
           w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
           w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(qptr) = w;   // in place: other items read only K / V rows, never this Q chunk
+          *reinterpret_cast<uint4*>(TQ + qoff) = w;   // in place: other items read only K / V rows, never this Q chunk
         }
       } else {
-        // short sequences: work item = (sequence, head[, query parity]), K and V held in registers
+        // short sequences: work item = (sequence, head[, query parity]), K (fp16 + 8-bit remainders) held in registers
         const int npairs = nseq * FH;
         // few pairs: two threads share one, queries split so that both walk about the same number of keys (query t
         // costs t + 1 key visits; a.qsplit is the balanced assignment); in the last layer only the last query is live
         const int nsplit = (!prune && npairs * 2 <= FGROUP_THREADS) ? 2 : 1;
-        for (int it = gt; it < npairs * nsplit; it += FGROUP_THREADS) {
+        if (gt < npairs * nsplit) {   // at most one work item per thread: npairs <= 256, and two threads share a pair only below 128
+          const int it = gt;
           const int p = nsplit == 2 ? it >> 1 : it;
           const int qpar = nsplit == 2 ? (it & 1) : -1;
           const int sl = p >> 3, hd = p & 7;
           const uint32_t row0 = (uint32_t)sl;   // row of (sequence sl, position j) = j * spt + sl
-          // K and V stay packed (4 registers per key / value row); the dot products read the fp16 halves in place
-          uint4 kp[MAXLEN], vp[MAXLEN];
+          uint4 kp[MAXLEN];
+          uint2 kl[MAXLEN];
 #pragma unroll
           for (int j = 0; j < MAXLEN; ++j) {
             if (j < len) {
-              kp[j] = *reinterpret_cast<const uint4*>(B1 + umma::sw128_offset(row0 + j * spt, hd));
-              vp[j] = *reinterpret_cast<const uint4*>(B2 + umma::sw128_offset(row0 + j * spt, hd));
+              const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
+              kp[j] = *reinterpret_cast<const uint4*>(TK + koff);
+              kl[j] = *reinterpret_cast<const uint2*>(TL + koff + 8u);
             }
           }
+          // every K remainder is in registers (of both threads of a split pair) before any chunk of the L tile is
+          // overwritten with an attention-output lo part below
+          __syncwarp(__activemask());
           const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
           for (int t = 0; t < MAXLEN; ++t) {
             if (t < len && (qpar < 0 || (int)((a.qsplit >> t) & 1u) == qpar) && (!prune || t == len - 1)) {
-              uint8_t* qptr = B0 + umma::sw128_offset(row0 + t * spt, hd);
-              const uint4 qw = *reinterpret_cast<const uint4*>(qptr);
+              const uint32_t qoff = umma::sw128_offset(row0 + t * spt, hd);
+              const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
+              const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
               float sc[MAXLEN];
               float mx = -INFINITY;
 #pragma unroll
               for (int j = 0; j <= t; ++j) {
-                sc[j] = dot8_f16(qw, kp[j]);
+                sc[j] = score_hilo(qw, ql, kp[j], widen_lo8(kl[j]));
                 mx = fmaxf(mx, sc[j]);
               }
               // softmax weights e_j = exp((s_j - max) / sqrt(dh)) in fp32, handed to the fp16-operand PV product as
               // a (high, low) pair of halves: e_j = hi_j + lo_j to 2^-22, so the product keeps fp32 weights
               const float nmx = -mx * qk_scale_log2e;
-              uint32_t ph[(MAXLEN + 1) / 2], pl[(MAXLEN + 1) / 2];
+              uint32_t ph[(MAXLEN + 1) / 2], pw[(MAXLEN + 1) / 2];
               float z = 0.f;
 #pragma unroll
               for (int j = 0; j <= t; j += 2) {
@@ -787,141 +986,158 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
                 z += e0 + e1;
                 ph[j >> 1] = umma::pack_f16x2(e0, e1);
                 const float2 hi = umma::unpack_f16x2(ph[j >> 1]);
-                pl[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
+                pw[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
               }
-              const float inv_z = __fdividef(1.0f, z);
               float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              uint32_t c2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
               for (int j = 0; j <= t; ++j) {
-                if (j & 1) { axpy8_f16<true>(ph[j >> 1], vp[j], o); axpy8_f16<true>(pl[j >> 1], vp[j], o); }
-                else       { axpy8_f16<false>(ph[j >> 1], vp[j], o); axpy8_f16<false>(pl[j >> 1], vp[j], o); }
+                const uint4 vh = *reinterpret_cast<const uint4*>(TV + umma::sw128_offset(row0 + j * spt, hd));
+                const uint4 vl = widen_lo8(*reinterpret_cast<const uint2*>(TVL + vlo_offset(row0 + j * spt, hd)));
+                if (j & 1) pv_step<true>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
+                else       pv_step<false>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
               }
-#pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] *= inv_z;
+              pv_finish(o, c2, __fdividef(1.0f, z));
               if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
                 const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
               }
-              uint4 w;
-              w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
-              w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(qptr) = w;
+              // hi part over the query's Q chunk, lo part over its chunk of the L tile (both consumed above)
+              uint4 w, wl;
+              umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
+              umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
+              *reinterpret_cast<uint4*>(TQ + qoff) = w;
+              *reinterpret_cast<uint4*>(TL + qoff) = wl;
             }
           }
         }
       }
 
       if (!live) {
-        // dead rows of the last layer: take part in the barriers of the three products and the two LayerNorm
-        // exchanges (thread 0 of the group still issues the MMAs inside gemm()), compute nothing
-        gemm(0, wl + lay.off_out, FD, 4);
-        if (!fold_ln1) umma::group_sync(bar_id, FGROUP_THREADS);
-        gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
-        gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+        // dead rows of the last layer: take part in the barriers of the products and the LayerNorm exchanges
+        // (thread 0 of the group still issues the MMAs inside product()), compute nothing
+        if (merged) {
+          product(PR_MERGED, l, next_wlo);
+          umma::group_sync(bar_id, FGROUP_THREADS);
+        } else {
+          product(PR_WOUT, l, next_wlo);
+          umma::group_sync(bar_id, FGROUP_THREADS);
+          product(PR_FFN1, l, -1);
+        }
+        product(PR_FFN2, l, -1, prune);
         umma::group_sync(bar_id, FGROUP_THREADS);
         continue;
       }
 
-      // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231) ----
-      gemm(0, wl + lay.off_out, FD, 4);
-      {
-        const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
-        const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
-        float v[HW];
-        tmem_load_half(tW + h * HW, v);
-        if (fl & BFB200_SITE_ATTN_RESID) drop_half(v, k_attn, ms.scale);
+      const uint32_t t_h = tA + (merged ? 128u : 64u);   // FFN hidden row as a TS operand: hi, lo at +32
+      if (merged) {
+        // ---- W_out and FFN1 in one product; residual from the block input; LayerNorm1 folded (transformer.py:125, :231-232) ----
+        product(PR_MERGED, l, next_wlo);
         {
-          float x[HW];
-          tmem_load_half(tX, x);
-#pragma unroll
-          for (int i = 0; i < HW; ++i) v[i] += x[i];
+          float v[HW];
+          tmem_load_half(tA + h * HW, v);
+          add_residual_half(tXh, tXl, v);
+          red[h * FROWS + row] = ln_partial(v);
         }
-        const float2 own = ln_partial(v);
-        red[h * FROWS + row] = own;
-        if (!fold_ln1) {
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        {
+          // W1 LN1(v) + b1 = rstd (v (W1 g1)^T - mean col_s) + col_c, ReLU (transformer.py:151-155); each half takes fp / 2 columns
+          float ln_mean, ln_rstd;
+          ln_combine(red[h * FROWS + row], red[(h ^ 1) * FROWS + row], a.ln_eps, ln_mean, ln_rstd);
+          const float* col_s = pl + P_COLS;
+          const float* col_c = pl + P_COLS + lay.fp;
+          const uint32_t half_cols = lay.fp >> 1;   // multiple of 8
+          for (uint32_t c0 = half_cols * h; c0 < half_cols * (h + 1); c0 += 8) {
+            uint32_t r[8];
+            umma::tmem_ld8(tA + FD + c0, r);
+            umma::tmem_ld_wait();
+            float hc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              hc[i] = fmaxf(fmaf(ln_rstd, fmaf(-ln_mean, col_s[c0 + i], __uint_as_float(r[i])), col_c[c0 + i]), 0.f);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) umma::split_f16x2(hc[2 * i], hc[2 * i + 1], hi[i], lo[i]);
+            umma::tmem_st4(t_h + (c0 >> 1), hi);
+            umma::tmem_st4(t_h + 32u + (c0 >> 1), lo);
+          }
+        }
+      } else {
+        // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231), then FFN1 ----
+        product(PR_WOUT, l, next_wlo);
+        {
+          const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
+          const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
+          float v[HW];
+          tmem_load_half(tA + h * HW, v);
+          if (fl & BFB200_SITE_ATTN_RESID) drop_half(v, k_attn, ms.scale);
+          add_residual_half(tXh, tXl, v);
+          const float2 own = ln_partial(v);
+          red[h * FROWS + row] = own;
           umma::group_sync(bar_id, FGROUP_THREADS);
-          ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + h * HW, pl + 64 + h * HW, a.ln_eps);
-          drop_half(v, k_ffn_in, ms.scale);
+          ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + P_LN1W + h * HW, pl + P_LN1B + h * HW, a.ln_eps);
+          if (fl & BFB200_SITE_FFN_IN) drop_half(v, k_ffn_in, ms.scale);
+          store_hilo_half(tA + 64u + 16u * (uint32_t)h, tA + 96u + 16u * (uint32_t)h, v);
         }
-        // Otherwise LayerNorm1 only feeds the FFN1 product with no dropout site in between, so it is folded into that
-        // product (W1 * gamma1 in the image): the UN-normalised row is the operand, the statistics wait in `red` for
-        // the FFN1 epilogue, and the exchange barrier merges with the product's own
-        store_half_f16(B0, row, h, v);
-      }
-
-      // ---- FFN: Linear(d -> F) + bias + ReLU (transformer.py:151-155); each half takes fp / 2 columns ----
-      gemm(0, wl + lay.off_w1, (int)lay.fp, 4);
-      {
-        const float* b1 = pl + 128;
-        const float* col_s = pl + 384;
-        const float* col_c = pl + 448;
-        float ln_mean = 0.f, ln_rstd = 1.f;
-        if (fold_ln1) {   // W1 LN(v) + b1 = rstd (v (W1 gamma)^T - mean col_s) + col_c
-          const float2 own = red[h * FROWS + row], other = red[(h ^ 1) * FROWS + row];
-          const float dm = own.x - other.x;
-          ln_mean = 0.5f * (own.x + other.x);
-          ln_rstd = rsqrtf((own.y + other.y + 16.0f * dm * dm) * (1.0f / FD) + a.ln_eps);
-        }
-        const uint32_t half_cols = lay.fp >> 1;   // multiple of 8
-        for (uint32_t c0 = half_cols * h; c0 < half_cols * (h + 1); c0 += 8) {
-          uint32_t r[8];
-          umma::tmem_ld8(tW + c0, r);
-          umma::tmem_ld_wait();
-          float hc[8];
+        product(PR_FFN1, l, -1);
+        {
+          const float* b1 = pl + P_B1;
+          const uint32_t half_cols = lay.fp >> 1;
+          for (uint32_t c0 = half_cols * h; c0 < half_cols * (h + 1); c0 += 8) {
+            uint32_t r[8];
+            umma::tmem_ld8(tA + 128u + c0, r);
+            umma::tmem_ld_wait();
+            uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            hc[i] = fold_ln1 ? fmaxf(fmaf(ln_rstd, fmaf(-ln_mean, col_s[c0 + i], __uint_as_float(r[i])), col_c[c0 + i]), 0.f)
-                             : fmaxf(__uint_as_float(r[i]) + b1[c0 + i], 0.f);
-          uint4 w;
-          w.x = umma::pack_f16x2(hc[0], hc[1]); w.y = umma::pack_f16x2(hc[2], hc[3]);
-          w.z = umma::pack_f16x2(hc[4], hc[5]); w.w = umma::pack_f16x2(hc[6], hc[7]);
-          *reinterpret_cast<uint4*>(B1 + umma::sw128_offset(row, c0 >> 3)) = w;
+            for (int i = 0; i < 4; ++i)
+              umma::split_f16x2(fmaxf(__uint_as_float(r[2 * i]) + b1[c0 + 2 * i], 0.f),
+                                fmaxf(__uint_as_float(r[2 * i + 1]) + b1[c0 + 2 * i + 1], 0.f), hi[i], lo[i]);
+            umma::tmem_st4(t_h + (c0 >> 1), hi);
+            umma::tmem_st4(t_h + 32u + (c0 >> 1), lo);
+          }
         }
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
-      gemm(1, wl + lay.off_w2, FD, (int)(lay.fp >> 4));
+      product(PR_FFN2, l, -1, prune);   // last layer: the Q tile is dead now and receives the vocabulary head
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (!FAST && (fl & BFB200_SITE_LAYER_OUT)) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
         float v[HW];
-        tmem_load_half(tW + h * HW, v);
-        const float* b2 = pl + 192 + h * HW;
+        tmem_load_half(tA + h * HW, v);
+        const float* b2 = pl + P_B2 + h * HW;
 #pragma unroll
         for (int i = 0; i < HW; ++i) v[i] += b2[i];
         if (fl & BFB200_SITE_FFN_RESID) drop_half(v, k_resid, ms.scale);
-        {
-          float x[HW];
-          tmem_load_half(tX, x);
-#pragma unroll
-          for (int i = 0; i < HW; ++i) v[i] += x[i];
-        }
+        add_residual_half(tXh, tXl, v);
         const float2 own = ln_partial(v);
         red[h * FROWS + row] = own;
         umma::group_sync(bar_id, FGROUP_THREADS);
-        ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + 256 + h * HW, pl + 320 + h * HW, a.ln_eps);
+        ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + P_LN2W + h * HW, pl + P_LN2B + h * HW, a.ln_eps);
         if (FAST == 1) drop_half_direct(v, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);   // transformer.py:370
         else if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);
-        if (!prune) tmem_store_half(tX, v);
-        store_half_f16(B0, row, h, v);
+        store_hilo_half(tXh, tXl, v);   // next block's input / the vocabulary head's operand
       }
     }
 
     // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
-    gemm(0, img_u32 + lay.off_head, FMAXV, 4);
+    product(PR_HEAD, 0, -1);
     const int stage_stride = FMAXV + a.tps;
-    float* stage = reinterpret_cast<float*>(B1);  // B1 + B2: 32 KB (K / V / FFN hidden are dead)
+    float* stage = reinterpret_cast<float*>(TK);  // K + L tiles: 32 KB (dead between the last W_out product and the next QKV product)
     {
-      const float* hb = params + a.n_layers * PARAMS_PER_LAYER;
       const bool is_last = row_valid && pos == len - 1;
+      const int V = a.vocab;
       for (uint32_t c0 = 64u * h; c0 < 64u * h + 64u; c0 += 16) {
         uint32_t r[16];
-        umma::tmem_ld16(tW + c0, r);
+        umma::tmem_ld16(tA + c0, r);
         umma::tmem_ld_wait();
         if (is_last) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) stage[seq_l * stage_stride + c0 + i] = __uint_as_float(r[i]) + hb[c0 + i];
+          for (int i = 0; i < 16; ++i) {
+            const int c = (int)c0 + i;   // classes >= V: -inf, they vanish from every softmax
+            stage[seq_l * stage_stride + c] = c < V ? __uint_as_float(r[i]) + __ldg(a.head_b + c) : -INFINITY;
+          }
         }
       }
     }
@@ -938,14 +1154,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   if ((gt & 31) == 5) {
     atomicAdd(&bfb_fused_dbg[0], (unsigned long long)dbg[0]);
     atomicAdd(&bfb_fused_dbg[1], (unsigned long long)dbg[1]);
-    atomicAdd(&bfb_fused_dbg[2], (unsigned long long)dbg[2]);
     atomicAdd(&bfb_fused_dbg[3], (unsigned long long)(clock64() - t_begin));
     atomicAdd(&bfb_fused_dbg[4], 1ull);
-  }
-  if (gt == 0) {
-    atomicAdd(&bfb_fused_dbg[5], (unsigned long long)dbi[0]);
-    atomicAdd(&bfb_fused_dbg[6], (unsigned long long)dbi[1]);
-    atomicAdd(&bfb_fused_dbg[7], (unsigned long long)dbi[2]);
   }
 #endif
   umma::tc_fence_before_sync();
@@ -973,20 +1183,21 @@ extern "C" int bfb200_debug_fused_timing(unsigned long long* out8, int reset) {
 bool fused_supported(const bfb200_transformer& m) {
   if (m.d_model != FD || m.n_heads != FH || m.n_layers < 1) return false;
   if (m.d_ff < 1 || m.d_ff > 64 || m.ntoken < 2 || m.ntoken > FMAXV) return false;
-  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
-  return fused_smem_bytes(lay) + kFusedStaticSlack <= 227 * 1024;
+  // tiles + weight image + the worst-case alignment pad must fit the 227 KB a CTA can have
+  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.site_flags);
+  return fused_smem_bytes(lay) + 1024 <= kFusedSmemMax;
 }
 
 size_t fused_image_bytes(const bfb200_transformer& m) {
-  return fused_supported(m) ? fused_layout(m.n_layers, m.d_ff, m.ntoken).image_bytes : 0;
+  return fused_supported(m) ? fused_layout(m.n_layers, m.d_ff, m.site_flags).total_bytes : 0;
 }
 
 int fused_pack(const bfb200_transformer& m, void* image, size_t bytes, cudaStream_t st) {
   BFB_REQUIRE(fused_supported(m), BFB200_ERR_UNSUPPORTED, "model shape is outside the fused kernel's class");
-  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
-  BFB_REQUIRE(bytes >= lay.image_bytes, BFB200_ERR_WORKSPACE, "fused image buffer too small: %zu < %u", bytes,
-              lay.image_bytes);
-  cudaError_t e = cudaMemsetAsync(image, 0, lay.image_bytes, st);
+  const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.site_flags);
+  BFB_REQUIRE(bytes >= lay.total_bytes, BFB200_ERR_WORKSPACE, "fused image buffer too small: %zu < %u", bytes,
+              lay.total_bytes);
+  cudaError_t e = cudaMemsetAsync(image, 0, lay.total_bytes, st);
   BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
   fused_pack_kernel<<<64, 256, 0, st>>>(m, lay, (uint8_t*)image);
   BFB_LAUNCH_CHECK("fused_pack_kernel", st);
@@ -999,34 +1210,33 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   BFB_REQUIRE(m.fused_image != nullptr, BFB200_ERR_INVALID_ARG, "compute=f16 needs model.fused_image (bfb200_fused_pack)");
   BFB_REQUIRE(len >= 1 && len <= FMAXLEN, BFB200_ERR_UNSUPPORTED, "fused kernel takes sequences of 1..%d tokens (got %d)",
               FMAXLEN, len);
+  BFB_REQUIRE(len <= m.pe_len, BFB200_ERR_INVALID_ARG, "sequence length %d exceeds the positional table (%d)", len, m.pe_len);
+  BFB_REQUIRE(n_seq >= 0 && n_seq < ((int64_t)1 << 31), BFB200_ERR_UNSUPPORTED,
+              "fused kernel takes fewer than 2^31 sequences per launch (got %lld): use a smaller workspace chunk", (long long)n_seq);
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.image = (const uint8_t*)m.fused_image;
   a.embedding = m.embedding;
-  a.lay = fused_layout(m.n_layers, m.d_ff, m.ntoken);
+  a.pe = m.pe;
+  a.head_b = m.head_b;
+  a.lay = fused_layout(m.n_layers, m.d_ff, m.site_flags);
   a.n_layers = m.n_layers; a.d_ff = m.d_ff; a.vocab = m.ntoken;
   a.site_flags = m.site_flags;
   a.ln_eps = m.ln_eps;
   a.len = len;
   a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 8 threads
   a.tps = (FGROUP_THREADS / a.spt) >= 16 ? 16 : 8;
-  {   // balanced two-way split of the queries 0..len-1 with weights t + 1 (exhaustive, cached per length)
-    static uint32_t cache[17] = {0};
-    static bool have[17] = {false};
+  {   // balanced two-way split of the queries 0..len-1 with weights t + 1 (exhaustive)
     const int n = len < 16 ? len : 16;
-    if (!have[n]) {
-      uint32_t best = 0xAAAAAAAAu;
-      int best_max = 1 << 30;
-      for (uint32_t m = 0; m < (1u << n); ++m) {
-        int s1 = 0, s0 = 0;
-        for (int t = 0; t < n; ++t) ((m >> t) & 1u ? s1 : s0) += t + 1;
-        const int mx = s1 > s0 ? s1 : s0;
-        if (mx < best_max) { best_max = mx; best = m; }
-      }
-      cache[n] = best;
-      have[n] = true;
+    uint32_t best = 0xAAAAAAAAu;
+    int best_max = 1 << 30;
+    for (uint32_t mm = 0; mm < (1u << n); ++mm) {
+      int s1 = 0, s0 = 0;
+      for (int t = 0; t < n; ++t) ((mm >> t) & 1u ? s1 : s0) += t + 1;
+      const int mx = s1 > s0 ? s1 : s0;
+      if (mx < best_max) { best_max = mx; best = mm; }
     }
-    a.qsplit = cache[n];
+    a.qsplit = best;
   }
   a.n_seq = n_seq;
   a.n_tiles = (n_seq + a.spt - 1) / a.spt;
@@ -1034,14 +1244,13 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   a.scheme = scheme; a.mode = mode; a.temperature = temperature;
   a.forced = forced; a.seq_scores = seq_scores; a.logp_out = logp_out;
   a.ms = ms;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  const size_t smem = fused_smem_bytes(a.lay);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  size_t smem = fused_smem_bytes(a.lay) + 1024;
+  if (smem > kFusedSmemMax) smem = kFusedSmemMax;
+  a.smem_bytes = (uint32_t)smem;
   int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
@@ -1062,7 +1271,7 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
     else if (fast == 3) FUSED_LAUNCH_F(ML, 3); \
     else FUSED_LAUNCH_F(ML, 0);           \
   } while (0)
-  // the pair phase keeps a sequence's K and V rows in registers: one instantiation per length up to 8 (the decode steps
+  // the pair phase keeps a sequence's K rows in registers: one instantiation per length up to 8 (the decode steps
   // of the reference's addition task run at lengths 4..8), so that the arrays are exactly as long as the sequences
   if (len <= 4) FUSED_LAUNCH(4);
   else if (len == 5) FUSED_LAUNCH(5);

@@ -112,6 +112,18 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : the "TS" form — the A operand (16-bit, two K elements per 32-bit column, lane =
+// row) is read from tensor memory, where the threads that produced it left it with tcgen05.st.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -156,6 +168,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -208,6 +232,33 @@ BFB_FH(fh_hh, "ah", "bh")
 BFB_FH(fh_lh, "al", "bh")
 BFB_FH(fh_hl, "ah", "bl")
 #undef BFB_FH
+
+// fp32 pair -> fp16 hi + fp16 lo words (a in the low halves): hi = fp16(v) (saturating), lo = fp16(v - hi); v = hi + lo
+// to 2^-22 relative.  The residuals come from one mixed-precision FMA each (hi * -1 + v, exact in fp32).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2(a, b);
+  constexpr uint32_t kNegOne = 0xBC00BC00u;
+  lo = pack_f16x2(fh_ll(hi, kNegOne, a), fh_hl(hi, kNegOne, b));
+}
+// acc += float(half `HI` of hi) + float(same half of lo)
+__device__ __forceinline__ float add_hilo_l(uint32_t hi, uint32_t lo, float acc) {
+  constexpr uint32_t kOne = 0x3C003C00u;
+  return fh_ll(lo, kOne, fh_ll(hi, kOne, acc));
+}
+__device__ __forceinline__ float add_hilo_h(uint32_t hi, uint32_t lo, float acc) {
+  constexpr uint32_t kOne = 0x3C003C00u;
+  return fh_hl(lo, kOne, fh_hl(hi, kOne, acc));
+}
+// two fp32 -> two e5m2 bytes (a in the low byte), round to nearest, saturating; and four e5m2 bytes -> two f16x2
+// words (e5m2 is the upper byte of the fp16 with the same value, so the widening is a byte permute)
+__device__ __forceinline__ uint32_t pack_e5m2x2(float a, float b) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t e5m2x4_to_f16x2_lo(uint32_t w) { return __byte_perm(w, 0u, 0x1404u); }
+__device__ __forceinline__ uint32_t e5m2x4_to_f16x2_hi(uint32_t w) { return __byte_perm(w, 0u, 0x3424u); }
+
 
 }  // namespace umma
 }  // namespace bfb

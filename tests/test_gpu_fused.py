@@ -237,7 +237,7 @@ def test_fused_other_model_shapes(engine, dev):
     """F = 64 (four K steps in the second FFN product), V = 67 (Shakespeare alphabet), one and two layers."""
     from bayesformer_b200.model.transformer import MyTransformer
 
-    for (V, F, L) in ((67, 64, 1), (128, 24, 2), (20, 8, 2)):
+    for (V, F, L) in ((67, 64, 1), (128, 16, 2), (20, 8, 2)):
         torch.manual_seed(V + F)
         model = MyTransformer(V, 64, 8, F, L, bayes_dropout=0.3, bayes=True).eval().to(dev)
         prompts = torch.randint(0, V, (5, 100), device=dev)
