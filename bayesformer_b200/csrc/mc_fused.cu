@@ -33,6 +33,8 @@
 //
 // Reference arithmetic: src/model/transformer.py:349-375 (forward), :211-234 (block), :37-65 (head),
 // :151-170 (FFN); src/libs/active_learning.py:62-68 / :103-112 / :146-152 (per-step scoring).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "umma.cuh"
@@ -62,6 +64,9 @@ constexpr uint32_t HEAD_BYTES = FMAXV * 128;  // vocabulary head: streamed per t
 constexpr uint32_t C_XHI = 0, C_XLO = 32, C_ACC = 64;
 constexpr size_t kFusedSmemMax = 227 * 1024;
 constexpr uint32_t kBarrierBytes = 64;
+#ifndef BFB_PAIR_SPLIT
+#define BFB_PAIR_SPLIT 1   // 0: one lane per (sequence, head) at every length (fewest instructions, half the lanes idle at 8 tokens)
+#endif
 constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)FGROUPS * VLO_BYTES;
 
 struct FusedLayout {
@@ -77,6 +82,7 @@ struct FusedLayout {
   uint32_t params_per_layer;
   uint32_t smem_image_bytes;   // what the kernel keeps in shared memory
   uint32_t off_head;      // absolute (global memory only from here on): vocabulary head, HEAD_BYTES
+  uint32_t off_headb;     // absolute: FMAXV fp32 head biases, -inf beyond the vocabulary (padded classes vanish from every softmax)
   uint32_t off_wlo;       // absolute: n_layers x WLO_BYTES
   uint32_t total_bytes;
 };
@@ -101,7 +107,8 @@ __host__ __device__ inline FusedLayout fused_layout(int L, int F, uint32_t site_
   lay.params_per_layer = lay.merged ? P_COLS + 2 * lay.fp : P_B1 + lay.fp;
   lay.smem_image_bytes = (lay.off_params + (uint32_t)L * lay.params_per_layer * 4 + 15u) & ~15u;
   lay.off_head = (lay.smem_image_bytes + 1023u) & ~1023u;
-  lay.off_wlo = lay.off_head + HEAD_BYTES;
+  lay.off_headb = lay.off_head + HEAD_BYTES;
+  lay.off_wlo = lay.off_headb + 1024u;
   lay.total_bytes = lay.off_wlo + (uint32_t)L * WLO_BYTES;
   return lay;
 }
@@ -124,6 +131,8 @@ __global__ void fused_pack_kernel(bfb200_transformer m, FusedLayout lay, uint8_t
   const int per_layer = n_qkv + n_out + n_m + n_w1 + n_w2 + n_lo;
   const int n_mat = L * per_layer + V * FD;
   const int n_par = L * (int)lay.params_per_layer;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FMAXV; i += gridDim.x * blockDim.x)
+    reinterpret_cast<float*>(image + lay.off_headb)[i] = i < V ? m.head_b[i] : -INFINITY;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mat + n_par; i += gridDim.x * blockDim.x) {
     if (i < n_mat) {
       float w;
@@ -198,7 +207,6 @@ struct FusedArgs {
   const uint8_t* image;
   const float* embedding;      // (V, 64) fp32
   const float* pe;             // (pe_len, 64) fp32
-  const float* head_b;         // (V) fp32
   FusedLayout lay;
   int n_layers, d_ff, vocab;
   uint32_t site_flags;
@@ -319,11 +327,10 @@ __device__ __forceinline__ void pv_finish(float (&o)[8], const uint32_t (&c2)[4]
     o[2 * i + 1] = fh_hl(c2[i], kOneOne, o[2 * i + 1]) * inv_z;
   }
 }
-// shared-memory offset of V's 8-bit remainders of (row, head): rows of 64 bytes, 16-byte pieces rotated so that the
-// 128-bit stores of eight consecutive rows hit eight different bank groups
-__device__ __forceinline__ uint32_t vlo_offset(uint32_t row, uint32_t head) {
-  return row * 64u + ((((head >> 1) ^ (row >> 1)) & 3u) << 4) + ((head & 1u) << 3);
-}
+// V's 8-bit remainders of (row, head) sit at HALF the byte offset of the (row, head) chunk in a swizzled fp16 tile
+// (rows of 64 bytes, 8-byte pieces permuted by row & 7: conflict-free for the stores of consecutive rows and the loads
+// of consecutive heads), so one offset per key row addresses V, its remainders and K.
+__device__ __forceinline__ uint32_t vlo_offset(uint32_t row, uint32_t head) { return umma::sw128_offset(row, head) >> 1; }
 __device__ __forceinline__ float ex2_approx(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -590,6 +597,7 @@ __device__ unsigned long long bfb_fused_dbg[8];
 // 512 columns, so its base is column 0) and therefore lives in uniform registers.
 // ------------------------------------------------------------------------------------------
 enum { PR_QKV = 0, PR_MERGED, PR_WOUT, PR_FFN1, PR_FFN2, PR_HEAD };
+template <int K> struct KindC { static constexpr int value = K; };
 
 struct IssueCtx {
   uint32_t tiles_u32;   // shared-memory address of group 0's first tile
@@ -602,8 +610,8 @@ struct IssueCtx {
   uint32_t off_om, off_w1, off_w2, layer_bytes;
 };
 
-template <int G>
-__device__ __forceinline__ void fused_issue(const IssueCtx& c, int kind, int layer, uint64_t* group_bar) {
+template <int G, int kind>
+__device__ __forceinline__ void fused_issue(const IssueCtx c, int layer, uint64_t* group_bar) {
   const uint32_t tile0 = c.tiles_u32 + (uint32_t)(G * FTILES) * TILE_BYTES;
   const uint32_t gb = (uint32_t)G * 256u;       // TMEM window of the group
   const uint32_t wl = c.img_u32 + (uint32_t)layer * c.layer_bytes;
@@ -698,8 +706,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x;
-  const int g = tid / FGROUP_THREADS, gt = tid % FGROUP_THREADS;   // group, thread in group
-  const int h = gt >> 7, row = gt & 127;                           // feature half, token row
+  // group and feature half are warp-uniform; taking them from votes lets the compiler know (uniform datapath for the
+  // address arithmetic and the branches they steer)
+  const int g = __any_sync(0xffffffffu, tid >= FGROUP_THREADS) ? 1 : 0, gt = tid % FGROUP_THREADS;   // group, thread in group
+  const int h = __any_sync(0xffffffffu, (gt >> 7) != 0) ? 1 : 0, row = gt & 127;                     // feature half, token row
   const int gw = row >> 5;                                         // TMEM lane quarter (= CTA warp % 4)
   uint8_t* TQ = smem + (uint32_t)(g * FTILES + T_Q) * TILE_BYTES;
   uint8_t* TK = smem + (uint32_t)(g * FTILES + T_K) * TILE_BYTES;
@@ -746,6 +756,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   uint64_t* bar = &bar_group[g];
   uint32_t phase = 0, wlo_phase = 0, head_phase = 0;
   const int bar_id = 1 + g;
+  // LayerNorm exchanges only couple the two threads of a row (warps w and w + 4 of the group): a 64-thread named barrier
+  // per warp pair instead of the group barrier (ids 3..10)
+  const int pair_bar_id = 3 + 4 * g + gw;
 
   const int len = a.len, spt = a.spt;
   // rows are position-major inside a tile (row = pos * spt + sequence): the rows of the LAST position, the only
@@ -753,7 +766,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   // work whose results nothing reads (see `live` below)
   const int pos = row / spt, seq_l = row - pos * spt;
   const int last_lo = (len - 1) * spt, last_hi = len * spt - 1;              // rows of the last position
-  const bool warp_has_last = (row & ~31) <= last_hi && (row | 31) >= last_lo;   // warp-uniform
+  // does this warp hold a row of the last position?  A vote rather than range arithmetic on the warp's rows: the compiler
+  // then KNOWS the flag is warp-uniform, and the branches it steers (which contain MMA issue code) stay convergent
+  const bool warp_has_last = __any_sync(0xffffffffu, row >= last_lo && row <= last_hi);
   const float sqrt_d = sqrtf((float)FD);
   const float qk_scale_log2e = 1.4426950408889634f / sqrtf((float)FDH);   // scores / sqrt(dh), in base-2 exponent units
   const uint32_t fl = a.site_flags;
@@ -776,7 +791,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   // next_wlo >= 0: the V tiles are dead from here on, so the issuing thread starts the bulk copies of that layer's
   // W_qkv lo rows into them (consumed by the next PR_QKV product, which waits for them).  stage_head: likewise the Q
   // tile is dead and receives the vocabulary head's weights (consumed by PR_HEAD).
-  auto product = [&](int kind, int layer, int next_wlo, bool stage_head = false) {
+  auto product = [&](auto kind_c, int layer, int next_wlo, bool stage_head = false) {
+    constexpr int kind = decltype(kind_c)::value;
 #ifdef BFB_FUSED_TIMING
     const long long _t0 = clock64();
 #endif
@@ -785,7 +801,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     umma::tmem_st_wait();
     umma::tc_fence_before_sync();
     umma::group_sync(bar_id, FGROUP_THREADS);
-    if (gt == 0) {
+    if (((tid >> 5) & 7) == 0) {   // warp 0 of the group (warp-uniform), then one lane: keeps the operand arithmetic on the uniform datapath
+     if ((tid & 31) == 0) {
       umma::tc_fence_after_sync();
       if (next_wlo >= 0) stream_wlo(next_wlo);
       if (stage_head) {
@@ -794,8 +811,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
       if (kind == PR_QKV) umma::mbar_wait(&bar_wlo[g], wlo_phase);
       if (kind == PR_HEAD) umma::mbar_wait(&bar_head[g], head_phase);
-      if (g == 0) fused_issue<0>(ic, kind, layer, &bar_group[0]);
-      else        fused_issue<1>(ic, kind, layer, &bar_group[1]);
+      if (g == 0) fused_issue<0, kind>(ic, layer, &bar_group[0]);
+      else        fused_issue<1, kind>(ic, layer, &bar_group[1]);
+     }
     }
     if (kind == PR_QKV) wlo_phase ^= 1u;
     if (kind == PR_HEAD) head_phase ^= 1u;
@@ -852,11 +870,11 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       const int next_wlo = !prune ? l + 1 : (more_tiles ? 0 : -1);
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
-      product(PR_QKV, l, -1);
+      product(KindC<PR_QKV>{}, l, -1);
       // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 tiles, and their fp16 rounding remainders
       // as e5m2 bytes: Q and K in the L tile (chunk of (row, head): 8 bytes of Q, 8 of K), V in the V-remainder tile.
       // This half takes heads [4h, 4h + 4) of each matrix, 16 columns = 2 heads per trip.
-#pragma unroll 1
+#pragma unroll 1   // rolled on purpose: the kernel is instruction-fetch sensitive (measured: unrolled 44.9 ms per pass, rolled 44.1)
       for (uint32_t trip = 0; trip < 6; ++trip) {
         const uint32_t mat = trip >> 1;                                  // 0 Q, 1 K, 2 V
         const uint32_t c0 = 64u * mat + 32u * (uint32_t)h + 16u * (trip & 1u);
@@ -880,7 +898,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch) + 8u * mat) = make_uint2(lo8.x, lo8.y);
           *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch + 1) + 8u * mat) = make_uint2(lo8.z, lo8.w);
         } else {
-          *reinterpret_cast<uint4*>(TVL + vlo_offset(row, ch)) = lo8;   // heads ch (even) and ch + 1 share a 16-byte piece
+          *reinterpret_cast<uint2*>(TVL + vlo_offset(row, ch)) = make_uint2(lo8.x, lo8.y);
+          *reinterpret_cast<uint2*>(TVL + vlo_offset(row, ch + 1)) = make_uint2(lo8.z, lo8.w);
         }
       }
       umma::tc_fence_before_sync();
@@ -921,7 +940,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
             const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
             const uint32_t pw = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
             pv_step<false>(ph, pw, *reinterpret_cast<const uint4*>(TV + koff),
-                           widen_lo8(*reinterpret_cast<const uint2*>(TVL + vlo_offset(row0 + j * spt, hd))), o, c2);
+                           widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff >> 1))), o, c2);
           }
           pv_finish(o, c2, __fdividef(1.0f, z));
           if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
@@ -936,43 +955,56 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           *reinterpret_cast<uint4*>(TQ + qoff) = w;   // in place: other items read only K / V rows, never this Q chunk
         }
       } else {
-        // short sequences: work item = (sequence, head[, query parity]), K (fp16 + 8-bit remainders) held in registers
+        // short sequences: work item = (sequence, head[, query parity]), K (fp16 + 8-bit remainders) held in registers.
+        // With NSPLIT = 2 (eight tokens and more: at most 128 pairs for 256 threads) two adjacent lanes share a pair and
+        // walk its queries in lock step, round i taking queries len - 1 - 2 i and len - 2 - 2 i: the rounds shrink
+        // together (8 + 6 + 4 + 2 key visits instead of 36) and no lane waits in a branch the other one took.  In the
+        // last layer only the last query is live (one lane per pair).
+        constexpr int NSPLIT = (MAXLEN >= 8 && BFB_PAIR_SPLIT) ? 2 : 1;
+        constexpr int NQ = (MAXLEN + NSPLIT - 1) / NSPLIT;
         const int npairs = nseq * FH;
-        // few pairs: two threads share one, queries split so that both walk about the same number of keys (query t
-        // costs t + 1 key visits; a.qsplit is the balanced assignment); in the last layer only the last query is live
-        const int nsplit = (!prune && npairs * 2 <= FGROUP_THREADS) ? 2 : 1;
-        if (gt < npairs * nsplit) {   // at most one work item per thread: npairs <= 256, and two threads share a pair only below 128
-          const int it = gt;
-          const int p = nsplit == 2 ? it >> 1 : it;
-          const int qpar = nsplit == 2 ? (it & 1) : -1;
+        const bool split = NSPLIT == 2 && !prune;
+        if (gt < (split ? 2 * npairs : npairs)) {   // at most one work item per thread
+          const int p = split ? gt >> 1 : gt;
+          const int qpar = split ? (gt & 1) : 0;
           const int sl = p >> 3, hd = p & 7;
           const uint32_t row0 = (uint32_t)sl;   // row of (sequence sl, position j) = j * spt + sl
           uint4 kp[MAXLEN];
           uint2 kl[MAXLEN];
+          uint32_t koff[MAXLEN];   // chunk offset of (key row j, head): addresses K, its remainders, V and (halved) V's remainders
 #pragma unroll
           for (int j = 0; j < MAXLEN; ++j) {
             if (j < len) {
-              const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
-              kp[j] = *reinterpret_cast<const uint4*>(TK + koff);
-              kl[j] = *reinterpret_cast<const uint2*>(TL + koff + 8u);
+              koff[j] = umma::sw128_offset(row0 + j * spt, hd);
+              kp[j] = *reinterpret_cast<const uint4*>(TK + koff[j]);
+              kl[j] = *reinterpret_cast<const uint2*>(TL + koff[j] + 8u);
             }
           }
-          // every K remainder is in registers (of both threads of a split pair) before any chunk of the L tile is
+          // every K remainder is in registers (of both lanes of a split pair) before any chunk of the L tile is
           // overwritten with an attention-output lo part below
           __syncwarp(__activemask());
           const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
 #pragma unroll
-          for (int t = 0; t < MAXLEN; ++t) {
-            if (t < len && (qpar < 0 || (int)((a.qsplit >> t) & 1u) == qpar) && (!prune || t == len - 1)) {
-              const uint32_t qoff = umma::sw128_offset(row0 + t * spt, hd);
+          for (int i = 0; i < NQ; ++i) {
+            constexpr int kStep = NSPLIT;
+            const int jmax = MAXLEN - 1 - kStep * i;              // compile-time bound on this round's query position
+            if (i == 0 || !prune) {                               // warp-uniform
+              const int t_raw = len - 1 - (split ? 2 * i + qpar : i);
+              const bool act = t_raw >= 0;
+              const int t = act ? t_raw : 0;
+              uint32_t qoff = koff[0];
+#pragma unroll
+              for (int j = 1; j < MAXLEN; ++j) qoff = j == t ? koff[j] : qoff;   // (register select: keeps koff[] out of local memory)
               const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
               const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
               float sc[MAXLEN];
               float mx = -INFINITY;
 #pragma unroll
-              for (int j = 0; j <= t; ++j) {
-                sc[j] = score_hilo(qw, ql, kp[j], widen_lo8(kl[j]));
-                mx = fmaxf(mx, sc[j]);
+              for (int j = 0; j < MAXLEN; ++j) {
+                if (j <= jmax) {
+                  sc[j] = j <= t ? score_hilo(qw, ql, kp[j], widen_lo8(kl[j])) : -INFINITY;
+                  mx = fmaxf(mx, sc[j]);
+                }
               }
               // softmax weights e_j = exp((s_j - max) / sqrt(dh)) in fp32, handed to the fp16-operand PV product as
               // a (high, low) pair of halves: e_j = hi_j + lo_j to 2^-22, so the product keeps fp32 weights
@@ -980,22 +1012,26 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
               uint32_t ph[(MAXLEN + 1) / 2], pw[(MAXLEN + 1) / 2];
               float z = 0.f;
 #pragma unroll
-              for (int j = 0; j <= t; j += 2) {
-                const float e0 = ex2_approx(fmaf(sc[j], qk_scale_log2e, nmx));
-                const float e1 = j + 1 <= t ? ex2_approx(fmaf(sc[j + 1], qk_scale_log2e, nmx)) : 0.f;
-                z += e0 + e1;
-                ph[j >> 1] = umma::pack_f16x2(e0, e1);
-                const float2 hi = umma::unpack_f16x2(ph[j >> 1]);
-                pw[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
+              for (int j = 0; j < MAXLEN; j += 2) {
+                if (j <= jmax) {
+                  const float e0 = ex2_approx(fmaf(sc[j], qk_scale_log2e, nmx));     // masked keys: exp2(-inf) = 0
+                  const float e1 = j + 1 <= jmax ? ex2_approx(fmaf(sc[j + 1], qk_scale_log2e, nmx)) : 0.f;
+                  z += e0 + e1;
+                  ph[j >> 1] = umma::pack_f16x2(e0, e1);
+                  const float2 hi = umma::unpack_f16x2(ph[j >> 1]);
+                  pw[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
+                }
               }
               float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               uint32_t c2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-              for (int j = 0; j <= t; ++j) {
-                const uint4 vh = *reinterpret_cast<const uint4*>(TV + umma::sw128_offset(row0 + j * spt, hd));
-                const uint4 vl = widen_lo8(*reinterpret_cast<const uint2*>(TVL + vlo_offset(row0 + j * spt, hd)));
-                if (j & 1) pv_step<true>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
-                else       pv_step<false>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
+              for (int j = 0; j < MAXLEN; ++j) {
+                if (j <= jmax && j < len) {   // (a masked key has weight 0)
+                  const uint4 vh = *reinterpret_cast<const uint4*>(TV + koff[j]);
+                  const uint4 vl = widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff[j] >> 1)));
+                  if (j & 1) pv_step<true>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
+                  else       pv_step<false>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
+                }
               }
               pv_finish(o, c2, __fdividef(1.0f, z));
               if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
@@ -1003,44 +1039,45 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 #pragma unroll
                 for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
               }
-              // hi part over the query's Q chunk, lo part over its chunk of the L tile (both consumed above)
-              uint4 w, wl;
-              umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
-              umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
-              *reinterpret_cast<uint4*>(TQ + qoff) = w;
-              *reinterpret_cast<uint4*>(TL + qoff) = wl;
+              if (act) {
+                // hi part over the query's Q chunk, lo part over its chunk of the L tile (both consumed above)
+                uint4 w, wl;
+                umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
+                umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
+                *reinterpret_cast<uint4*>(TQ + qoff) = w;
+                *reinterpret_cast<uint4*>(TL + qoff) = wl;
+              }
             }
           }
         }
       }
 
       if (!live) {
-        // dead rows of the last layer: take part in the barriers of the products and the LayerNorm exchanges
-        // (thread 0 of the group still issues the MMAs inside product()), compute nothing
+        // dead rows of the last layer: take part in the barriers of the products (thread 0 of the group still issues
+        // the MMAs inside product()), compute nothing; the LayerNorm exchanges are per warp pair and both warps of a
+        // pair are dead together
         if (merged) {
-          product(PR_MERGED, l, next_wlo);
-          umma::group_sync(bar_id, FGROUP_THREADS);
+          product(KindC<PR_MERGED>{}, l, next_wlo);
         } else {
-          product(PR_WOUT, l, next_wlo);
-          umma::group_sync(bar_id, FGROUP_THREADS);
-          product(PR_FFN1, l, -1);
+          product(KindC<PR_WOUT>{}, l, next_wlo);
+          product(KindC<PR_FFN1>{}, l, -1);
         }
-        product(PR_FFN2, l, -1, prune);
-        umma::group_sync(bar_id, FGROUP_THREADS);
-        continue;
-      }
+        product(KindC<PR_FFN2>{}, l, -1, prune);
+      } else {
+      // (no `continue` above: a divergent loop-continue would make the layer counter look thread-dependent to the
+      // compiler, and every MMA operand derived from it would leave the uniform datapath)
 
       const uint32_t t_h = tA + (merged ? 128u : 64u);   // FFN hidden row as a TS operand: hi, lo at +32
       if (merged) {
         // ---- W_out and FFN1 in one product; residual from the block input; LayerNorm1 folded (transformer.py:125, :231-232) ----
-        product(PR_MERGED, l, next_wlo);
+        product(KindC<PR_MERGED>{}, l, next_wlo);
         {
           float v[HW];
           tmem_load_half(tA + h * HW, v);
           add_residual_half(tXh, tXl, v);
           red[h * FROWS + row] = ln_partial(v);
         }
-        umma::group_sync(bar_id, FGROUP_THREADS);
+        umma::group_sync(pair_bar_id, 64);   // the two half-row threads of a row sit in warps w and w + 4
         {
           // W1 LN1(v) + b1 = rstd (v (W1 g1)^T - mean col_s) + col_c, ReLU (transformer.py:151-155); each half takes fp / 2 columns
           float ln_mean, ln_rstd;
@@ -1065,7 +1102,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         }
       } else {
         // ---- W_out, residual from the block input, LayerNorm1 (transformer.py:125, :226, :231), then FFN1 ----
-        product(PR_WOUT, l, next_wlo);
+        product(KindC<PR_WOUT>{}, l, next_wlo);
         {
           const uint32_t k_attn = (fl & BFB200_SITE_ATTN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 1u, (uint32_t)h) : 0u;
           const uint32_t k_ffn_in = (fl & BFB200_SITE_FFN_IN) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 2u, (uint32_t)h) : 0u;
@@ -1075,12 +1112,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           add_residual_half(tXh, tXl, v);
           const float2 own = ln_partial(v);
           red[h * FROWS + row] = own;
-          umma::group_sync(bar_id, FGROUP_THREADS);
+          umma::group_sync(pair_bar_id, 64);   // the two half-row threads of a row sit in warps w and w + 4
           ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + P_LN1W + h * HW, pl + P_LN1B + h * HW, a.ln_eps);
           if (fl & BFB200_SITE_FFN_IN) drop_half(v, k_ffn_in, ms.scale);
           store_hilo_half(tA + 64u + 16u * (uint32_t)h, tA + 96u + 16u * (uint32_t)h, v);
         }
-        product(PR_FFN1, l, -1);
+        product(KindC<PR_FFN1>{}, l, -1);
         {
           const float* b1 = pl + P_B1;
           const uint32_t half_cols = lay.fp >> 1;
@@ -1100,7 +1137,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
-      product(PR_FFN2, l, -1, prune);   // last layer: the Q tile is dead now and receives the vocabulary head
+      product(KindC<PR_FFN2>{}, l, -1, prune);   // last layer: the Q tile is dead now and receives the vocabulary head
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (!FAST && (fl & BFB200_SITE_LAYER_OUT)) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
@@ -1113,30 +1150,33 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         add_residual_half(tXh, tXl, v);
         const float2 own = ln_partial(v);
         red[h * FROWS + row] = own;
-        umma::group_sync(bar_id, FGROUP_THREADS);
+        umma::group_sync(pair_bar_id, 64);   // the two half-row threads of a row sit in warps w and w + 4
         ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + P_LN2W + h * HW, pl + P_LN2B + h * HW, a.ln_eps);
         if (FAST == 1) drop_half_direct(v, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);   // transformer.py:370
         else if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);
         store_hilo_half(tXh, tXl, v);   // next block's input / the vocabulary head's operand
       }
+      }   // live
     }
 
     // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
-    product(PR_HEAD, 0, -1);
+    product(KindC<PR_HEAD>{}, 0, -1);
     const int stage_stride = FMAXV + a.tps;
     float* stage = reinterpret_cast<float*>(TK);  // K + L tiles: 32 KB (dead between the last W_out product and the next QKV product)
     {
       const bool is_last = row_valid && pos == len - 1;
-      const int V = a.vocab;
+      const float4* hb = reinterpret_cast<const float4*>(a.image + lay.off_headb);   // classes >= V carry -inf
       for (uint32_t c0 = 64u * h; c0 < 64u * h + 64u; c0 += 16) {
         uint32_t r[16];
         umma::tmem_ld16(tA + c0, r);
         umma::tmem_ld_wait();
         if (is_last) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = (int)c0 + i;   // classes >= V: -inf, they vanish from every softmax
-            stage[seq_l * stage_stride + c] = c < V ? __uint_as_float(r[i]) + __ldg(a.head_b + c) : -INFINITY;
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(hb + (c0 >> 2) + i);
+            float* dstp = stage + seq_l * stage_stride + c0 + 4 * i;
+            dstp[0] = __uint_as_float(r[4 * i]) + b.x; dstp[1] = __uint_as_float(r[4 * i + 1]) + b.y;
+            dstp[2] = __uint_as_float(r[4 * i + 2]) + b.z; dstp[3] = __uint_as_float(r[4 * i + 3]) + b.w;
           }
         }
       }
@@ -1218,7 +1258,6 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   a.image = (const uint8_t*)m.fused_image;
   a.embedding = m.embedding;
   a.pe = m.pe;
-  a.head_b = m.head_b;
   a.lay = fused_layout(m.n_layers, m.d_ff, m.site_flags);
   a.n_layers = m.n_layers; a.d_ff = m.d_ff; a.vocab = m.ntoken;
   a.site_flags = m.site_flags;
@@ -1273,7 +1312,9 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   } while (0)
   // the pair phase keeps a sequence's K rows in registers: one instantiation per length up to 8 (the decode steps
   // of the reference's addition task run at lengths 4..8), so that the arrays are exactly as long as the sequences
-  if (len <= 4) FUSED_LAUNCH(4);
+  static const bool force_long = getenv("BFB200_FUSED_FORCE_LONG") != nullptr;   // experiment switch: streaming pair phase at every length
+  if (force_long) FUSED_LAUNCH(FMAXLEN);
+  else if (len <= 4) FUSED_LAUNCH(4);
   else if (len == 5) FUSED_LAUNCH(5);
   else if (len == 6) FUSED_LAUNCH(6);
   else if (len == 7) FUSED_LAUNCH(7);
