@@ -198,6 +198,68 @@ def scaled_c4(ref):
     print("scaled_c4.npz", logp.shape)
 
 
+def char_level_c1(ref):
+    """C1 shape (SURVEY 8d / BASELINE configs[0]): char-level model MyTransformer(67, 64, 8, 8, 2) over windows of the
+    reference's data/shakespeare.txt (32-character prompts, 4-character answers: sequences of 32..36 tokens), a few
+    epochs of the reference's own utils.train, then dropout_uncertainty with its masks recorded (B = 8, T = 6)."""
+    al, tr, pre, utils = ref.active_learning, ref.transformer, ref.preprocessing, ref.utils
+    constants = ref.constants
+    text = open(os.path.join(ref_shim.REFERENCE_ROOT, "data", "shakespeare.txt")).read()
+    chars = sorted(set(text))
+    assert len(chars) == 65  # SURVEY 0.1
+
+    class CharTok(ref.tokenizer.Tokenizer):   # 65 characters + PAD + EOS, the interface preprocessing.pad / get_batch use
+        def __init__(self):
+            self.vocab = chars + [constants.PAD_TOKEN, constants.EOS_TOKEN]
+            self.token_to_id = {c: i for i, c in enumerate(self.vocab)}
+            self.ntokens = len(self.vocab)
+
+        def encode(self, t):
+            return [self.token_to_id[c] for c in t]
+
+        def decode(self, ids):
+            return "".join(self.vocab[i] for i in ids)
+
+    tok = CharTok()
+    windows = [(text[36 * i: 36 * i + 32], text[36 * i + 32: 36 * i + 36]) for i in range(400)]
+    random.seed(42)
+    torch.manual_seed(42)
+    model = tr.MyTransformer(tok.ntokens, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True)
+    utils.train(model, windows[8:328], windows[328:392], 6, 32, 2e-3, tok.ntokens, tok, "cpu")
+    model.eval()
+    pool = windows[:8]
+    prompts, answers, P, A, _, _ = pre.get_batch(pool, tok, 0, len(pool))
+    N, T, B, L = A + 1, 6, prompts.shape[1], 2
+    assert (P, N) == (32, 5)
+    out = {"prompts": prompts.numpy(), "P": P, "N": N, "T": T, "p": 0.3, "chars": np.array([ord(c) for c in chars])}
+    out.update({"sd." + k: v for k, v in sd_to_np(model.state_dict()).items()})
+    with torch.no_grad():
+        log, logps = [], []
+        hook = capture_last_logp(model, logps)
+        torch.manual_seed(4321)
+        with ref_shim.record_dropout(log):
+            scores = al.dropout_uncertainty(model, prompts, N, "cpu", "entropy", T)
+        hook.remove()
+        assert len(log) == T * N * (1 + L)
+        live = np.zeros((N, 1 + L, B * T, P + N - 1, 2), dtype=np.uint32)
+        it = iter(log)
+        for draw in range(T):
+            for step in range(N):
+                for site in range(1 + L):
+                    keep = next(it).numpy()
+                    live[step, site, draw::T, : P + step, :] = R.pack_bits(np.transpose(keep, (1, 0, 2)))
+        out["dropout.keep_bits"] = live
+        lp = torch.stack(logps).view(T, N, B, -1)
+        out["dropout.logp"] = lp.numpy()
+        out["dropout.tokens"] = lp.argmax(-1).numpy().astype(np.int16)
+        out["dropout.scores.entropy"] = scores.numpy()
+        for mode in ("max", "margin"):
+            with ref_shim.replay_dropout(log):
+                out[f"dropout.scores.{mode}"] = al.dropout_uncertainty(model, prompts, N, "cpu", mode, T).numpy()
+    np.savez_compressed(os.path.join(OUT, "c1_char_level.npz"), **out)
+    print("c1_char_level.npz", {k: getattr(v, "shape", v) for k, v in out.items() if not k.startswith("sd.")})
+
+
 def classifiers(ref):
     bc, pc = ref.bayesian_classification, ref.preprocessing_classif
     X, _ = pc.get_data(256)
@@ -278,7 +340,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["transformer", "latent", "mid", "c4", "classifiers", "misc"]
+    which = sys.argv[1:] or ["transformer", "latent", "mid", "c4", "c1", "classifiers", "misc"]
     if "transformer" in which:
         main_transformer(ref)
     if "latent" in which:
@@ -287,6 +349,8 @@ def main():
         mid_model(ref)
     if "c4" in which:
         scaled_c4(ref)
+    if "c1" in which:
+        char_level_c1(ref)
     if "classifiers" in which:
         classifiers(ref)
     if "misc" in which:

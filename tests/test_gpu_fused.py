@@ -169,16 +169,15 @@ def _fused_vs_exact(engine, dev, model, prompts, N, T, scheme, mode, seed, rtol=
                                      (9, 4, 45, 5), (12, 5, 23, 3), (16, 1, 9, 2), (17, 3, 11, 3), (32, 5, 29, 4),
                                      (40, 1, 7, 2), (25, 6, 10, 5)])
 def test_fused_matches_exact_path_all_shapes(engine, dev, c2, P, N, B, T):
-    """Tile tails, 1..40-token sequences (all three kernel variants), every mode.  Uniformly random token prompts are
-    far outside the trained model's input distribution (flatter, less stable logits); fp16 operand rounding then
-    reaches 1-2 % on single probabilities and 2e-4 absolute on the smallest ones, so this structural test allows
-    2e-2 relative + 5e-4 absolute — the reference-data tests above hold the stated 1e-2."""
+    """Tile tails, 1..40-token sequences (all three kernel variants), every mode, uniformly random token prompts (far
+    outside the trained model's input distribution), at the stated bound: 1e-2 relative + 1e-4 absolute on every
+    probability (tools/fused_accuracy.py: the worst of 10^7 probabilities sits at 0.5 of it)."""
     z, sd = c2
     model = H.build_model(sd, float(z["p"]), True).to(dev)
     g = torch.Generator().manual_seed(P * 100 + N)
     prompts = torch.randint(0, 114, (P, B), generator=g).to(dev)
     for mode in H.MODES:
-        _fused_vs_exact(engine, dev, model, prompts, N, T, "dropout", mode, seed=1000 + P, rtol=2e-2, atol=5e-4)
+        _fused_vs_exact(engine, dev, model, prompts, N, T, "dropout", mode, seed=1000 + P)
 
 
 def test_fused_serves_the_char_level_configuration(engine, dev):
@@ -192,12 +191,33 @@ def test_fused_serves_the_char_level_configuration(engine, dev):
     prompts = torch.randint(0, 65, (32, 50), generator=torch.Generator().manual_seed(5)).to(dev)
     assert engine.scoring_pack(model.to(dev), dev, 32, 5, "auto").compute == "fp16"
     for mode in H.MODES:
-        _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 6, "dropout", mode, seed=4242, rtol=2e-2, atol=5e-4)
+        _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 6, "dropout", mode, seed=4242)
     for layer in model.layers:
         layer.bayes, layer.bayes_dropout = True, 0.3
         layer.ff.bayes_dropout = 0.3
         layer.self_attn.bayes, layer.self_attn.bayes_dropout = True, 0.3
-    _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 4, "sampling", "entropy", seed=77, rtol=2e-2, atol=5e-4)
+    _fused_vs_exact(engine, dev, model.to(dev), prompts, 5, 4, "sampling", "entropy", seed=77)
+
+
+@pytest.mark.parametrize("compute,rtol,atol", [("fp16", RTOL, ATOL_P), ("fp32", 1e-3, 1e-5)])
+@pytest.mark.parametrize("mode", H.MODES)
+def test_char_level_c1_with_reference_masks(engine, dev, mode, compute, rtol, atol):
+    """SURVEY C1 / BASELINE configs[0] against the REFERENCE itself: the char-level model (V = 67) on windows of
+    data/shakespeare.txt, sequences of 32..36 tokens, the reference's own dropout masks injected and its tokens forced
+    (tests/golden/c1_char_level.npz, recorded from the unmodified reference by oracle/make_golden.py)."""
+    z = H.load("c1_char_level.npz")
+    sd = H.state_dict_from(z)
+    N, T, L, p = int(z["N"]), int(z["T"]), 2, float(z["p"])
+    B = z["prompts"].shape[1]
+    bits = H.expand_live_bits(z["dropout.keep_bits"], L)
+    forced = torch.from_numpy(z["dropout.tokens"].astype(np.int64)).permute(1, 2, 0).reshape(N, B * T)
+    model = H.build_model(sd, p, True).to(dev)
+    res = engine.mc_score_transformer(model.native_pack(dev, compute), torch.from_numpy(z["prompts"]).to(dev), N, T,
+                                      "dropout", mode, mask_bits=_bits(bits, dev), mask_max_len=bits.shape[3],
+                                      forced_tokens=forced, return_logp=True)
+    np.testing.assert_allclose(res.step_scores.cpu().numpy(), z[f"dropout.scores.{mode}"], rtol=rtol, atol=ATOL_SCORE * rtol / RTOL)
+    lp = res.logp.cpu().view(N, B, T, -1).permute(2, 0, 1, 3).numpy()
+    _assert_probs_close(lp, z["dropout.logp"], rtol, atol)
 
 
 def test_fused_latent_sites_match_exact_path(engine, dev, c2):
@@ -315,7 +335,7 @@ def test_weight_updates_invalidate_the_packed_images(engine, dev, c2):
                                         return_tokens=True)
     forced = exact.tokens[:, 4:].t().contiguous()
     again = engine.mc_score_transformer(pack_after, prompts, N, 4, "dropout", "entropy", seed=5, forced_tokens=forced)
-    np.testing.assert_allclose(again.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=2e-2, atol=2e-3)
+    np.testing.assert_allclose(again.step_scores.cpu().numpy(), exact.step_scores.cpu().numpy(), rtol=RTOL, atol=ATOL_SCORE)
     # a deep copy (active_learning.ipynb cell 24) gets its own packs
     import copy
     clone = copy.deepcopy(model)

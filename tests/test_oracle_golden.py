@@ -115,3 +115,21 @@ def test_topk_rule_and_keys():
     assert order[:5].tolist() == [1, 2, 3, 4, 0]
     with pytest.raises(RuntimeError):
         R.topk_lowest_index(s, 9)
+
+
+@pytest.mark.parametrize("mode", H.MODES)
+def test_char_level_c1_scores_match_reference(mode):
+    """SURVEY C1 / BASELINE configs[0]: char-level model (V = 67), sequences of 32..36 tokens, the reference's own
+    masks (tests/golden/c1_char_level.npz, oracle/make_golden.py char_level_c1)."""
+    z = H.load("c1_char_level.npz")
+    sd = H.state_dict_from(z)
+    P, N, T, L, d = int(z["P"]), int(z["N"]), int(z["T"]), 2, 64
+    B = z["prompts"].shape[1]
+    pm = H.packed_masks_from_bits(H.expand_live_bits(z["dropout.keep_bits"], L), L, d)
+    forced = torch.from_numpy(z["dropout.tokens"].astype(np.int64)).permute(1, 2, 0).reshape(N, B * T)
+    out = R.mc_scores(sd, torch.from_numpy(z["prompts"]), N, T, "dropout", mode, float(z["p"]),
+                      lambda step: pm.mask_fn(step, R.default_live_sites(L, True)), forced_tokens=forced)
+    np.testing.assert_allclose(out["step_scores"].numpy(), z[f"dropout.scores.{mode}"], **TOL)
+    lp = out["logp"].view(N, B, T, -1).permute(2, 0, 1, 3)
+    np.testing.assert_allclose(lp.numpy(), z["dropout.logp"], rtol=2e-5, atol=2e-5)
+    assert np.array_equal(lp.argmax(-1).numpy(), z["dropout.tokens"].astype(np.int64))
