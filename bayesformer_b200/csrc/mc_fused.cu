@@ -50,7 +50,7 @@ constexpr int FROWS = 128;      // token rows per group tile (UMMA M)
 constexpr int FGROUPS = 2;      // independent groups per CTA, one tile of 128 token rows each
 constexpr int FGROUP_THREADS = 256;   // two threads per token row (32 features each)
 constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
-constexpr int FMAXLEN = 40;     // longest sequence the fused path takes
+constexpr int FMAXLEN = 128;    // longest sequence the fused path takes (one sequence per 128-row tile)
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
 // shared-memory tiles of a group: Q (then the attention output), K, the 8-bit remainders of Q and K, V (between the
@@ -64,9 +64,6 @@ constexpr uint32_t HEAD_BYTES = FMAXV * 128;  // vocabulary head: streamed per t
 constexpr uint32_t C_XHI = 0, C_XLO = 32, C_ACC = 64;
 constexpr size_t kFusedSmemMax = 227 * 1024;
 constexpr uint32_t kBarrierBytes = 64;
-#ifndef BFB_PAIR_SPLIT
-#define BFB_PAIR_SPLIT 1   // 0: one lane per (sequence, head) at every length (fewest instructions, half the lanes idle at 8 tokens)
-#endif
 constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)FGROUPS * VLO_BYTES;
 
 struct FusedLayout {
@@ -216,7 +213,6 @@ struct FusedArgs {
   int len;                     // tokens per sequence in this step
   int spt;                     // sequences per tile = 128 / len
   int tps;                     // score-phase threads per sequence (8 or 16)
-  uint32_t qsplit;             // pair phase with two threads per (sequence, head): bit t = which of them takes query t
   int64_t n_seq;               // sequences in the chunk
   int64_t n_tiles;
   const int32_t* tokens;       // (n_seq, tok_stride)
@@ -678,8 +674,8 @@ __device__ __forceinline__ void fused_issue(const IssueCtx c, int layer, uint64_
 // BayesFormer, or none for the standard Transformer; Philox masks, greedy decoding, no log-prob / forced-token side
 // channels): the latent-site, mask-injection, sampling and side-channel branches are compiled out instead of tested
 // at run time.
-template <int MAXLEN, int FAST>   // 0: everything at run time; 1: sites E + layer-out (BayesFormer); 2: no site (Transformer);
-                                  // 3: no site, temperature sampling (Transformer, sampling_uncertainty)
+template <int FAST>   // 0: everything at run time; 1: sites E + layer-out (BayesFormer); 2: no site (Transformer);
+                      // 3: no site, temperature sampling (Transformer, sampling_uncertainty)
 __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs a_in) {
   FusedArgs a = a_in;
   if (FAST) {
@@ -779,7 +775,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   ic.tiles_u32 = umma::smem_u32(smem);
   ic.img_u32 = umma::smem_u32(img);
   ic.fp = lay.fp; ic.merged = lay.merged; ic.w2_per_tile = lay.w2_per_tile; ic.w2_lo = lay.w2_lo;
-  ic.attn_lo = MAXLEN <= 16 ? 1u : 0u;
+  ic.attn_lo = 1u;
   ic.off_om = lay.off_om; ic.off_w1 = lay.off_w1; ic.off_w2 = lay.off_w2;
   ic.layer_bytes = lay.layer_bytes;
 
@@ -906,150 +902,86 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       umma::group_sync(bar_id, FGROUP_THREADS);
 
       // ---- causal attention (transformer.py:58-65) ----
-      if constexpr (MAXLEN > 16) {
-        // Long sequences (the char-level configuration: 32..36 tokens): work item = (query position, sequence, head),
-        // query-major so that the lanes of a warp walk (nearly) the same number of keys.  K and V rows are streamed
-        // from the fp16 tiles, two passes over the keys (row maximum, then weights and the PV sum): no per-key state
-        // survives in registers, whatever the length.
+      {
+        // Work item = (query position, sequence, head), query-major (the lanes of a warp walk the same number of keys),
+        // heaviest queries first; a tile holds at most 128 x 8 items, i.e. at most four per thread.  K, V and their
+        // remainders are streamed from shared memory in ONE pass over the keys: the softmax is taken relative to the first
+        // key's score instead of the row maximum (it is shift-invariant); in the rare case that a score exceeds the
+        // reference by more than 14 octaves the accumulators are rescaled and the reference moves, so the weights stay
+        // within fp16 range.  The loops are rolled on purpose (the kernel is instruction-fetch sensitive).
+        // The attention output's hi part overwrites the query's Q chunk in place; its lo part belongs in the L tile,
+        // whose chunks other items still read (K remainders), so it waits in registers for the barrier.
         const int npairs = nseq * FH;
-        const int nitems = prune ? npairs : npairs * len;
-        for (int it = gt; it < nitems; it += FGROUP_THREADS) {
-          const int t = prune ? len - 1 : it / npairs;
-          const int p = prune ? it : it - t * npairs;
-          const int sl = p >> 3, hd = p & 7;
-          const uint32_t row0 = (uint32_t)sl;
-          const uint32_t qoff = umma::sw128_offset(row0 + t * spt, hd);
-          const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
-          const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
-          float mx = -INFINITY;
-          for (int j = 0; j <= t; ++j) {
-            const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
-            mx = fmaxf(mx, score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
-                                      widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u))));
-          }
-          const float nmx = -mx * qk_scale_log2e;
-          float z = 0.f;
-          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          uint32_t c2[4] = {0u, 0u, 0u, 0u};
-          for (int j = 0; j <= t; ++j) {
-            const uint32_t koff = umma::sw128_offset(row0 + j * spt, hd);
-            const float sj = score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
-                                        widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u)));
-            const float e = ex2_approx(fmaf(sj, qk_scale_log2e, nmx));
-            z += e;
-            const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
-            const uint32_t pw = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
-            pv_step<false>(ph, pw, *reinterpret_cast<const uint4*>(TV + koff),
-                           widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff >> 1))), o, c2);
-          }
-          pv_finish(o, c2, __fdividef(1.0f, z));
-          if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
-            const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
-            const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
+        const int nq = prune ? 1 : len;                      // last layer: only the last query is live
+        const int nitems = npairs * nq;
+        const float inv_npairs = __fdividef(1.0f, (float)npairs);
+        uint4 lo_keep[4];
+        uint32_t lo_off[4];
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+          const int it = gt + u * FGROUP_THREADS;
+          uint4 wl = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t keep_off = 0xFFFFFFFFu;
+          if (it < nitems) {
+            int b = (int)(((float)it + 0.5f) * inv_npairs);  // query block = it / npairs (exact: it < 1024, npairs <= 256)
+            const int p = it - b * npairs;
+            const int b2 = b ^ ((b >> 1) & 1);               // blocks 2m, 2m + 1 swapped for odd m: the two halves of the
+            b = b2 < nq ? b2 : b;                            // group (items it and it + 128) get equal numbers of key visits
+            const int t = len - 1 - b;
+            const int sl = p >> 3, hd = p & 7;
+            const uint32_t qoff = umma::sw128_offset((uint32_t)(sl + t * spt), (uint32_t)hd);
+            const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
+            const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
+            float ref = 0.f, z = 0.f;
+            float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint32_t c2[4] = {0u, 0u, 0u, 0u};
+            uint32_t krow = (uint32_t)sl;
+#pragma unroll 1
+            for (int j = 0; j <= t; ++j, krow += (uint32_t)spt) {
+              const uint32_t koff = umma::sw128_offset(krow, (uint32_t)hd);
+              const float sj = score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
+                                          widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u)));
+              ref = j == 0 ? sj : ref;
+              float arg = (sj - ref) * qk_scale_log2e;
+              if (arg > 14.0f) {   // rare
+                const float f = ex2_approx(-arg);
+                const uint32_t f2 = umma::pack_f16x2(f, f);
+                z *= f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
-          }
-          uint4 w;
-          w.x = umma::pack_f16x2(o[0], o[1]); w.y = umma::pack_f16x2(o[2], o[3]);
-          w.z = umma::pack_f16x2(o[4], o[5]); w.w = umma::pack_f16x2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(TQ + qoff) = w;   // in place: other items read only K / V rows, never this Q chunk
-        }
-      } else {
-        // short sequences: work item = (sequence, head[, query parity]), K (fp16 + 8-bit remainders) held in registers.
-        // With NSPLIT = 2 (eight tokens and more: at most 128 pairs for 256 threads) two adjacent lanes share a pair and
-        // walk its queries in lock step, round i taking queries len - 1 - 2 i and len - 2 - 2 i: the rounds shrink
-        // together (8 + 6 + 4 + 2 key visits instead of 36) and no lane waits in a branch the other one took.  In the
-        // last layer only the last query is live (one lane per pair).
-        constexpr int NSPLIT = (MAXLEN >= 8 && BFB_PAIR_SPLIT) ? 2 : 1;
-        constexpr int NQ = (MAXLEN + NSPLIT - 1) / NSPLIT;
-        const int npairs = nseq * FH;
-        const bool split = NSPLIT == 2 && !prune;
-        if (gt < (split ? 2 * npairs : npairs)) {   // at most one work item per thread
-          const int p = split ? gt >> 1 : gt;
-          const int qpar = split ? (gt & 1) : 0;
-          const int sl = p >> 3, hd = p & 7;
-          const uint32_t row0 = (uint32_t)sl;   // row of (sequence sl, position j) = j * spt + sl
-          uint4 kp[MAXLEN];
-          uint2 kl[MAXLEN];
-          uint32_t koff[MAXLEN];   // chunk offset of (key row j, head): addresses K, its remainders, V and (halved) V's remainders
+                for (int c = 0; c < 8; ++c) o[c] *= f;
 #pragma unroll
-          for (int j = 0; j < MAXLEN; ++j) {
-            if (j < len) {
-              koff[j] = umma::sw128_offset(row0 + j * spt, hd);
-              kp[j] = *reinterpret_cast<const uint4*>(TK + koff[j]);
-              kl[j] = *reinterpret_cast<const uint2*>(TL + koff[j] + 8u);
+                for (int c = 0; c < 4; ++c) c2[c] = hfma2(c2[c], f2, 0u);
+                ref = sj;
+                arg = 0.f;
+              }
+              const float e = ex2_approx(arg);
+              z += e;
+              const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
+              const uint32_t pw = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
+              pv_step<false>(ph, pw, *reinterpret_cast<const uint4*>(TV + koff),
+                             widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff >> 1))), o, c2);
             }
-          }
-          // every K remainder is in registers (of both lanes of a split pair) before any chunk of the L tile is
-          // overwritten with an attention-output lo part below
-          __syncwarp(__activemask());
-          const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
+            pv_finish(o, c2, __fdividef(1.0f, z));
+            if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
+              const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
+              const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
 #pragma unroll
-          for (int i = 0; i < NQ; ++i) {
-            constexpr int kStep = NSPLIT;
-            const int jmax = MAXLEN - 1 - kStep * i;              // compile-time bound on this round's query position
-            if (i == 0 || !prune) {                               // warp-uniform
-              const int t_raw = len - 1 - (split ? 2 * i + qpar : i);
-              const bool act = t_raw >= 0;
-              const int t = act ? t_raw : 0;
-              uint32_t qoff = koff[0];
-#pragma unroll
-              for (int j = 1; j < MAXLEN; ++j) qoff = j == t ? koff[j] : qoff;   // (register select: keeps koff[] out of local memory)
-              const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
-              const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
-              float sc[MAXLEN];
-              float mx = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < MAXLEN; ++j) {
-                if (j <= jmax) {
-                  sc[j] = j <= t ? score_hilo(qw, ql, kp[j], widen_lo8(kl[j])) : -INFINITY;
-                  mx = fmaxf(mx, sc[j]);
-                }
-              }
-              // softmax weights e_j = exp((s_j - max) / sqrt(dh)) in fp32, handed to the fp16-operand PV product as
-              // a (high, low) pair of halves: e_j = hi_j + lo_j to 2^-22, so the product keeps fp32 weights
-              const float nmx = -mx * qk_scale_log2e;
-              uint32_t ph[(MAXLEN + 1) / 2], pw[(MAXLEN + 1) / 2];
-              float z = 0.f;
-#pragma unroll
-              for (int j = 0; j < MAXLEN; j += 2) {
-                if (j <= jmax) {
-                  const float e0 = ex2_approx(fmaf(sc[j], qk_scale_log2e, nmx));     // masked keys: exp2(-inf) = 0
-                  const float e1 = j + 1 <= jmax ? ex2_approx(fmaf(sc[j + 1], qk_scale_log2e, nmx)) : 0.f;
-                  z += e0 + e1;
-                  ph[j >> 1] = umma::pack_f16x2(e0, e1);
-                  const float2 hi = umma::unpack_f16x2(ph[j >> 1]);
-                  pw[j >> 1] = umma::pack_f16x2(e0 - hi.x, e1 - hi.y);
-                }
-              }
-              float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              uint32_t c2[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-              for (int j = 0; j < MAXLEN; ++j) {
-                if (j <= jmax && j < len) {   // (a masked key has weight 0)
-                  const uint4 vh = *reinterpret_cast<const uint4*>(TV + koff[j]);
-                  const uint4 vl = widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff[j] >> 1)));
-                  if (j & 1) pv_step<true>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
-                  else       pv_step<false>(ph[j >> 1], pw[j >> 1], vh, vl, o, c2);
-                }
-              }
-              pv_finish(o, c2, __fdividef(1.0f, z));
-              if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
-                const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
-              }
-              if (act) {
-                // hi part over the query's Q chunk, lo part over its chunk of the L tile (both consumed above)
-                uint4 w, wl;
-                umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
-                umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
-                *reinterpret_cast<uint4*>(TQ + qoff) = w;
-                *reinterpret_cast<uint4*>(TL + qoff) = wl;
-              }
+              for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
             }
+            uint4 w;
+            umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
+            umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
+            *reinterpret_cast<uint4*>(TQ + qoff) = w;   // in place: other items read only K / V rows, never this Q chunk
+            keep_off = qoff;
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // (register select: keeps the arrays out of local memory)
+            if (u == k) { lo_keep[k] = wl; lo_off[k] = keep_off; }
         }
+        umma::group_sync(bar_id, FGROUP_THREADS);   // every K remainder has been read
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lo_off[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(TL + lo_off[k]) = lo_keep[k];
       }
 
       if (!live) {
@@ -1265,18 +1197,6 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   a.len = len;
   a.spt = FROWS / len < 32 ? FROWS / len : 32;   // the score phase gives every sequence >= 8 threads
   a.tps = (FGROUP_THREADS / a.spt) >= 16 ? 16 : 8;
-  {   // balanced two-way split of the queries 0..len-1 with weights t + 1 (exhaustive)
-    const int n = len < 16 ? len : 16;
-    uint32_t best = 0xAAAAAAAAu;
-    int best_max = 1 << 30;
-    for (uint32_t mm = 0; mm < (1u << n); ++mm) {
-      int s1 = 0, s0 = 0;
-      for (int t = 0; t < n; ++t) ((mm >> t) & 1u ? s1 : s0) += t + 1;
-      const int mx = s1 > s0 ? s1 : s0;
-      if (mx < best_max) { best_max = mx; best = mm; }
-    }
-    a.qsplit = best;
-  }
   a.n_seq = n_seq;
   a.n_tiles = (n_seq + a.spt - 1) / a.spt;
   a.tokens = tokens; a.tokens_out = tokens_out; a.tok_stride = tok_stride;
@@ -1298,31 +1218,16 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   const int fast = !plain ? 0
                    : (!sampling && a.site_flags == (uint32_t)(BFB200_SITE_EMBED | BFB200_SITE_LAYER_OUT)) ? 1
                    : (a.site_flags == 0u) ? (sampling ? 3 : 2) : 0;
-#define FUSED_LAUNCH_F(ML, FV)                                                                              \
-  do {                                                                                                      \
-    cudaFuncSetAttribute(mc_forward_kernel<ML, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    mc_forward_kernel<ML, FV><<<(int)grid, FTHREADS, smem, st>>>(a);                                        \
+#define FUSED_LAUNCH(FV)                                                                                \
+  do {                                                                                                  \
+    cudaFuncSetAttribute(mc_forward_kernel<FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    mc_forward_kernel<FV><<<(int)grid, FTHREADS, smem, st>>>(a);                                        \
   } while (0)
-#define FUSED_LAUNCH(ML)                  \
-  do {                                    \
-    if (fast == 1) FUSED_LAUNCH_F(ML, 1); \
-    else if (fast == 2) FUSED_LAUNCH_F(ML, 2); \
-    else if (fast == 3) FUSED_LAUNCH_F(ML, 3); \
-    else FUSED_LAUNCH_F(ML, 0);           \
-  } while (0)
-  // the pair phase keeps a sequence's K rows in registers: one instantiation per length up to 8 (the decode steps
-  // of the reference's addition task run at lengths 4..8), so that the arrays are exactly as long as the sequences
-  static const bool force_long = getenv("BFB200_FUSED_FORCE_LONG") != nullptr;   // experiment switch: streaming pair phase at every length
-  if (force_long) FUSED_LAUNCH(FMAXLEN);
-  else if (len <= 4) FUSED_LAUNCH(4);
-  else if (len == 5) FUSED_LAUNCH(5);
-  else if (len == 6) FUSED_LAUNCH(6);
-  else if (len == 7) FUSED_LAUNCH(7);
-  else if (len == 8) FUSED_LAUNCH(8);
-  else if (len <= 16) FUSED_LAUNCH(16);
-  else FUSED_LAUNCH(FMAXLEN);
+  if (fast == 1) FUSED_LAUNCH(1);
+  else if (fast == 2) FUSED_LAUNCH(2);
+  else if (fast == 3) FUSED_LAUNCH(3);
+  else FUSED_LAUNCH(0);
 #undef FUSED_LAUNCH
-#undef FUSED_LAUNCH_F
   BFB_LAUNCH_CHECK("mc_forward_kernel", st);
   return BFB200_OK;
 }

@@ -439,8 +439,8 @@ extern "C" int bfb200_mc_score_transformer(const bfb200_transformer* model, cons
   const int64_t S_total = a.n_items * T;
   const bool fused = use_fused(m);
   if (fused)
-    BFB_REQUIRE(P + N - 1 <= 40, BFB200_ERR_UNSUPPORTED,
-                "compute=f16 (fused kernel) takes sequences of at most 40 tokens; P + N - 1 = %d", P + N - 1);
+    BFB_REQUIRE(P + N - 1 <= 128, BFB200_ERR_UNSUPPORTED,
+                "compute=f16 (fused kernel) takes sequences of at most 128 tokens; P + N - 1 = %d", P + N - 1);
   if (use_tc(m))
     BFB_REQUIRE(P + N - 1 <= 256, BFB200_ERR_UNSUPPORTED,
                 "the layered tensor-core path takes sequences of at most 256 tokens; P + N - 1 = %d", P + N - 1);

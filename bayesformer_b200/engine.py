@@ -437,7 +437,7 @@ def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransfo
     return entry[1]
 
 
-FUSED_MAX_LEN = 40   # longest sequence (P + N - 1) the fused fp16 kernel takes (csrc/mc_fused.cu FMAXLEN)
+FUSED_MAX_LEN = 128   # longest sequence (P + N - 1) the fused fp16 kernel takes (csrc/mc_fused.cu FMAXLEN)
 TC_MAX_LEN = 256     # ... and the layered tensor-core path
 
 

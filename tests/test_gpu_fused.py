@@ -167,9 +167,9 @@ def _fused_vs_exact(engine, dev, model, prompts, N, T, scheme, mode, seed, rtol=
 
 @pytest.mark.parametrize("P,N,B,T", [(4, 5, 257, 20), (1, 3, 33, 4), (2, 2, 1, 1), (3, 6, 70, 7), (7, 2, 19, 20),
                                      (9, 4, 45, 5), (12, 5, 23, 3), (16, 1, 9, 2), (17, 3, 11, 3), (32, 5, 29, 4),
-                                     (40, 1, 7, 2), (25, 6, 10, 5)])
+                                     (40, 1, 7, 2), (25, 6, 10, 5), (60, 3, 5, 3), (127, 2, 3, 2)])
 def test_fused_matches_exact_path_all_shapes(engine, dev, c2, P, N, B, T):
-    """Tile tails, 1..40-token sequences (all three kernel variants), every mode, uniformly random token prompts (far
+    """Tile tails, 1..128-token sequences, every mode, uniformly random token prompts (far
     outside the trained model's input distribution), at the stated bound: 1e-2 relative + 1e-4 absolute on every
     probability (tools/fused_accuracy.py: the worst of 10^7 probabilities sits at 0.5 of it)."""
     z, sd = c2
@@ -275,10 +275,11 @@ def test_fp16_outside_the_fused_class_is_an_error(engine, dev):
     assert pack.compute == "fp32"
     small = MyTransformer(114, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval().to(dev)
     assert engine.scoring_pack(small, dev, 4, 5, "auto").compute == "fp16"
-    assert engine.scoring_pack(small, dev, 32, 5, "auto").compute == "fp16"   # 36-token sequences: long variant
-    assert engine.scoring_pack(small, dev, 40, 5, "auto").compute == "fp32"   # 44-token sequences: outside the class
+    assert engine.scoring_pack(small, dev, 32, 5, "auto").compute == "fp16"   # 36-token sequences
+    assert engine.scoring_pack(small, dev, 124, 5, "auto").compute == "fp16"  # 128-token sequences: one per tile
+    assert engine.scoring_pack(small, dev, 125, 5, "auto").compute == "fp32"  # 129 tokens: outside the class
     with pytest.raises(NotImplementedError):
-        engine.mc_score_transformer(small.native_pack(dev, "fp16"), torch.zeros(40, 4, dtype=torch.int64, device=dev),
+        engine.mc_score_transformer(small.native_pack(dev, "fp16"), torch.zeros(125, 4, dtype=torch.int64, device=dev),
                                     5, 2, "dropout", "max")
 
 
