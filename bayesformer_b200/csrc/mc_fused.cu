@@ -64,6 +64,10 @@ constexpr uint32_t HEAD_BYTES = FMAXV * 128;  // vocabulary head: streamed per t
 constexpr uint32_t C_XHI = 0, C_XLO = 32, C_ACC = 64;
 constexpr size_t kFusedSmemMax = 227 * 1024;
 constexpr uint32_t kBarrierBytes = 64;
+#ifndef BFB_KEY_UNROLL
+#define BFB_KEY_UNROLL 2   // key loop of the pair phase (measured)
+#endif
+constexpr int kKeyUnroll = BFB_KEY_UNROLL;
 constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)FGROUPS * VLO_BYTES;
 
 struct FusedLayout {
@@ -261,15 +265,16 @@ using umma::fh_lh;
 using umma::fh_hl;
 
 // d + a . b over the 8 fp16 values of two packed words (fp32 accumulation; products of halves are exact)
-__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b, float d) {
+__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b, float d) {   // two chains of four (latency)
+  float e = fh_ll(a.z, b.z, 0.f);
   d = fh_ll(a.x, b.x, d);
+  e = fh_hh(a.z, b.z, e);
   d = fh_hh(a.x, b.x, d);
+  e = fh_ll(a.w, b.w, e);
   d = fh_ll(a.y, b.y, d);
+  e = fh_hh(a.w, b.w, e);
   d = fh_hh(a.y, b.y, d);
-  d = fh_ll(a.z, b.z, d);
-  d = fh_hh(a.z, b.z, d);
-  d = fh_ll(a.w, b.w, d);
-  return fh_hh(a.w, b.w, d);
+  return d + e;
 }
 // the 8-bit remainders of a Q or K head row (8 bytes) as packed fp16
 __device__ __forceinline__ uint4 widen_lo8(const uint2& w) {
@@ -286,14 +291,14 @@ constexpr uint32_t kOneOne = 0x3C003C00u;   // (1.0h, 1.0h)
 // ql . kh + qh . kl (2^-11 of the result) as packed-half FMAs; the ql . kl term is below 2^-22 of |q||k|.  The clamp
 // keeps an overflowing cross term (|q||k| beyond 1e8) from turning the row into NaNs.
 __device__ __forceinline__ float score_hilo(const uint4& qh, const uint4& ql, const uint4& kh, const uint4& kl) {
-  uint32_t c = hfma2(ql.x, kh.x, 0u);
-  c = hfma2(qh.x, kl.x, c);
+  uint32_t c = hfma2(ql.x, kh.x, 0u), c1 = hfma2(qh.x, kl.x, 0u);   // two chains of four (latency)
   c = hfma2(ql.y, kh.y, c);
-  c = hfma2(qh.y, kl.y, c);
+  c1 = hfma2(qh.y, kl.y, c1);
   c = hfma2(ql.z, kh.z, c);
-  c = hfma2(qh.z, kl.z, c);
+  c1 = hfma2(qh.z, kl.z, c1);
   c = hfma2(ql.w, kh.w, c);
-  c = hfma2(qh.w, kl.w, c);
+  c1 = hfma2(qh.w, kl.w, c1);
+  c = hfma2(c, kOneOne, c1);
   const float s = fh_hl(c, kOneOne, fh_ll(c, kOneOne, dot8_f16(qh, kh, 0.f)));
   return fminf(fmaxf(s, -3.0e38f), 3.0e38f);
 }
@@ -936,7 +941,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
             float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             uint32_t c2[4] = {0u, 0u, 0u, 0u};
             uint32_t krow = (uint32_t)sl;
-#pragma unroll 1
+#pragma unroll kKeyUnroll
             for (int j = 0; j <= t; ++j, krow += (uint32_t)spt) {
               const uint32_t koff = umma::sw128_offset(krow, (uint32_t)hd);
               const float sj = score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),

@@ -15,15 +15,25 @@ import torch
 
 from bayesformer_b200 import _lib
 
-# Monotonic counter giving every stochastic native call its own Philox stream, the way each
-# F.dropout call of the reference advances the global generator.
+# Every stochastic native call gets its own Philox stream, the way each F.dropout call of the reference advances the
+# global generator.  The stream id is taken from — and advances — the philox offset of torch's default CUDA generator,
+# so `torch.manual_seed(s)` restarts the sequence exactly as it does for the reference (same seed => same masks, same
+# acquired indices), and ranks that ran different numbers of unrelated native calls still need the explicit `seed=`
+# argument to agree.  (Fallback without that generator API: a process-global counter.)
 _call_counter = 0
 
 
-def _next_call_id() -> int:
+def _next_call_id(device=None) -> int:
     global _call_counter
-    _call_counter += 1
-    return _call_counter
+    try:
+        idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+        gen = torch.cuda.default_generators[idx]
+        off = int(gen.get_offset())
+        gen.set_offset(off + 4)          # one Philox block, like a small torch random op
+        return off // 4 + 1
+    except (AttributeError, IndexError, RuntimeError):
+        _call_counter += 1
+        return _call_counter
 
 
 def default_seed() -> int:
@@ -435,6 +445,19 @@ def packed(module, device: torch.device, compute: str = "fp32") -> PackedTransfo
         entry = (sig, PackedTransformer(module, device, compute))
         per_module[compute] = entry
     return entry[1]
+
+
+def default_compute(module, scheme: str) -> str:
+    """Arithmetic class of a scoring call that does not name one.  `module.native_compute` ("fp32" | "fp16" | "bf16" |
+    "auto") wins when set.  Otherwise the stochastic schemes (MC dropout, temperature sampling) take 'auto' — a
+    tensor-core path where the model is in its class: its error (1e-2 class, measured 5e-4 rms on log-probs) is far
+    below their sampling noise — while the DETERMINISTIC greedy scheme (greedy_uncertainty, generate, evaluate) takes
+    the exact fp32 CUDA path: with no MC noise to absorb it, a near-tie arg-max could otherwise differ from the
+    reference's fp32 decision.  Set `model.native_compute = "fp16"` to opt the greedy calls into the fused kernel."""
+    explicit = getattr(module, "native_compute", None)
+    if explicit is not None:
+        return explicit
+    return "fp32" if scheme == "greedy" else "auto"
 
 
 FUSED_MAX_LEN = 128   # longest sequence (P + N - 1) the fused fp16 kernel takes (csrc/mc_fused.cu FMAXLEN)

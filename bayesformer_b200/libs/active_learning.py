@@ -69,7 +69,7 @@ def _scores(model, prompts, new_tokens, device, mode, scheme, n_draws, temperatu
                            "(nn.Dropout sites off, always-on bayes sites live)")
     from bayesformer_b200 import engine
 
-    pack = engine.scoring_pack(model, dev, prompts.shape[0], new_tokens, getattr(model, "native_compute", "auto"))
+    pack = engine.scoring_pack(model, dev, prompts.shape[0], new_tokens, engine.default_compute(model, scheme))
     res = engine.mc_score_transformer(pack, prompts.to(dev), new_tokens, n_draws, scheme, mode,
                                       temperature=temperature)
     return res.step_scores

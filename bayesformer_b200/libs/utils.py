@@ -130,47 +130,54 @@ def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, ba
     history_train, history_valid = [], []
     best = float("inf")
     batches: dict[int, tuple] = {}
-    for epoch in range(1, nb_epochs + 1):
-        model.train()
-        running = 0.0
-        running_dev = torch.zeros((), device=device) if use_graphs else None
-        for start in range(0, len(train_dataset) - 1, batch_size):
+    try:
+        for epoch in range(1, nb_epochs + 1):
+            model.train()
+            running = 0.0
+            running_dev = torch.zeros((), device=device) if use_graphs else None
+            for start in range(0, len(train_dataset) - 1, batch_size):
+                if use_graphs:
+                    # the reference walks the same slices in the same order every epoch (no shuffling, :60): each batch is
+                    # tokenised and copied to the device once per call
+                    if start not in batches:
+                        prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
+                        batches[start] = (prompts.to(device), answers.to(device), p_len, a_len)
+                    prompts, answers, p_len, a_len = batches[start]
+                    key = (p_len, a_len, prompts.shape[1])
+                    if key not in graphs:
+                        graphs[key] = _GraphedTrainStep(model, optimizer, criterion, p_len, a_len, prompts.shape[1], vocab_size,
+                                                        device)
+                    running_dev += graphs[key].run(prompts, answers).detach()
+                    continue
+                model.zero_grad()
+                loss = _batch_loss(model, train_dataset, tokenizer, start, batch_size, vocab_size, device, criterion)
+                loss.backward()
+                optimizer.step()
+                running += loss.item()
             if use_graphs:
-                # the reference walks the same slices in the same order every epoch (no shuffling, :60): each batch is
-                # tokenised and copied to the device once per call
-                if start not in batches:
-                    prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
-                    batches[start] = (prompts.to(device), answers.to(device), p_len, a_len)
-                prompts, answers, p_len, a_len = batches[start]
-                key = (p_len, a_len, prompts.shape[1])
-                if key not in graphs:
-                    graphs[key] = _GraphedTrainStep(model, optimizer, criterion, p_len, a_len, prompts.shape[1], vocab_size,
-                                                    device)
-                running_dev += graphs[key].run(prompts, answers).detach()
-                continue
-            model.zero_grad()
-            loss = _batch_loss(model, train_dataset, tokenizer, start, batch_size, vocab_size, device, criterion)
-            loss.backward()
-            optimizer.step()
-            running += loss.item()
-        if use_graphs:
-            running = float(running_dev.item())
+                running = float(running_dev.item())
+                from bayesformer_b200 import engine
+
+                engine.mark_weights_changed(model)   # graph replays update the weights without bumping tensor versions
+            model.eval()
+            running_valid = 0.0
+            with torch.no_grad():
+                for start in range(0, len(valid_dataset) - 1, batch_size):
+                    running_valid += _batch_loss(model, valid_dataset, tokenizer, start, batch_size, vocab_size, device,
+                                                 criterion).item()
+            train_loss = running / len(train_dataset)
+            valid_loss = running_valid / len(valid_dataset)
+            history_train.append(train_loss)
+            history_valid.append(valid_loss)
+            if nb_epochs < 10 or epoch % (nb_epochs // 10) == 0:
+                print(f"EPOCH [{epoch} / {nb_epochs}] ----------- TRAIN LOSS : {train_loss:.4f}, VALID LOSS : {valid_loss:.4f}")
+            best = min(best, valid_loss)
+
+    finally:
+        if use_graphs:   # also on KeyboardInterrupt / an exception mid-epoch: the packs must never be half-fresh
             from bayesformer_b200 import engine
 
-            engine.mark_weights_changed(model)   # graph replays update the weights without bumping tensor versions
-        model.eval()
-        running_valid = 0.0
-        with torch.no_grad():
-            for start in range(0, len(valid_dataset) - 1, batch_size):
-                running_valid += _batch_loss(model, valid_dataset, tokenizer, start, batch_size, vocab_size, device,
-                                             criterion).item()
-        train_loss = running / len(train_dataset)
-        valid_loss = running_valid / len(valid_dataset)
-        history_train.append(train_loss)
-        history_valid.append(valid_loss)
-        if nb_epochs < 10 or epoch % (nb_epochs // 10) == 0:
-            print(f"EPOCH [{epoch} / {nb_epochs}] ----------- TRAIN LOSS : {train_loss:.4f}, VALID LOSS : {valid_loss:.4f}")
-        best = min(best, valid_loss)
+            engine.mark_weights_changed(model)
     print(f"Best valid loss : {best:.4f}")
     return np.array(history_train), np.array(history_valid)
 
@@ -187,7 +194,7 @@ def generate(model: MyTransformer, prompts: torch.Tensor, new_tokens: int, devic
             and model._train_only_dropout_inactive() and new_tokens > 0 and seq.shape[1] > 0):
         from bayesformer_b200 import engine
 
-        pack = engine.scoring_pack(model, seq.device, seq.shape[0], new_tokens, getattr(model, "native_compute", "auto"))
+        pack = engine.scoring_pack(model, seq.device, seq.shape[0], new_tokens, engine.default_compute(model, "greedy"))
         res = engine.mc_score_transformer(pack, seq, new_tokens, 1, "greedy", "max", return_tokens=True)
         return res.tokens.t().contiguous().to(torch.int64)
     for _ in range(new_tokens):

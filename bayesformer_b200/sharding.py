@@ -47,7 +47,7 @@ def gather_candidate_keys(local_keys: torch.Tensor, k: int, group=None) -> torch
 def select_samples_sharded(model, local_prompts: torch.Tensor, new_tokens: int, device, nb_samples: int = 200,
                            compute: str = "dropout", mode: str = "max", index_base: int = 0, n_total: int | None = None,
                            seed: int | None = None, n_draws: int = 20, temperature: float = 0.8, group=None,
-                           native_compute: str = "auto") -> list[int]:
+                           native_compute: str | None = None) -> list[int]:
     """`select_samples` (reference src/libs/active_learning.py:158-211) over a pool sharded across ranks.
 
     local_prompts (P, B_local) int64 are this rank's contiguous shard starting at global index
@@ -73,6 +73,8 @@ def select_samples_sharded(model, local_prompts: torch.Tensor, new_tokens: int, 
             n_total = n_local * world
         if nb_samples > n_total:
             raise RuntimeError("selected index k out of range")
+        if native_compute is None:   # stochastic schemes: 'auto' (tensor-core path where in class); greedy: exact fp32
+            native_compute = engine.default_compute(model, compute)
         pack = engine.scoring_pack(model, dev, prompts.shape[0], new_tokens, native_compute)
         res = engine.mc_score_transformer(pack, prompts, new_tokens, 1 if compute == "greedy" else n_draws, compute,
                                           mode, temperature=temperature, seed=seed, index_base=index_base)
