@@ -51,7 +51,7 @@ PAD_ID, EQ_ID, VOCAB = 112, 111, 114
 def synthetic_addition_prompts(n: int, seed: int, num_digits: int = 3) -> np.ndarray:
     """(P=num_digits+1, n) int64 prompt ids of random `abc+def=` problems, identical to what
     `preprocessing.get_batch(create_dataset(...), ReversedPairingTokenizer())` produces for the same operands
-    (units-first digit-pair tokens, '=', left-padded with PAD; tests/test_bench_inputs.py pins this)."""
+    (units-first digit-pair tokens, '=', left-padded with PAD; tests/test_host_logic.py pins this)."""
     rng = np.random.RandomState(seed)
     digits = rng.randint(0, 10, size=(n, 2, num_digits))          # most significant digit first
     sig = np.maximum(num_digits - (np.cumsum(digits, axis=2) == 0).sum(axis=2), 1)  # length without leading zeros (>= 1)
@@ -174,6 +174,45 @@ def time_cpu_port(model, prompts_np: np.ndarray, N: int, sample: int, steps: int
             "seconds_per_pass": dt}
 
 
+def time_unmodified_reference(sample: int, steps: int, warmup: int):
+    """The reference's own `select_samples` (src/libs/active_learning.py:158-211, unmodified, imported from
+    /root/reference, $BAYESFORMER_REFERENCE or baseline/_ref when one of them exists on this box) on `sample` pool items,
+    all host threads.  Returns None where no reference tree is present (the GPU boxes: the port is timed instead)."""
+    import random
+
+    from oracle import ref_shim
+
+    roots = [os.environ.get("BAYESFORMER_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")]
+    root = next((r for r in roots if r and os.path.isdir(os.path.join(r, "src", "model"))), None)
+    if root is None:
+        return None
+    ref_shim.REFERENCE_ROOT = root
+    ref = ref_shim.load_reference()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tok = ref.tokenizer.ReversedPairingTokenizer()
+    random.seed(SEED)
+    pool = ref.preprocessing.create_dataset(sample, 3)
+    torch.manual_seed(SEED)
+    model = ref.transformer.MyTransformer(tok.ntokens, D_MODEL, N_HEADS, D_FF, N_LAYERS, bayes_dropout=P_DROP, bayes=True)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c2_transformer.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd["pos_enc.pe"] = model.pos_enc.pe.clone()
+    model.load_state_dict(sd)
+    for _ in range(warmup):
+        ref.active_learning.select_samples(model, tok, pool[: max(64, sample // 8)], "cpu", nb_samples=8, compute=SCHEME, mode=MODE)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ref.active_learning.select_samples(model, tok, pool, "cpu", nb_samples=min(K_TOP, sample), compute=SCHEME, mode=MODE)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{sample} pool items x T={T_MC} x N=5 steps per pass ({dt:.2f} s/pass, mean of {steps}), unmodified "
+                      f"reference select_samples from {root} on torch {torch.__version__} CPU kernels, {cores} threads",
+            "seconds_per_pass": dt}
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -183,7 +222,13 @@ def run_reference_arm(args) -> None:
     sample = 2000
     prompts_np = synthetic_addition_prompts(sample, SEED)
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    base = time_cpu_port(model, prompts_np, N, sample, min(steps, 5), min(warmup, 1))
+    base = None
+    try:   # the unchanged reference if present on the box, else the pinned port
+        base = time_unmodified_reference(sample, min(steps, 5), min(warmup, 1))
+    except Exception as exc:  # noqa: BLE001 - a broken reference tree must not lose the arm
+        print(f"[bench] unmodified reference unusable ({exc!r}); timing the port", file=sys.stderr)
+    if base is None:
+        base = time_cpu_port(model, prompts_np, N, sample, min(steps, 5), min(warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": min(steps, 5), "warmup": min(warmup, 1), "ms_per_step": base["seconds_per_pass"] * 1e3,
@@ -221,6 +266,9 @@ def main() -> None:
     ap.add_argument("--pool", type=int, default=POOL_PER_GPU, help="pool items per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the stand-alone kernel measurements")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the strong-scaling 1 M pool, the scaled configuration C4 and the fp32-class pass")
+    ap.add_argument("--c4-items", type=int, default=8192, help="pool items per GPU of the scaled configuration (C4) pass")
     ap.add_argument("--compute", default="auto", choices=["auto", "fp16", "fp32"],
                     help="auto/fp16: fused tcgen05 kernel (fp16 operands, fp32 accumulate); fp32: exact layered CUDA path")
     args = ap.parse_args()
@@ -356,6 +404,12 @@ def main() -> None:
             "peak_tflops": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
             "frac": value / world * flops_per_pool_sample(P, N) / 1e12 / peaks["bf16_tflops_sustained"]},
     }
+    if not args.no_extras:
+        # BASELINE configs[2] (1 M-item pool split over the ranks), configs[3] (scaled model, 8,192 items per GPU) and the
+        # fp32 (1e-3) class of the headline workload: measured at EVERY N, collectives included (all ranks take part)
+        extras = multi_gpu_extras(dev, world, rank, model, barrier, max_over_ranks, args)
+        if rank == 0:
+            line.update(extras)
     if rank == 0 and world == 1 and not args.no_aux:
         try:
             line["aux_kernels"] = aux_kernel_benchmarks(dev, peaks, peak_src)
@@ -365,10 +419,181 @@ def main() -> None:
         if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (rank 0 of a multi-rank job skips it)
             line["cpu_baseline"] = {k: v for k, v in
                                     time_cpu_port(model, prompts_np, N, 2000, 2, 1).items() if k != "seconds_per_pass"}
+            try:   # the CPU path of the other configurations beside their GPU numbers
+                line["cpu_baseline"]["other_configs"] = cpu_port_other_configs()
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"]["other_configs"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_gpu_extras(dev, world: int, rank: int, model, barrier, max_over_ranks, args) -> dict:
+    """Measured at every --gpus N (all ranks take part; rank 0 reports):
+      fp32_class   the headline workload on the exact fp32 CUDA path (1e-3 parity class), 20,000 items per GPU;
+      strong_1m    BASELINE configs[2]: ONE pool of 1,000,000 prompts split over the N ranks (strong scaling), local
+                   top-k + all-gather merge; afterwards rank 0 scores the whole pool alone and the acquired indices must
+                   be identical (shard invariance of the counter-based masks);
+      scaled_c4    BASELINE configs[3]: MyTransformer(114, 512, 8, 2048, 6), 256-token prompts, T = 50, entropy, k = 200,
+                   8,192 pool items per GPU (weak), fp16 operands on the layered tensor-core path."""
+    from bayesformer_b200 import engine, sharding
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    out = {}
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, warm: int, reps: int):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(reps):
+            res = fn()
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max_over_ranks(max(e0.elapsed_time(e1), wall)) / reps, res
+
+    P, N = 4, 5
+    # --- fp32 class ------------------------------------------------------------------------------------
+    try:
+        n32 = 20_000
+        pr = torch.from_numpy(synthetic_addition_prompts(n32, SEED + 100 + rank)).to(dev)
+        pk32 = engine.scoring_pack(model, dev, P, N, "fp32")
+        ms, _ = timed(lambda: engine.topk_keys(engine.mc_score_transformer(pk32, pr, N, T_MC, SCHEME, MODE, seed=SEED,
+                                                                           index_base=rank * n32).pool_scores, K_TOP), 1, 3)
+        out["fp32_class"] = {"value": n32 * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "pool_per_gpu": n32,
+                             "compute": "fp32 (layered CUDA-core kernels; parity class 1e-3, measured ~1e-5)",
+                             "note": "same workload as the headline line, whose fp16 split-precision kernel is the 1e-2 class"}
+        del pr
+    except Exception as exc:  # noqa: BLE001
+        out["fp32_class"] = {"error": repr(exc)}
+    # --- BASELINE configs[2]: 1 M-item pool, strong scaling ---------------------------------------------
+    try:
+        total = 1_000_000
+        lo, hi = rank * total // world, (rank + 1) * total // world
+        full_np = synthetic_addition_prompts(total, SEED + 7)          # every rank generates the same pool, keeps its shard
+        shard = torch.from_numpy(np.ascontiguousarray(full_np[:, lo:hi])).pin_memory()
+
+        def strong_step():
+            return sharding.select_samples_sharded(model, shard, N, dev, nb_samples=K_TOP, compute=SCHEME, mode=MODE,
+                                                   index_base=lo, n_total=total, seed=SEED, n_draws=T_MC,
+                                                   native_compute=args.compute)
+
+        ms, picked = timed(strong_step, 1, 3)
+        entry = {"value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "pool_total": total, "scaling": "strong",
+                 "n_gpus": world, "path": "select_samples_sharded: pinned host shard in, local top-k, all-gather of "
+                                          f"{K_TOP} keys per rank, merged indices out"}
+        if world > 1:   # the sharded selection must equal the single-GPU selection (rank 0 scores the whole pool alone)
+            same = True
+            if rank == 0:
+                whole = torch.from_numpy(full_np).to(dev)
+                pk = engine.scoring_pack(model, dev, P, N, args.compute)
+                res = engine.mc_score_transformer(pk, whole, N, T_MC, SCHEME, MODE, seed=SEED, index_base=0)
+                alone = engine.unpack_keys(engine.topk_keys(res.pool_scores, K_TOP))[1].tolist()
+                same = alone == picked
+                del whole, res
+            entry["equals_single_gpu_selection"] = bool(same)
+            assert same, "sharded and single-GPU selections differ"
+        out["strong_1m"] = entry
+        del shard, full_np
+    except AssertionError:
+        raise
+    except Exception as exc:  # noqa: BLE001
+        out["strong_1m"] = {"error": repr(exc)}
+    # --- BASELINE configs[3]: scaled model, 8,192 items per GPU ------------------------------------------
+    try:
+        torch.manual_seed(SEED)
+        big = MyTransformer(114, 512, 8, 2048, 6, bayes_dropout=0.3, bayes=True).eval().to(dev)
+        n_c4, t_mc = args.c4_items, 50
+        g = torch.Generator().manual_seed(SEED + 11 + rank)
+        pr_host = torch.randint(0, 114, (256, n_c4), generator=g).pin_memory()
+        small = pr_host[:, :64].contiguous().pin_memory()
+
+        def c4_step(p):
+            return sharding.select_samples_sharded(big, p, 1, dev, nb_samples=min(K_TOP, p.shape[1] * world), compute="dropout", mode="entropy",
+                                                   index_base=rank * p.shape[1], n_total=p.shape[1] * world, seed=SEED,
+                                                   n_draws=t_mc, native_compute="auto")
+
+        for _ in range(2):
+            c4_step(small)
+        ms, _ = timed(lambda: c4_step(pr_host), 0, 1)
+        flops = t_mc * (6 * (8 * 256 * 512 * 512 + 4 * 256 * 512 * 2048 + 2 * 256 * 257 * 512) + 2 * 512 * 114)
+        sps = n_c4 * world / (ms * 1e-3)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
+        out["scaled_c4"] = {"value": sps, "unit": UNIT, "ms_per_step": ms, "pool_per_gpu": n_c4, "scaling": "weak",
+                            "n_gpus": world, "T_mc": t_mc, "len": 256, "mode": "entropy", "k": K_TOP,
+                            "compute": "fp16 operands on tcgen05 (layered tensor-core path), fp32 accumulate / residual / "
+                                       "LayerNorm: the 1e-2 class; BASELINE names bf16, whose 8-bit mantissa measures 5e-2 "
+                                       "on this model (tests/test_gpu_tc_path.py) and runs at the same speed",
+                            "flops_per_pool_sample": flops, "achieved_tflops_per_gpu": sps / world * flops / 1e12,
+                            "frac_of_sustained_tensor_peak": sps / world * flops / 1e12 / peaks["bf16_tflops_sustained"]}
+        del big, pr_host
+    except Exception as exc:  # noqa: BLE001
+        out["scaled_c4"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_port_other_configs() -> dict:
+    """CPU path (oracle port, all host threads) of the other BASELINE configurations on bounded samples, N = 1 only:
+    C1 (char-level, 36-token sequences), C4 (scaled model, 2 pool items x T = 50) and the toy classifier (100 k points)."""
+    from oracle import restatement as R
+    from bayesformer_b200.model.transformer import MyTransformer
+    from bayesformer_b200.model.bayesian_classification import MLP
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {}
+
+    def port_pass(sd, prompts, n_steps, t_mc, p, L, d, mode):
+        live = R.default_live_sites(L, True)
+        S = prompts.shape[1] * t_mc
+
+        def step_fn(_step):
+            def fn(site, n_pos):
+                return torch.empty(n_pos, S, d).bernoulli_(1 - p).bool() if site in live else None
+            return fn
+        with torch.no_grad():
+            return R.mc_scores(sd, prompts, n_steps, t_mc, "dropout", mode, p, step_fn)
+
+    torch.manual_seed(SEED)
+    c1 = MyTransformer(67, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).eval()
+    sd = {k: v.detach().float() for k, v in c1.state_dict().items()}
+    n = 150
+    pr = torch.randint(0, 65, (32, n))
+    t0 = time.perf_counter()
+    port_pass(sd, pr, 5, T_MC, 0.3, 2, 64, "entropy")
+    dt = time.perf_counter() - t0
+    out["char_level_c1"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{n} windows x T={T_MC} x 5 steps (32..36 tokens), {dt:.2f} s"}
+    torch.manual_seed(SEED)
+    c4 = MyTransformer(114, 512, 8, 2048, 6, bayes_dropout=0.3, bayes=True).eval()
+    sd = {k: v.detach().float() for k, v in c4.state_dict().items()}
+    n, t_mc = 2, 50
+    pr = torch.randint(0, 114, (256, n))
+    t0 = time.perf_counter()
+    port_pass(sd, pr, 1, t_mc, 0.3, 6, 512, "entropy")
+    dt = time.perf_counter() - t0
+    out["scaled_c4"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n} pool items x T={t_mc} x 1 step (256 tokens), {dt:.2f} s"}
+    torch.manual_seed(SEED)
+    mlp = MLP(2, 50, 1, dropout=True, dropout_rate=0.5).eval()
+    pts = torch.randn(100_000, 2)
+    w = [t.detach() for t in (mlp.hidden_layer.weight, mlp.hidden_layer.bias, mlp.output_layer.weight, mlp.output_layer.bias)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        keep = torch.empty(T_MC, pts.shape[0], 50).bernoulli_(0.5).bool()
+        res = R.mlp_mc(pts, *w, 0.5, keep)
+        R.topk_lowest_index(res["score_of_mean"][1].numpy(), K_TOP)
+    dt = time.perf_counter() - t0
+    out["mlp_classifier"] = {"value": pts.shape[0] / dt, "unit": "items/s", "cores": cores, "kind": "port",
+                             "sample": f"100,000 moons-like points x T={T_MC}, three scores, top-{K_TOP}, {dt:.2f} s"}
+    return out
 
 
 def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
@@ -410,7 +635,7 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
     del x, probs
     scores = torch.randn(1_000_000, device=dev)
     ms = timed(lambda: engine.topk_keys(scores, K_TOP))
-    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident, latency bound (3 launches)"}
+    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident; radix select, 62 blocks + 1 block (two launches)"}
     # MC-batched tensor-core GEMMs at the scaled configuration's shapes (d = 512, F = 2048; one chunk of
     # 256 sequences x 256 tokens = 65,536 token rows), against the measured dense bf16 matmul peak
     tc_peak = peaks["bf16_tflops"]
@@ -515,9 +740,13 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
         pts = torch.randn(n, 2, device=dev)
         with torch.no_grad():
             ms = timed(lambda: mlp.mc_predict(pts, nsamples=T_MC, return_scores=True))
+        fma_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6     # FP32 FMA lanes x clock
         out[f"mlp_mc_kernel[{n}]"] = {"items": n, "T_mc": T_MC, "ms": ms, "items_per_s": n / (ms * 1e-3),
                                       "bernoulli_draws_per_s": n * T_MC * 50 / (ms * 1e-3),
                                       "hbm_gbs": n * 12 / ms / 1e6,
+                                      "bound": "sm issue (ALU / RNG)", "algorithmic_fma_per_item": 1100,
+                                      "achieved_fma_per_s": n * 1100 / (ms * 1e-3), "fma_peak_per_s": fma_peak,
+                                      "frac_of_fma_peak": n * 1100 / (ms * 1e-3) / fma_peak,
                                       "note": "ALU/RNG bound by construction: 12 B of HBM, 1,000 Bernoulli draws and "
                                               "1,100 FMA per item (SURVEY 8d)"}
     return out
@@ -543,15 +772,15 @@ def kernel_roofline(name: str, stat: dict, passes: int, pool: int, P: int, N: in
         flops = passes * pool * flops_per_pool_sample(P, N)
         ach = flops / (ms * 1e-3) / 1e12
         traffic, traffic_note = None, None
-        prof = os.path.join(ROOT, "profiles", "r1p_ncu_mc_forward_bench_size.json")
+        prof = os.path.join(ROOT, "profiles", "r2_ncu_mc_forward_bench_size.json")
         if os.path.exists(prof) and pool == POOL_PER_GPU:   # dram__bytes_read + write of one `ncu --set full` capture
             traffic = int(json.load(open(prof))["dram_bytes_per_launch_mean"])
             traffic_note = "mean over the 5 launches of a pass (len 4..8), " + os.path.basename(prof)
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "traffic_note": traffic_note, "avg_launch_ms": avg_ms, "peak_source": peak_src,
-                "note": "issue-bound by construction (dh = 8, F = 8, len <= 8): ncu shows 41-45 % of issue slots and 6 % "
-                        "of tensor-pipe cycles busy; algorithmic HBM traffic is 40 B per sequence-step"}
+                "note": "issue / latency bound by construction (dh = 8, F = 8, len <= 8): ncu shows 40-44 % of issue slots "
+                        "and 12 % of tensor-pipe cycles busy; algorithmic HBM traffic is 40 B per sequence-step"}
     per_row = {"attention_kernel": 4 * d * 4,            # read q,k,v + write out
                "resid_ln_kernel": 3 * d * 4,             # read x, y + write out
                "embed_kernel": 4 + d * 4}.get(name)
