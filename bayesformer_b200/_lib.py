@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_INVALID_ARG, ERR_NOT_DEVICE_PTR, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 
@@ -25,6 +25,7 @@ SITE_ATTN_RESID = 1 << 2
 SITE_FFN_IN = 1 << 3
 SITE_FFN_RESID = 1 << 4
 SITE_HEAD_OUT = 1 << 5
+SITE_HEAD_IN = 1 << 6    # Head.bayes: per-head masks on the Q / K / V projection inputs (fp32 path only)
 SITES_PER_LAYER = 5
 
 

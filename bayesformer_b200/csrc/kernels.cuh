@@ -27,6 +27,10 @@ int launch_embed(const int32_t* tokens, int tok_stride, const float* emb, const 
                  uint32_t fmt = 0);
 int launch_sgemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
                  int64_t a_row_mul, int64_t a_row_off, int relu, cudaStream_t st);
+// Q, K, V projections with Head.bayes input dropout (transformer.py:50-53): projection c of head h multiplies its own
+// masked copy of x, site = site_base + 3 * h + c
+int launch_qkv_head_in(const float* x, const float* w_qkv, float* qkv, int64_t n_seq, int len, int d, int n_heads,
+                       const MaskSource& ms, int site_base, cudaStream_t st);
 int launch_attention(const float* qkv, float* out, int64_t n_seq, int len, int d, int n_heads,
                      const MaskSource& ms, int site, cudaStream_t st);
 int launch_resid_ln(const float* x, const float* y, float* out, int64_t n_rows, int len, int d,

@@ -1160,6 +1160,7 @@ extern "C" int bfb200_debug_fused_timing(unsigned long long* out8, int reset) {
 bool fused_supported(const bfb200_transformer& m) {
   if (m.d_model != FD || m.n_heads != FH || m.n_layers < 1) return false;
   if (m.d_ff < 1 || m.d_ff > 64 || m.ntoken < 2 || m.ntoken > FMAXV) return false;
+  if (m.site_flags & BFB200_SITE_HEAD_IN) return false;   // Head.bayes input dropout: fp32 path only
   // tiles + weight image + the worst-case alignment pad must fit the 227 KB a CTA can have
   const FusedLayout lay = fused_layout(m.n_layers, m.d_ff, m.site_flags);
   return fused_smem_bytes(lay) + 1024 <= kFusedSmemMax;

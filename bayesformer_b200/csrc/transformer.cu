@@ -37,8 +37,9 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 //   f16 / bf16 else : layered tensor-core path — TMA-fed tcgen05 GEMMs (gemm_tc.cu), tcgen05 attention
 //                     (attention_tc.cu), fp32 residual stream / LayerNorm; heads of width 64, len <= 256
 static bool use_fused(const bfb200_transformer& m) { return m.compute == BFB200_COMPUTE_F16 && fused_supported(m); }
+// the per-head input-dropout site (Head.bayes) is served by the fp32 kernels only
 static bool tc_shape_ok(const bfb200_transformer& m) {
-  return m.n_layers >= 1 && m.d_model == m.n_heads * 64 && (m.d_ff & 7) == 0 && m.d_ff >= 8;
+  return !(m.site_flags & BFB200_SITE_HEAD_IN) && m.n_layers >= 1 && m.d_model == m.n_heads * 64 && (m.d_ff & 7) == 0 && m.d_ff >= 8;
 }
 static bool use_tc(const bfb200_transformer& m) {
   return (m.compute == BFB200_COMPUTE_F16 && !fused_supported(m)) || m.compute == BFB200_COMPUTE_BF16;
@@ -140,6 +141,8 @@ static int validate_model(const bfb200_transformer* m) {
   BFB_REQUIRE(m->compute == BFB200_COMPUTE_FP32 || m->compute == BFB200_COMPUTE_F16 || m->compute == BFB200_COMPUTE_BF16,
               BFB200_ERR_INVALID_ARG, "unknown compute type %d", m->compute);
   if (m->compute != BFB200_COMPUTE_FP32) {
+    BFB_REQUIRE(!(m->site_flags & BFB200_SITE_HEAD_IN), BFB200_ERR_UNSUPPORTED,
+                "the Head.bayes input-dropout site runs on the fp32 path only (compute = BFB200_COMPUTE_FP32)");
     BFB_REQUIRE(use_fused(*m) || tc_shape_ok(*m), BFB200_ERR_UNSUPPORTED,
                 "16-bit tensor-core compute serves (a) f16: d_model 64, 8 heads, F <= 64, V <= 128 (fused kernel) and "
                 "(b) f16 / bf16: heads of width 64, F %% 8 == 0 (layered tensor-core path); got d=%d H=%d F=%d V=%d L=%d",
@@ -165,7 +168,7 @@ static MaskSource make_mask_source(const bfb200_transformer& m, const bfb200_mas
   ms.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   ms.threshold = keep_threshold(p);
   ms.scale = 1.0f / (1.0f - p);
-  ms.n_sites = 1 + BFB200_SITES_PER_LAYER * m.n_layers;
+  ms.n_sites = 1 + BFB200_SITES_PER_LAYER * m.n_layers + ((m.site_flags & BFB200_SITE_HEAD_IN) ? 3 * m.n_heads * m.n_layers : 0);
   ms.max_len = masks != nullptr ? masks->max_len : 0;
   ms.words = (m.d_model + 31) / 32;
   ms.n_draws = 1;
@@ -187,7 +190,11 @@ static int forward_chunk(const bfb200_transformer& m, Workspace& ws, int64_t S, 
     const int sb = 1 + BFB200_SITES_PER_LAYER * l;
     const float* wqkv = m.w_qkv + (size_t)l * 3 * d * d;
     const float* wout = m.w_out + (size_t)l * d * d;
-    BFB_CALL(launch_sgemm(ws.x, wqkv, nullptr, ws.qkv, R, 3 * d, d, 1, 0, 0, st));
+    if (fl & BFB200_SITE_HEAD_IN)   // Head.bayes: three masked copies of x per head (transformer.py:50-53)
+      BFB_CALL(launch_qkv_head_in(ws.x, wqkv, ws.qkv, S, len, d, m.n_heads, ms,
+                                  1 + BFB200_SITES_PER_LAYER * m.n_layers + 3 * m.n_heads * l, st));
+    else
+      BFB_CALL(launch_sgemm(ws.x, wqkv, nullptr, ws.qkv, R, 3 * d, d, 1, 0, 0, st));
     BFB_CALL(launch_attention(ws.qkv, ws.att, S, len, d, m.n_heads, ms,
                               (fl & BFB200_SITE_HEAD_OUT) ? sb + 4 : -1, st));
     BFB_CALL(launch_sgemm(ws.att, wout, nullptr, ws.y, R, d, d, 1, 0, 0, st));

@@ -989,4 +989,57 @@ int launch_step_mean(const float* step_scores, int64_t n_items, int n_steps, flo
   return BFB200_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Head.bayes (transformer.py:50-53, a latent site: Head(..., bayes=True) built by hand): every head draws THREE
+// independent (l, B, d) masks, one per projection, on the block input:
+//   Q_h = W_q,h (x * m_hq / (1 - p)),  K_h = W_k,h (x * m_hk / (1 - p)),  V_h = W_v,h (x * m_hv / (1 - p))
+// so the packed QKV product does not apply (3 H differently masked copies of x).  One block per token row: the row
+// and the 3 H keep masks (d bits each) are staged in shared memory, then thread = output element.  Correctness path
+// of a site nothing constructs by default; not tuned.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qkv_head_in_kernel(const float* __restrict__ x, const float* __restrict__ w_qkv,
+                                                          float* __restrict__ qkv, int64_t n_rows, int len, int d,
+                                                          int n_heads, MaskSource ms, int site_base) {
+  extern __shared__ float hin_smem[];
+  float* xs = hin_smem;                                         // d
+  uint32_t* keep = reinterpret_cast<uint32_t*>(hin_smem + d);   // 3 H x ceil(d / 32) words
+  const int words = (d + 31) >> 5, dh = d / n_heads, n_sites = 3 * n_heads;
+  for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const int64_t s = r / len;
+    const uint32_t t = (uint32_t)(r - s * len);
+    for (int f = threadIdx.x; f < d; f += blockDim.x) xs[f] = x[r * d + f];
+    for (int i = threadIdx.x; i < n_sites * words; i += blockDim.x) {
+      const int site = i / words, w = i - site * words;
+      uint32_t bits = 0u;
+      for (int q = 0; q < 8 && (w * 8 + q) * 4 < d; ++q)
+        bits |= keep4(ms, s, t, (uint32_t)(site_base + site), (uint32_t)(w * 8 + q)) << (4 * q);
+      keep[i] = bits;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 3 * d; o += blockDim.x) {
+      const int c = o / d, within = o - c * d, h = within / dh;   // output column o = c * d + h * dh + j
+      const uint32_t* kb = keep + (3 * h + c) * words;
+      const float* wrow = w_qkv + (int64_t)o * d;
+      float acc = 0.f;
+      for (int f = 0; f < d; ++f) {
+        const float xv = (kb[f >> 5] >> (f & 31)) & 1u ? xs[f] * ms.scale : 0.f;
+        acc = fmaf(xv, __ldg(wrow + f), acc);
+      }
+      qkv[r * 3 * d + o] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_qkv_head_in(const float* x, const float* w_qkv, float* qkv, int64_t n_seq, int len, int d, int n_heads,
+                       const MaskSource& ms, int site_base, cudaStream_t st) {
+  const int64_t rows = n_seq * len;
+  if (rows == 0) return BFB200_OK;
+  const size_t smem = (size_t)d * 4 + (size_t)3 * n_heads * ((d + 31) / 32) * 4;
+  BFB_REQUIRE(smem <= 48 * 1024, BFB200_ERR_UNSUPPORTED, "Head.bayes site: d_model %d x %d heads exceeds the staging buffer", d, n_heads);
+  qkv_head_in_kernel<<<stride_grid(rows, 8), 256, smem, st>>>(x, w_qkv, qkv, rows, len, d, n_heads, ms, site_base);
+  BFB_LAUNCH_CHECK("qkv_head_in_kernel", st);
+  return BFB200_OK;
+}
+
 }  // namespace bfb

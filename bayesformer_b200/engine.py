@@ -396,9 +396,12 @@ def site_flags_of(module) -> tuple[int, float]:
         if getattr(layer.self_attn, "bayes", False):
             lf |= _lib.SITE_HEAD_OUT
             rates.add(layer.self_attn.bayes_dropout)
-        if any(getattr(h, "bayes", False) for h in layer.self_attn.heads):
-            raise NotImplementedError(
-                "per-head Q/K/V input dropout (Head.bayes, reference transformer.py:50-53) is not on the native path")
+        head_flags = [bool(getattr(h, "bayes", False)) for h in layer.self_attn.heads]
+        if any(head_flags):   # Head.bayes (reference transformer.py:50-53): three input masks per head, fp32 path only
+            if not all(head_flags):
+                raise NotImplementedError("native path needs Head.bayes set on all heads of a layer or on none")
+            lf |= _lib.SITE_HEAD_IN
+            rates.update(h.bayes_dropout for h in layer.self_attn.heads)
         per_layer.append(lf)
     if len(set(per_layer)) > 1:
         raise NotImplementedError("native path needs the same latent dropout sites in every layer")

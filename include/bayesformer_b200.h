@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BFB200_ABI_VERSION 3
+#define BFB200_ABI_VERSION 4
 
 enum {
   BFB200_OK = 0,
@@ -67,7 +67,9 @@ enum {
   BFB200_SITE_ATTN_RESID = 1u << 2, /* :226, latent: TransformerBlock.bayes              */
   BFB200_SITE_FFN_IN = 1u << 3,     /* :167-168, latent: FeedForward.bayes_dropout       */
   BFB200_SITE_FFN_RESID = 1u << 4,  /* :228, latent: TransformerBlock.bayes              */
-  BFB200_SITE_HEAD_OUT = 1u << 5    /* :116-122, latent: MultiHeadAttention.bayes        */
+  BFB200_SITE_HEAD_OUT = 1u << 5,   /* :116-122, latent: MultiHeadAttention.bayes        */
+  BFB200_SITE_HEAD_IN = 1u << 6     /* :50-53, latent: Head.bayes — three independent (l,B,d) masks per head on the
+                                       inputs of its Q, K and V projections (fp32 path only)    */
 };
 
 /* site ids used in the Philox counter and in the packed-mask layout:
@@ -77,6 +79,9 @@ enum {
  *   1 + 5*i + 2      : layer i FFN input     (FFN_IN)
  *   1 + 5*i + 3      : layer i FFN residual  (FFN_RESID)
  *   1 + 5*i + 4      : layer i head outputs  (HEAD_OUT, all heads concatenated)
+ *   1 + 5*L + 3*(i*H + h) + c : layer i, head h, input of projection c (0 Q, 1 K, 2 V)   (HEAD_IN; these sites
+ *                      exist — in the counter scheme and in the packed-mask layout — only when the flag is set:
+ *                      n_sites = 1 + 5*L + 3*H*L then)
  */
 #define BFB200_SITES_PER_LAYER 5
 #define BFB200_SITE_SAMPLING_TOKEN 0xFFFFu /* multinomial draw of the sampling scheme */

@@ -159,6 +159,43 @@ def latent_sites(ref):
     print("latent_sites.npz", logp.shape, len(log))
 
 
+def head_in_sites(ref):
+    """Head.bayes (reference transformer.py:50-53): every head built with bayes=True draws three independent input
+    masks; together with MultiHeadAttention.bayes (head outputs) and the default sites.  One forward pass."""
+    tr = ref.transformer
+    torch.manual_seed(9)
+    V, d, H, F, L, n_pos, B, p = 20, 32, 4, 16, 2, 6, 3, 0.25
+    model = tr.MyTransformer(V, d, H, F, L, bayes_dropout=p, bayes=True).eval()
+    for layer in model.layers:
+        layer.self_attn.bayes, layer.self_attn.bayes_dropout = True, p
+        for head in layer.self_attn.heads:
+            head.bayes, head.bayes_dropout = True, p
+    src = torch.randint(0, V, (n_pos, B))
+    log = []
+    with torch.no_grad(), ref_shim.record_dropout(log):
+        logp = model(src)
+    # order (SURVEY 3.2, verified by instrumenting F.dropout): E; per layer: per head Q, K, V inputs (n_pos,B,d) then that
+    # head's output (n_pos,B,dh); LO
+    assert len(log) == 1 + L * (4 * H + 1)
+    packed = R.PackedMasks(1, L, B, n_pos, d, H)
+    it = iter(log)
+    packed.set(0, R.SITE_EMBED, next(it).numpy())
+    for i in range(L):
+        ho = []
+        for h in range(H):
+            for c in range(3):
+                m = next(it).numpy()
+                assert m.shape == (n_pos, B, d)
+                packed.set(0, R.site_head_in(i, h, c, L, H), m)
+            ho.append(next(it).numpy())
+        packed.set(0, R.site_head_out(i), np.concatenate(ho, axis=-1))
+        packed.set(0, R.site_layer_out(i), next(it).numpy())
+    out = {"src": src.numpy(), "logp": logp.numpy(), "bits": packed.bits, "p": p, "dims": np.array([V, d, H, F, L])}
+    out.update({"sd." + k: v for k, v in sd_to_np(model.state_dict()).items()})
+    np.savez_compressed(os.path.join(OUT, "head_in_sites.npz"), **out)
+    print("head_in_sites.npz", logp.shape, len(log))
+
+
 def mid_model(ref):
     """dh=32, len=40 (two keys per lane in attention), L=3, p=0.2 — plain forward with recorded masks."""
     tr = ref.transformer
@@ -340,11 +377,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["transformer", "latent", "mid", "c4", "c1", "classifiers", "misc"]
+    which = sys.argv[1:] or ["transformer", "latent", "headin", "mid", "c4", "c1", "classifiers", "misc"]
     if "transformer" in which:
         main_transformer(ref)
     if "latent" in which:
         latent_sites(ref)
+    if "headin" in which:
+        head_in_sites(ref)
     if "mid" in which:
         mid_model(ref)
     if "c4" in which:

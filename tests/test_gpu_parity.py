@@ -314,6 +314,36 @@ def test_forward_latent_sites(engine, dev):
     np.testing.assert_allclose(got, z["logp"], rtol=RTOL, atol=ATOL_LOGP)
 
 
+def test_forward_head_in_sites(engine, dev):
+    """Head.bayes (reference transformer.py:50-53): three independent (l, B, d) input masks per head — the reference's
+    own masks injected (tests/golden/head_in_sites.npz), together with the head-output and default sites."""
+    z = H.load("head_in_sites.npz")
+    sd, p = H.state_dict_from(z), float(z["p"])
+    model = H.build_model(sd, p, True)
+    for layer in model.layers:
+        layer.self_attn.bayes, layer.self_attn.bayes_dropout = True, p
+        for head in layer.self_attn.heads:
+            head.bayes, head.bayes_dropout = True, p
+    model = model.to(dev)
+    pack = model.native_pack(dev)          # fp32: the only path that serves this site
+    with torch.no_grad():
+        got = engine.transformer_forward(pack, torch.from_numpy(z["src"]).to(dev), mask_bits=_bits(z["bits"], dev)).cpu().numpy()
+    np.testing.assert_allclose(got, z["logp"], rtol=RTOL, atol=ATOL_LOGP)
+    with pytest.raises(NotImplementedError):
+        model.native_pack(dev, "fp16")
+    # Philox mode: the library's counter scheme for the new sites against the oracle run with the same masks
+    V, d, Hh, F, L = (int(v) for v in z["dims"])
+    src = torch.from_numpy(z["src"])
+    seed, draw, base = 0xABCDEF12345, 3, 70
+    with torch.no_grad():
+        got = engine.transformer_forward(pack, src.to(dev), seed=seed, draw=draw, index_base=base).cpu().numpy()
+    live = ({R.SITE_EMBED} | {R.site_layer_out(i) for i in range(L)} | {R.site_head_out(i) for i in range(L)}
+            | {R.site_head_in(i, h, c, L, Hh) for i in range(L) for h in range(Hh) for c in range(3)})
+    B = src.shape[1]
+    want = R.transformer_forward(sd, src, p, R.philox_mask_fn(seed, p, np.arange(base, base + B), np.full(B, draw), 0, d, live))
+    np.testing.assert_allclose(got, want.numpy(), rtol=RTOL, atol=ATOL_LOGP)
+
+
 def test_forward_deterministic_model_matches_golden_greedy_step0(engine, dev):
     z = H.load("c2_transformer.npz")
     got = _native_forward(engine, dev, H.state_dict_from(z), None, False, z["prompts"], None)

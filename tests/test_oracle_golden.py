@@ -68,6 +68,23 @@ def test_latent_sites_forward():
     np.testing.assert_allclose(out.numpy(), z["logp"], rtol=2e-5, atol=2e-5)
 
 
+def test_head_in_sites_forward():
+    """Head.bayes (reference transformer.py:50-53): three independent input masks per head, recorded from the reference."""
+    z = H.load("head_in_sites.npz")
+    sd = H.state_dict_from(z)
+    V, d, Hh, F, L = (int(v) for v in z["dims"])
+    pm = R.PackedMasks(1, L, z["bits"].shape[2], z["bits"].shape[3], d, Hh)
+    pm.bits = z["bits"]
+    live = ({R.SITE_EMBED} | {R.site_layer_out(i) for i in range(L)} | {R.site_head_out(i) for i in range(L)}
+            | {R.site_head_in(i, h, c, L, Hh) for i in range(L) for h in range(Hh) for c in range(3)})
+    out = R.transformer_forward(sd, torch.from_numpy(z["src"]), float(z["p"]), pm.mask_fn(0, live))
+    np.testing.assert_allclose(out.numpy(), z["logp"], rtol=2e-5, atol=2e-5)
+    # the site matters: without the head-input masks the outputs differ
+    out2 = R.transformer_forward(sd, torch.from_numpy(z["src"]), float(z["p"]),
+                                 pm.mask_fn(0, {s for s in live if s < R.n_sites(L)}))
+    assert np.abs(out2.numpy() - z["logp"]).max() > 1e-2
+
+
 def test_mid_model_forward():
     z = H.load("mid_model.npz")
     sd = H.state_dict_from(z)
