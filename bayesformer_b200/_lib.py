@@ -89,6 +89,29 @@ class McArgs(C.Structure):
     ]
 
 
+class TrainSegment(C.Structure):
+    """struct bfb200_train_segment"""
+
+    _fields_ = [("offset", C.c_int32), ("count", C.c_int32), ("ptr", C.c_void_p)]
+
+
+class TrainArgs(C.Structure):
+    """struct bfb200_train_args"""
+
+    _fields_ = [
+        ("ntoken", C.c_int32), ("d_model", C.c_int32), ("n_heads", C.c_int32), ("d_ff", C.c_int32),
+        ("n_layers", C.c_int32), ("pe_len", C.c_int32),
+        ("batch", C.c_int32), ("seq_len", C.c_int32), ("prompt_len", C.c_int32),
+        ("n_segments", C.c_int32), ("step", C.c_int32),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("p_train", C.c_float), ("p_bayes", C.c_float), ("ln_eps", C.c_float),
+        ("seed", C.c_uint64),
+        ("segments", C.c_void_p), ("tokens", C.c_void_p), ("pe", C.c_void_p),
+        ("flat", C.c_void_p), ("grad", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+        ("scratch", C.c_void_p), ("loss_out", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 # every symbol include/bayesformer_b200.h declares: name -> (restype, argtypes)
 _SIGNATURES = {
@@ -124,6 +147,10 @@ _SIGNATURES = {
                                    C.c_int32, _P]),
     "bfb200_attention_tc": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bfb200_step_mean": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    "bfb200_train_state_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "bfb200_train_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "bfb200_train_flat_offset": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "bfb200_train_step": (C.c_int, [C.POINTER(TrainArgs), _P]),
     "bfb200_launch_count": (C.c_int64, []),
     "bfb200_reset_launch_count": (None, []),
     "bfb200_profile_begin": (C.c_int, [_P]),

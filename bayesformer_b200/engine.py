@@ -597,3 +597,105 @@ def default_mc_workspace_bytes(pack: PackedTransformer, args, n_items: int) -> i
         return full
     one = lib.bfb200_mc_workspace_bytes(C.byref(pack.desc), C.byref(args), 1)
     return max(one, _MAX_WORKSPACE_BYTES)
+
+
+# ---------------------------------------------------------------------------
+# fused fine-tune step (reference src/libs/utils.py:68-78)
+# ---------------------------------------------------------------------------
+
+
+class FusedTrainer:
+    """AdamW fine-tuning of a MyTransformer of the notebook class (d_model 64, 8 heads, default dropout sites) through
+    `bfb200_train_step`: forward, loss, backward and the update of one batch per kernel launch.  Holds the optimizer
+    state (flat first / second moments, step count) and the segment table that maps the module's parameter tensors to
+    the kernel's flat layout; the parameters themselves stay in the module (updated in place, like torch.optim.AdamW).
+    """
+
+    BETAS, EPS, WEIGHT_DECAY = (0.9, 0.999), 1e-8, 0.01   # torch.optim.AdamW defaults, as the reference uses them
+    MAX_SEQ = 16                                          # csrc/train_fused.cu TMAXT
+
+    @staticmethod
+    def supports(module) -> bool:
+        try:
+            flags, _p = site_flags_of(module)
+        except (NotImplementedError, ValueError):
+            return False
+        if flags & ~(_lib.SITE_EMBED | _lib.SITE_LAYER_OUT):
+            return False   # latent block-level sites: the eager / graphed path trains those
+        heads = module.layers[0].self_attn.heads if len(module.layers) else []
+        return (len(module.layers) >= 1 and module.embedding.weight.shape[1] == 64 and len(heads) == 8
+                and module.embedding.weight.is_cuda and module.embedding.weight.dtype == torch.float32)
+
+    def __init__(self, module, lr: float):
+        lib = _lib.load()
+        self.module, self.lr = module, float(lr)
+        dev = module.embedding.weight.device
+        self.device = dev
+        V = module.embedding.weight.shape[0]
+        L = len(module.layers)
+        F = module.layers[0].ff.net[0].weight.shape[0]
+        self.V, self.F, self.L = V, F, L
+        self.n_state = int(lib.bfb200_train_state_floats(V, F, L))
+        off = lambda layer, which: int(lib.bfb200_train_flat_offset(V, F, L, layer, which))
+        segs = [(off(0, 0), module.embedding.weight)]
+        for i, layer in enumerate(module.layers):
+            base = off(i, 1)
+            for c, name in enumerate(("W_q", "W_k", "W_v")):
+                for h, head in enumerate(layer.self_attn.heads):
+                    segs.append((base + (c * 64 + h * 8) * 64, getattr(head, name).weight))
+            segs += [(off(i, 2), layer.self_attn.W_out.weight), (off(i, 3), layer.norm1.weight), (off(i, 4), layer.norm1.bias),
+                     (off(i, 5), layer.ff.net[0].weight), (off(i, 6), layer.ff.net[0].bias),
+                     (off(i, 7), layer.ff.net[2].weight), (off(i, 8), layer.ff.net[2].bias),
+                     (off(i, 9), layer.norm2.weight), (off(i, 10), layer.norm2.bias)]
+        segs += [(off(0, 11), module.linear_out.weight), (off(0, 12), module.linear_out.bias)]
+        covered = sum(p.numel() for _, p in segs)
+        if covered != self.n_state or covered != sum(p.numel() for p in module.parameters()):
+            raise RuntimeError("segment table does not cover the module's parameters")
+        for _, p in segs:
+            if not p.is_contiguous() or p.dtype != torch.float32 or p.device != dev:
+                raise RuntimeError("fused training needs contiguous fp32 parameters on one CUDA device")
+        self._params = [p for _, p in segs]
+        arr = (_lib.TrainSegment * len(segs))(*[_lib.TrainSegment(o, p.numel(), p.data_ptr()) for o, p in segs])
+        self.segments = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.n_segments = len(segs)
+        self.flat = torch.empty(self.n_state, dtype=torch.float32, device=dev)
+        self.grad = torch.empty(self.n_state, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(self.n_state, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(self.n_state, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self._scratch = None
+        self.pe = module.pos_enc.pe.detach().reshape(-1, 64).to(dev, torch.float32).contiguous()
+
+    def valid_for(self, module) -> bool:
+        """The segment table holds raw pointers: still pointing at this module's (unmoved) parameters?"""
+        return module is self.module and all(p.data_ptr() == int(s.ptr) for p, s in zip(self._params, self._segment_view()))
+
+    def _segment_view(self):
+        raw = bytes(self.segments.cpu().numpy().tobytes())
+        return (_lib.TrainSegment * self.n_segments).from_buffer_copy(raw)
+
+    def step(self, tokens: torch.Tensor, prompt_len: int, p_train: float, p_bayes: float, seed: int | None = None) -> None:
+        """One AdamW step on the batch `tokens` (T, B) int64 = prompts followed by answers; the batch's mean loss is
+        ADDED to `self.loss` (read it once per epoch)."""
+        lib = _lib.load()
+        T, B = tokens.shape
+        tokens = tokens.to(self.device, torch.int64).contiguous()
+        need = int(lib.bfb200_train_scratch_floats(B, T, prompt_len, self.V, self.F, self.L))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        self.step_count += 1
+        if seed is None:
+            seed = default_seed() ^ (_next_call_id(self.device) << 32)
+        b1, b2 = self.BETAS
+        args = _lib.TrainArgs(
+            ntoken=self.V, d_model=64, n_heads=8, d_ff=self.F, n_layers=self.L, pe_len=self.pe.shape[0],
+            batch=B, seq_len=T, prompt_len=prompt_len, n_segments=self.n_segments, step=self.step_count,
+            lr=self.lr, beta1=b1, beta2=b2, eps=self.EPS, weight_decay=self.WEIGHT_DECAY,
+            p_train=float(p_train), p_bayes=float(p_bayes), ln_eps=1e-5, seed=seed & 0xFFFFFFFFFFFFFFFF,
+            segments=self.segments.data_ptr(), tokens=tokens.data_ptr(), pe=self.pe.data_ptr(),
+            flat=self.flat.data_ptr(), grad=self.grad.data_ptr(), adam_m=self.adam_m.data_ptr(),
+            adam_v=self.adam_v.data_ptr(), scratch=self._scratch.data_ptr(), loss_out=self.loss.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(lib.bfb200_train_step(C.byref(args), _stream_ptr(self.device)))
+        mark_weights_changed(self.module)   # in-place updates behind autograd's back: the scoring packs must follow

@@ -107,6 +107,40 @@ def _graph_state(model, lr: float, criterion, device):
     return optimizer, graphs
 
 
+_FUSED_TRAINERS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _fused_enabled(model, device) -> bool:
+    """The hand-written fused step (csrc/train_fused.cu) serves the notebook model class on a CUDA device; set
+    BFB200_FUSED_TRAIN=0 for the graphed / eager autograd loop."""
+    import os
+
+    if torch.device(device).type != "cuda" or os.environ.get("BFB200_FUSED_TRAIN", "1") == "0":
+        return False
+    from bayesformer_b200 import engine
+
+    return isinstance(model, MyTransformer) and engine.FusedTrainer.supports(model)
+
+
+def _fused_trainer(model, lr: float):
+    """Per-model trainer; like the reference, every train() call starts from a FRESH AdamW state (utils.py:51)."""
+    from bayesformer_b200 import engine
+
+    tr = _FUSED_TRAINERS.get(model)
+    if tr is None or not tr.valid_for(model):
+        tr = _FUSED_TRAINERS[model] = engine.FusedTrainer(model, lr)
+    tr.lr = float(lr)
+    tr.adam_m.zero_()
+    tr.adam_v.zero_()
+    tr.step_count = 0
+    return tr
+
+
+def _train_dropout_rate(model) -> float:
+    """nn.Dropout rate of the training-only sites (one rate for the whole model: MyTransformer(dropout=...))."""
+    return float(model.pos_enc.dropout.p)
+
+
 def _graphs_enabled(device) -> bool:
     import os
 
@@ -121,21 +155,43 @@ def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, ba
     On a CUDA device every distinct batch shape is captured once as a CUDA graph (`_GraphedTrainStep`; set
     BFB200_GRAPH_TRAIN=0 for the plain eager loop) and the batch losses are summed on the device, read once per epoch.
     """
-    use_graphs = _graphs_enabled(device)
+    use_fused = _fused_enabled(model, device)
+    use_graphs = not use_fused and _graphs_enabled(device)
     criterion = nn.CrossEntropyLoss()
-    if use_graphs:
+    trainer = None
+    batches: dict[int, tuple] = {}
+    if use_fused:
+        # the fused step keeps a query's score row in registers: sequences of at most 16 tokens (the notebooks' are 9);
+        # every batch is tokenised and copied to the device once per call
+        from bayesformer_b200 import engine
+
+        for start in range(0, len(train_dataset) - 1, batch_size):
+            prompts, answers, p_len, a_len, _, _ = preprocessing.get_batch(train_dataset, tokenizer, start, batch_size)
+            batches[start] = (torch.cat((prompts, answers), 0).to(device), p_len)
+        if any(t.shape[0] > engine.FusedTrainer.MAX_SEQ for t, _ in batches.values()):
+            use_fused, use_graphs, batches = False, _graphs_enabled(device), {}
+    if use_fused:
+        trainer = _fused_trainer(model, lr)
+        optimizer, graphs = None, {}
+    elif use_graphs:
         optimizer, graphs = _graph_state(model, lr, criterion, device)
     else:
         optimizer, graphs = torch.optim.AdamW(model.parameters(), lr=lr), {}
     history_train, history_valid = [], []
     best = float("inf")
-    batches: dict[int, tuple] = {}
     try:
         for epoch in range(1, nb_epochs + 1):
             model.train()
             running = 0.0
             running_dev = torch.zeros((), device=device) if use_graphs else None
+            if use_fused:
+                trainer.loss.zero_()
             for start in range(0, len(train_dataset) - 1, batch_size):
+                if use_fused:
+                    # ONE kernel per batch: forward, loss, backward, AdamW (csrc/train_fused.cu)
+                    tokens, p_len = batches[start]
+                    trainer.step(tokens, p_len, _train_dropout_rate(model), float(model.bayes_dropout) if model.bayes else 0.0)
+                    continue
                 if use_graphs:
                     # the reference walks the same slices in the same order every epoch (no shuffling, :60): each batch is
                     # tokenised and copied to the device once per call
@@ -154,6 +210,8 @@ def train(model: MyTransformer, train_dataset, valid_dataset, nb_epochs: int, ba
                 loss.backward()
                 optimizer.step()
                 running += loss.item()
+            if use_fused:
+                running = float(trainer.loss.item())
             if use_graphs:
                 running = float(running_dev.item())
                 from bayesformer_b200 import engine

@@ -281,6 +281,51 @@ int bfb200_linear_tc(const void* A, int64_t a_pitch, const void* W, const float*
 int bfb200_attention_tc(const void* qkv, void* out, int64_t n_seq, int32_t len, int32_t d_model, int32_t n_heads,
                         int32_t fmt, void* stream);
 
+/*
+ * One fine-tune step of the reference's training loop (src/libs/utils.py:68-78: model(batch) in train mode,
+ * CrossEntropyLoss on the log-softmax outputs of the answer positions, backward, AdamW.step()) for the notebook
+ * model class (d_model 64, 8 heads) as ONE kernel launch — forward, loss, backward and the parameter update.
+ * The parameters stay in the module's own tensors: `segments` maps them to the flat layout the kernel works in
+ * (bfb200_train_flat_offset gives the layout; per-head W_q/W_k/W_v are rows [c*64 + h*8, +8) of the layer's W_qkv
+ * block, c = 0 Q, 1 K, 2 V).  adam_m / adam_v persist between steps (zero before the first), `step` counts from 1.
+ * Dropout masks (nn.Dropout at rate p_train on the positional-encoding output and on both branch outputs,
+ * transformer.py:231-233, :272; the always-on bayes sites at rate p_bayes, :356, :370) are drawn from Philox with key
+ * `seed`; both rates 0 give the deterministic step the parity test compares with eager autograd.
+ */
+typedef struct bfb200_train_segment {
+  int32_t offset; /* first float of the segment in the flat layout */
+  int32_t count;  /* floats */
+  float* ptr;     /* [dev] the parameter tensor's storage (contiguous) */
+} bfb200_train_segment;
+
+typedef struct bfb200_train_args {
+  int32_t ntoken, d_model, n_heads, d_ff, n_layers, pe_len;
+  int32_t batch, seq_len, prompt_len; /* tokens (seq_len, batch): prompt_len prompt rows, then the answer rows */
+  int32_t n_segments;
+  int32_t step;                        /* AdamW step number of this call (1, 2, ...) */
+  float lr, beta1, beta2, eps, weight_decay;
+  float p_train, p_bayes, ln_eps;
+  uint64_t seed;
+  const bfb200_train_segment* segments; /* [dev] n_segments entries covering the flat layout exactly once */
+  const int64_t* tokens;                /* [dev] (seq_len, batch) */
+  const float* pe;                      /* [dev] (pe_len, d_model) */
+  float* flat;                          /* [dev] bfb200_train_state_floats() floats: parameter scratch */
+  float* grad;                          /* [dev] same size: gradients of this step (output, for inspection) */
+  float* adam_m;                        /* [dev] same size, persistent */
+  float* adam_v;                        /* [dev] same size, persistent */
+  float* scratch;                       /* [dev] bfb200_train_scratch_floats() floats */
+  float* loss_out;                      /* [dev] 1 float: += mean loss of the batch */
+} bfb200_train_args;
+
+size_t bfb200_train_state_floats(int32_t ntoken, int32_t d_ff, int32_t n_layers);
+size_t bfb200_train_scratch_floats(int32_t batch, int32_t seq_len, int32_t prompt_len, int32_t ntoken, int32_t d_ff,
+                                   int32_t n_layers);
+/* flat offset of a parameter: which = 0 embedding, 1 W_qkv, 2 W_out, 3 norm1.weight, 4 norm1.bias, 5 ff.net.0.weight,
+ * 6 ff.net.0.bias, 7 ff.net.2.weight, 8 ff.net.2.bias, 9 norm2.weight, 10 norm2.bias (1..10: of `layer`),
+ * 11 linear_out.weight, 12 linear_out.bias */
+int bfb200_train_flat_offset(int32_t ntoken, int32_t d_ff, int32_t n_layers, int32_t layer, int32_t which);
+int bfb200_train_step(const bfb200_train_args* args, void* stream);
+
 /* torch.mean(uncertainties, dim=0) of select_samples (src/libs/active_learning.py:209):
  * step_scores (n_steps, n_items) -> pool_scores (n_items), steps summed in order then divided. */
 int bfb200_step_mean(const float* step_scores, int32_t n_steps, int64_t n_items, float* pool_scores,

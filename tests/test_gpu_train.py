@@ -15,6 +15,7 @@ def _run(monkeypatch, graphs: bool, model, data, tok, dev, epochs=3):
     from bayesformer_b200.libs import utils
 
     monkeypatch.setenv("BFB200_GRAPH_TRAIN", "1" if graphs else "0")
+    monkeypatch.setenv("BFB200_FUSED_TRAIN", "0")   # this file tests the autograd loops (the fused step: test_gpu_train_fused.py)
     m = copy.deepcopy(model)
     torch.manual_seed(5)
     hist = utils.train(m, data[0], data[1], epochs, 20, 1e-3, tok.ntokens, tok, dev)
@@ -58,6 +59,7 @@ def test_graphed_training_with_dropout_learns(monkeypatch):
     data = (preprocessing.create_dataset(200, 3), preprocessing.create_dataset(40, 3))
     model = MyTransformer(tok.ntokens, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).to(dev)
     monkeypatch.setenv("BFB200_GRAPH_TRAIN", "1")
+    monkeypatch.setenv("BFB200_FUSED_TRAIN", "0")
     tr, va = utils.train(model, data[0], data[1], 12, 20, 1e-3, tok.ntokens, tok, dev)
     assert tr[-1] < 0.8 * tr[0] and np.isfinite(tr).all() and np.isfinite(va).all()
     # two replays of one graph must not reuse a mask: consecutive epochs over the same batches give different losses
