@@ -213,6 +213,7 @@ struct FusedArgs {
   uint32_t site_flags;
   float ln_eps;
   uint32_t smem_bytes;         // dynamic shared memory of the launch
+  uint32_t opaque_zero;        // 0, unknown to the compiler: ties work meant to overlap a product to the wait that follows it
   // this launch
   int len;                     // tokens per sequence in this step
   int spt;                     // sequences per tile = 128 / len
@@ -506,22 +507,46 @@ __device__ __forceinline__ uint32_t half_keep_mask(const MaskSource& m, const Ro
   return philox_keep32(m.key.x, m.key.y, m.threshold, rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h));
 }
 
-// FAST instantiations (two dropout sites): the four Philox calls of a half row are inlined and decide straight on the
-// 16-bit halves of their output words, eight features at a time — no keep-bit packing / unpacking in between
-// (same decisions as philox_keep32 + drop_half: feature j of a call <- half j & 1 of word j >> 1, kept iff >= threshold).
-__device__ __forceinline__ void drop_half_direct(float (&v)[HW], const MaskSource& m, const RowRng& rr, uint32_t pos,
-                                                 uint32_t site, uint32_t h) {
+// FAST == 1 (two dropout sites): the four Philox calls of a half row decide straight on the 16-bit halves of their
+// output words, eight features at a time (same decisions as philox_keep32 + drop_half: feature j of a call <- half j & 1
+// of word j >> 1, kept iff >= threshold).  In two steps, so that the random words can be drawn while the group waits for
+// a product (they depend on the row's identity only) and applied after it: philox_half_raw during the wait,
+// drop_half_raw after; drop_half_direct does both at once.
+__device__ __forceinline__ void philox_half_raw(uint4 (&r)[4], const MaskSource& m, const RowRng& rr, uint32_t pos,
+                                                uint32_t site, uint32_t h) {
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c) {
+    r[c] = philox4x32_10(make_uint4(rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h + c)), m.key);
+  }
+}
+
+// A word that depends on every draw; the caller ANDs it with a run-time zero into the wait's operand so that ptxas
+// cannot schedule the draws after the wait (it otherwise hoists the first try_wait above independent arithmetic).
+__device__ __forceinline__ uint32_t fold_raw(const uint4 (&r)[4]) {
+  uint32_t f = 0u;
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c) f ^= r[c].x ^ r[c].y ^ r[c].z ^ r[c].w;
+  return f;
+}
+
+__device__ __forceinline__ void drop_half_raw(float (&v)[HW], const uint4 (&r)[4], const MaskSource& m) {
   const uint32_t thr_hi = m.threshold << 16;
 #pragma unroll
   for (uint32_t c = 0; c < 4; ++c) {
-    const uint4 r = philox4x32_10(make_uint4(rr.item, rr.draw, (m.step << 16) | pos, (site << 16) | (4u * h + c)), m.key);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t w[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
 #pragma unroll
     for (uint32_t i = 0; i < 4; ++i) {
       v[8 * c + 2 * i] = (w[i] << 16) >= thr_hi ? v[8 * c + 2 * i] * m.scale : 0.f;
       v[8 * c + 2 * i + 1] = w[i] >= thr_hi ? v[8 * c + 2 * i + 1] * m.scale : 0.f;
     }
   }
+}
+
+__device__ __forceinline__ void drop_half_direct(float (&v)[HW], const MaskSource& m, const RowRng& rr, uint32_t pos,
+                                                 uint32_t site, uint32_t h) {
+  uint4 r[4];
+  philox_half_raw(r, m, rr, pos, site, h);
+  drop_half_raw(v, r, m);
 }
 
 __device__ __forceinline__ void tmem_load_half(uint32_t taddr, float (&v)[HW]) {
@@ -792,7 +817,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   // next_wlo >= 0: the V tiles are dead from here on, so the issuing thread starts the bulk copies of that layer's
   // W_qkv lo rows into them (consumed by the next PR_QKV product, which waits for them).  stage_head: likewise the Q
   // tile is dead and receives the vocabulary head's weights (consumed by PR_HEAD).
-  auto product = [&](auto kind_c, int layer, int next_wlo, bool stage_head = false) {
+  // `overlap` runs between the issue and the wait: work that does not depend on the product (dropout draws).
+  auto product_ov = [&](auto kind_c, int layer, int next_wlo, bool stage_head, auto&& overlap) {
     constexpr int kind = decltype(kind_c)::value;
 #ifdef BFB_FUSED_TIMING
     const long long _t0 = clock64();
@@ -818,12 +844,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     }
     if (kind == PR_QKV) wlo_phase ^= 1u;
     if (kind == PR_HEAD) head_phase ^= 1u;
-    umma::mbar_wait(bar, phase);
+    umma::mbar_wait(bar, phase ^ (overlap() & a.opaque_zero));
     phase ^= 1u;
     umma::tc_fence_after_sync();
 #ifdef BFB_FUSED_TIMING
     if ((gt & 31) == 5) { dbg[0] += clock64() - _t0; dbg[1] += 1; }
 #endif
+  };
+  auto product = [&](auto kind_c, int layer, int next_wlo, bool stage_head = false) {
+    product_ov(kind_c, layer, next_wlo, stage_head, [] { return 0u; });
   };
 
   for (int64_t tile = tile_first; tile < a.n_tiles; tile += tile_step) {
@@ -1074,7 +1103,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
-      product(KindC<PR_FFN2>{}, l, -1, prune);   // last layer: the Q tile is dead now and receives the vocabulary head
+      uint4 rnd_out[4];   // FAST == 1: the layer-out site's random words, drawn while the FFN2 product runs
+      product_ov(KindC<PR_FFN2>{}, l, -1, prune,   // last layer: the Q tile is dead now and receives the vocabulary head
+                 [&] {
+                   if (FAST != 1) return 0u;
+                   philox_half_raw(rnd_out, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);
+                   return fold_raw(rnd_out);
+                 });
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (!FAST && (fl & BFB200_SITE_LAYER_OUT)) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
@@ -1089,7 +1124,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         red[h * FROWS + row] = own;
         umma::group_sync(pair_bar_id, 64);   // the two half-row threads of a row sit in warps w and w + 4
         ln_finish(v, own, red[(h ^ 1) * FROWS + row], pl + P_LN2W + h * HW, pl + P_LN2B + h * HW, a.ln_eps);
-        if (FAST == 1) drop_half_direct(v, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);   // transformer.py:370
+        if (FAST == 1) drop_half_raw(v, rnd_out, ms);   // transformer.py:370
         else if (fl & BFB200_SITE_LAYER_OUT) drop_half(v, k_out, ms.scale);
         store_hilo_half(tXh, tXl, v);   // next block's input / the vocabulary head's operand
       }
@@ -1216,6 +1251,7 @@ int launch_mc_forward_fused(const bfb200_transformer& m, const int32_t* tokens, 
   size_t smem = fused_smem_bytes(a.lay) + 1024;
   if (smem > kFusedSmemMax) smem = kFusedSmemMax;
   a.smem_bytes = (uint32_t)smem;
+  a.opaque_zero = 0u;
   int64_t grid = (a.n_tiles + FGROUPS - 1) / FGROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;

@@ -16,7 +16,7 @@ def hilo8(t):
     return hi.double() + lo.double()
 
 
-def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=False, v_lo=False, wv_lo=False, head_lo=False, wout_lo=False):
+def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=False, v_lo=False, wv_lo=False, head_lo=False, wout_lo=False, qk8=True, wqk_lo=True, xlo_qk=True):
     D = R.model_dims(sd); d, Hh, dh, L = D["d"], D["H"], D["dh"], D["L"]
     n = src.shape[0]; scale = 1.0 / (1.0 - p)
     x = sd["embedding.weight"].double()[src]
@@ -28,7 +28,10 @@ def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=F
         wq = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_q.weight"] for h in range(Hh)]).double()
         wk = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_k.weight"] for h in range(Hh)]).double()
         wv = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_v.weight"] for h in range(Hh)]).double()
-        q = hilo8(x @ hilo(wq).t()); k = hilo8(x @ hilo(wk).t())
+        fq = hilo8 if qk8 else r16
+        fw = hilo if wqk_lo else r16
+        xq = x if xlo_qk else r16(x)
+        q = fq(xq @ fw(wq).t()); k = fq(xq @ fw(wk).t())
         v = (hilo if v_lo else r16)(x @ (hilo if wv_lo else r16)(wv).t())
         S = x.shape[1]
         qh = q.view(n, S, Hh, dh).permute(1, 2, 0, 3); kh = k.view(n, S, Hh, dh).permute(1, 2, 0, 3)
@@ -60,7 +63,10 @@ def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=F
 
 if __name__ == "__main__":
     z = H.load("c2_transformer.npz"); sd = H.state_dict_from(z); p = float(z["p"])
-    E.VARIANTS = {"shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
+    S = dict(attn_lo=True, w2_lo=True, v_lo=True, wv_lo=True)
+    E.VARIANTS = {"shipped": S, "no_qk8": dict(S, qk8=False), "no_wqk_lo": dict(S, wqk_lo=False),
+                  "no_qk8_wqk": dict(S, qk8=False, wqk_lo=False), "no_qk8_wqk_xlo": dict(S, qk8=False, wqk_lo=False, xlo_qk=False),
+                  "no_w2lo": dict(S, w2_lo=False), "shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
                   "attn+w2+m+w1": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True),
                   "attn+w2+m+w1+v+wv": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True),
                   "all": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True, head_lo=True, wout_lo=True)}
