@@ -623,8 +623,12 @@ class FusedTrainer:
         if flags & ~(_lib.SITE_EMBED | _lib.SITE_LAYER_OUT):
             return False   # latent block-level sites: the eager / graphed path trains those
         heads = module.layers[0].self_attn.heads if len(module.layers) else []
-        return (len(module.layers) >= 1 and module.embedding.weight.shape[1] == 64 and len(heads) == 8
-                and module.embedding.weight.is_cuda and module.embedding.weight.dtype == torch.float32)
+        if not (len(module.layers) >= 1 and module.embedding.weight.shape[1] == 64 and len(heads) == 8
+                and module.embedding.weight.is_cuda and module.embedding.weight.dtype == torch.float32):
+            return False
+        # one sequence's activations must fit a CTA's shared memory (0 = they do not)
+        V, L, F = module.embedding.weight.shape[0], len(module.layers), module.layers[0].ff.net[0].weight.shape[0]
+        return int(_lib.load().bfb200_train_scratch_floats(1, FusedTrainer.MAX_SEQ, 1, V, F, L)) > 0
 
     def __init__(self, module, lr: float):
         lib = _lib.load()
@@ -682,6 +686,8 @@ class FusedTrainer:
         T, B = tokens.shape
         tokens = tokens.to(self.device, torch.int64).contiguous()
         need = int(lib.bfb200_train_scratch_floats(B, T, prompt_len, self.V, self.F, self.L))
+        if need == 0:
+            raise ValueError(f"fused train step does not take this batch shape (T={T}, B={B}, prompt {prompt_len})")
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
         self.step_count += 1

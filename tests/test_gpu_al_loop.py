@@ -53,7 +53,7 @@ def test_two_round_loop(setup):
     with engine.profile(dev) as prof:
         recs = al_loop.active_learning_rounds(model, tok, data["train"], data["valid"], data["test"], pool, dev, rounds=2,
                                               k=50, compute="dropout", mode="entropy", epochs=2, seed=7)
-    assert "mc_forward_kernel" in prof.kernels and "train_step_kernel" in prof.kernels and "topk_select_kernel" in prof.kernels
+    assert "mc_forward_kernel" in prof.kernels and "train_seq_kernel" in prof.kernels and "topk_select_kernel" in prof.kernels
     assert [r["train_size"] for r in recs] == [110, 160]
     assert all(len(set(r["picked"])) == 50 and 0.0 <= r["test_accuracy"] <= 1.0 for r in recs)
     # device-side gather == strings route: create_new_train_set + tokenisation (reference active_learning.py:214-233)

@@ -82,7 +82,7 @@ def test_fused_step_matches_eager_autograd_and_adamw(dev, F, L):
 
 
 def test_train_uses_the_fused_step_and_learns(dev):
-    """utils.train on a CUDA device runs `train_step_kernel` (one launch per batch) for the notebook model, with the
+    """utils.train on a CUDA device runs `train_seq_kernel` (one launch per batch, one CTA per sequence) for the notebook model, with the
     training-mode dropout sites live; the loss falls, the scoring packs follow the weights, and the graphed autograd
     path (BFB200_FUSED_TRAIN=0) reaches a comparable loss from the same start."""
     import os
@@ -103,7 +103,7 @@ def test_train_uses_the_fused_step_and_learns(dev):
     before = engine.mc_score_transformer(engine.scoring_pack(model, dev, 4, 5), prompts, 5, 4, "dropout", "entropy", seed=9)
     with engine.profile(dev) as prof:
         tr_loss, va_loss = utils.train(model, train_set, valid_set, 8, 20, 2e-3, tok.ntokens, tok, dev)
-    assert prof.kernels["train_step_kernel"]["launches"] == 8 * 10
+    assert prof.kernels["train_seq_kernel"]["launches"] == 8 * 10
     assert tr_loss[-1] < 0.8 * tr_loss[0] and np.isfinite(va_loss).all()
     model.eval()
     after = engine.mc_score_transformer(engine.scoring_pack(model, dev, 4, 5), prompts, 5, 4, "dropout", "entropy", seed=9)
