@@ -35,6 +35,7 @@ constexpr int TD = 64, TH = 8, TDH = 8;
 constexpr int TMAXT = 16;   // longest training sequence (prompt + answer + EOS): per-query score rows live in registers
 constexpr int TTHREADS = 1024;
 constexpr int TSMEM_MAX = 227 * 1024;
+constexpr int TSTAGE = 3 * TD * TD;   // floats of the weight stage: the largest matrix a phase parks (W_qkv)
 
 struct TrainLayout {   // offsets in floats inside the flat parameter layout
   int V, F, L;
@@ -188,9 +189,16 @@ __device__ __forceinline__ void fma4(float4& acc, float d, const float4& w) {
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 quad_sum(float4 v) {   // sum over the 4 lanes that share (lane >> 2)
+// "Quad" phases: out[r][4 f4 ..] = sum_c in[r][c] * Wm[c][4 f4 ..] with thread = (row r, feature group f4, quarter
+// `part` of the c range).  Lane bits 0-2 are the low bits of f4 and bits 3-4 the part, so the eight lanes of a
+// quarter-warp — the unit a 128-bit shared-memory load is served in — read 128 contiguous bytes of one Wm row
+// (with the part in the low lane bits they hit the same eight banks four times: measured 7.5 us instead of 2).
+__device__ __forceinline__ int quad_f4(int tid) { return (tid & 7) | ((tid >> 2) & 8); }
+__device__ __forceinline__ int quad_part(int tid) { return (tid >> 3) & 3; }
+__device__ __forceinline__ int quad_row(int tid) { return tid >> 6; }
+__device__ __forceinline__ float4 quad_sum(float4 v) {   // sum over the 4 lanes that differ in the part bits
 #pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {
+  for (int o = 8; o <= 16; o <<= 1) {
     v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o);
     v.z += __shfl_xor_sync(0xFFFFFFFFu, v.z, o); v.w += __shfl_xor_sync(0xFFFFFFFFu, v.w, o);
   }
@@ -265,6 +273,20 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
   const float inv_sqrt_dh = rsqrtf((float)TDH);
   const float sqrt_d = sqrtf((float)TD);
   float& s_loss = S[sc.total];   // one extra float behind the activations
+  // Weight stage (48 KB behind the activations): a phase that multiplies by a weight matrix first prefetches it into
+  // registers with coalesced loads (one L2 round trip for the whole CTA), does its weight-free work, then parks it here,
+  // so that the per-thread reduction loops read shared memory instead of paying the L2 latency once per unrolled batch.
+  float* WS = S + sc.total + 4;
+  auto prefetch = [&](float4 (&pf)[3], const float* src, int n4) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) pf[q] = tid + q * TTHREADS < n4 ? ld4(src + 4 * (tid + q * TTHREADS)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto park = [&](const float4 (&pf)[3], int n4) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) if (tid + q * TTHREADS < n4) st4(WS + 4 * (tid + q * TTHREADS), pf[q]);
+    __syncthreads();
+  };
+  float4 pf[3];
 #define FOR_T(i, n) for (int i = tid; i < (n); i += TTHREADS)
 
   // ---- forward ----------------------------------------------------------------------------------------------
@@ -297,16 +319,19 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     const uint32_t site0 = 4u * (uint32_t)l;
     const float* WTl = WT + l * gl.wt_layer;
     // Q, K, V of all heads (bias-free, transformer.py:54-57): thread = (row, four adjacent outputs)
+    prefetch(pf, WTl, 3 * TD * TD / 4);
+    park(pf, 3 * TD * TD / 4);
     FOR_T(i, T * (3 * TD / 4)) {
       const int r = i / (3 * TD / 4), c4 = i % (3 * TD / 4);
       const float* xr = X + r * TD;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 16
-      for (int k = 0; k < TD; ++k) fma4(acc, xr[k], ld4(WTl + k * 3 * TD + 4 * c4));
+      for (int k = 0; k < TD; ++k) fma4(acc, xr[k], ld4(WS + k * 3 * TD + 4 * c4));
       st4(QKV + r * 3 * TD + 4 * c4, acc);
     }
     cta_sync();
     // causal softmax(QK^T / sqrt(dh)) V, thread = (head, query) (transformer.py:58-65); scores in registers
+    prefetch(pf, WTl + gl.wt_out, TD * TD / 4);   // W_out^T for the next phase travels meanwhile
     FOR_T(i, TH * T) {
       const int h = i / T, t = i % T;
       const float* qp = QKV + t * 3 * TD + h * TDH;
@@ -345,6 +370,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
       st4(ATT + t * TD + h * TDH, o0);
       st4(ATT + t * TD + h * TDH + 4, o1);
     }
+    park(pf, TD * TD / 4);
     cta_sync();
     // W_out, nn.Dropout, residual from the block input (transformer.py:125, :231)
     FOR_T(i, T * (TD / 4)) {
@@ -352,7 +378,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
       const float* ar = ATT + r * TD;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 16
-      for (int k = 0; k < TD; ++k) fma4(acc, ar[k], ld4(WTl + gl.wt_out + k * TD + 4 * n4));
+      for (int k = 0; k < TD; ++k) fma4(acc, ar[k], ld4(WS + k * TD + 4 * n4));
       acc = drop4(a, row0 + r, site0 + TS_ATTN, (uint32_t)n4, a.thr_train, a.p_train, acc);
       const float4 xv = ld4(X + r * TD + 4 * n4);
       st4(V1 + r * TD + 4 * n4, make_float4(xv.x + acc.x, xv.y + acc.y, xv.z + acc.z, xv.w + acc.w));
@@ -380,11 +406,15 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     }
     cta_sync();
     // Linear(F -> d) on ReLU, nn.Dropout, residual from the block input (transformer.py:233)
-    FOR_T(i, T * TD) {
-      const int r = i / TD, n = i % TD;
-      float acc = Wl[lay.b2 + n];
-      for (int m = 0; m < F; ++m) acc = fmaf(fmaxf(U[r * F + m], 0.f), Wl[lay.w2 + n * F + m], acc);
-      Y[i] = X[i] + drop1(a, row0 + r, site0 + TS_FFN, (uint32_t)n, a.thr_train, a.p_train, acc);
+    FOR_T(i, TD * F) WS[(i % F) * TD + i / F] = Wl[lay.w2 + i];   // W2^T (F x 64) into the stage: coalesced read
+    __syncthreads();
+    FOR_T(i, T * (TD / 4)) {   // thread = (row, four adjacent outputs)
+      const int r = i / (TD / 4), n4 = i % (TD / 4);
+      float4 acc = ld4(Wl + lay.b2 + 4 * n4);
+      for (int m = 0; m < F; ++m) fma4(acc, fmaxf(U[r * F + m], 0.f), ld4(WS + m * TD + 4 * n4));
+      acc = drop4(a, row0 + r, site0 + TS_FFN, (uint32_t)n4, a.thr_train, a.p_train, acc);
+      const float4 xv = ld4(X + r * TD + 4 * n4);
+      st4(Y + r * TD + 4 * n4, make_float4(xv.x + acc.x, xv.y + acc.y, xv.z + acc.z, xv.w + acc.w));
     }
     cta_sync();
     // LayerNorm2 + bayes layer-output dropout (transformer.py:233, :370)
@@ -405,10 +435,12 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
   // vocabulary head on the predicting positions (transformer.py:374), local pred row q = t - (P - 1)
   const float* XL = S + sc.x + L * T * TD;
   float* LG = S + sc.logit;
+  prefetch(pf, WT + gl.wt_head, TD * gl.vp / 4);
+  park(pf, TD * gl.vp / 4);
   FOR_T(i, NPL * (gl.vp / 4)) {
     const int q = i / (gl.vp / 4), v4 = i % (gl.vp / 4);
     const float* xr = XL + (P - 1 + q) * TD;
-    const float* HT = WT + gl.wt_head;
+    const float* HT = WS;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 16
     for (int k = 0; k < TD; ++k) fma4(acc, xr[k], ld4(HT + k * gl.vp + 4 * v4));
@@ -443,6 +475,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
   float* DU = S + sc.du;
   float* DATT = S + sc.datt;
   // head: dW, db, dx_L
+  prefetch(pf, W + lay.head_w, V * TD / 4);
   FOR_T(i, V * (TD / 4)) {
     const int v = i / (TD / 4), f4 = i % (TD / 4);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -454,13 +487,14 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     for (int q = 0; q < NPL; ++q) acc += LG[q * V + v];
     G[lay.head_b + v] = acc;
   }
+  park(pf, V * TD / 4);
   {   // dx_L[t] = d logits[t] W_head: thread = (row, four features, quarter of the vocabulary)
-    const int part = tid & 3, f4 = (tid >> 2) & 15, t = tid >> 6;
+    const int part = quad_part(tid), f4 = quad_f4(tid), t = quad_row(tid);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < T && t >= P - 1 && t <= T - 2) {
       const float* dl = LG + (t - (P - 1)) * V;
 #pragma unroll 8
-      for (int v = part; v < V; v += 4) fma4(acc, dl[v], ld4(W + lay.head_w + v * TD + 4 * f4));
+      for (int v = part; v < V; v += 4) fma4(acc, dl[v], ld4(WS + v * TD + 4 * f4));
     }
     acc = quad_sum(acc);
     if (part == 0 && t < T) st4(DX + t * TD + 4 * f4, acc);
@@ -579,18 +613,20 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     }
     cta_sync();
     // W_out: dW, d(concatenated head outputs) -> DATT
+    prefetch(pf, Wl + lay.wout, TD * TD / 4);
     FOR_T(i, TD * (TD / 4)) {
       const int n = i / (TD / 4), k4 = i % (TD / 4);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < T; ++r) fma4(acc, DX[r * TD + n], ld4(ATT + r * TD + 4 * k4));
       st4(Gl + lay.wout + n * TD + 4 * k4, acc);
     }
+    park(pf, TD * TD / 4);
     {   // thread = (row, four inputs, quarter of the outputs)
-      const int part = tid & 3, k4 = (tid >> 2) & 15, r = tid >> 6;
+      const int part = quad_part(tid), k4 = quad_f4(tid), r = quad_row(tid);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < T) {
 #pragma unroll 16
-        for (int n = part; n < TD; n += 4) fma4(acc, DX[r * TD + n], ld4(Wl + lay.wout + n * TD + 4 * k4));
+        for (int n = part; n < TD; n += 4) fma4(acc, DX[r * TD + n], ld4(WS + n * TD + 4 * k4));
       }
       acc = quad_sum(acc);
       if (part == 0 && r < T) st4(DATT + r * TD + 4 * k4, acc);
@@ -652,18 +688,20 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     }
     cta_sync();
     // Q/K/V projections: dW, and the block-input gradient DX <- DXIN + dQKV W
+    prefetch(pf, Wl + lay.wqkv, 3 * TD * TD / 4);
     FOR_T(i, 3 * TD * (TD / 4)) {
       const int c = i / (TD / 4), f4 = i % (TD / 4);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < T; ++r) fma4(acc, DQKV[r * 3 * TD + c], ld4(X + r * TD + 4 * f4));
       st4(Gl + lay.wqkv + c * TD + 4 * f4, acc);
     }
+    park(pf, 3 * TD * TD / 4);
     {   // thread = (row, four features, quarter of the 192 projection outputs)
-      const int part = tid & 3, f4 = (tid >> 2) & 15, r = tid >> 6;
+      const int part = quad_part(tid), f4 = quad_f4(tid), r = quad_row(tid);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < T) {
 #pragma unroll 12
-        for (int c = part; c < 3 * TD; c += 4) fma4(acc, DQKV[r * 3 * TD + c], ld4(Wl + lay.wqkv + c * TD + 4 * f4));
+        for (int c = part; c < 3 * TD; c += 4) fma4(acc, DQKV[r * 3 * TD + c], ld4(WS + c * TD + 4 * f4));
       }
       acc = quad_sum(acc);
       if (part == 0 && r < T) {
@@ -739,8 +777,10 @@ extern "C" size_t bfb200_train_scratch_floats(int32_t batch, int32_t seq_len, in
                                               int32_t d_ff, int32_t n_layers) {
   if (batch < 1 || seq_len < 2 || prompt_len < 1 || prompt_len >= seq_len || seq_len > TMAXT) return 0;
   if (ntoken < 2 || d_ff < 1 || n_layers < 1) return 0;
+  if ((d_ff & 3) != 0 || d_ff * TD > TSTAGE) return 0;   // float4 alignment of the flat layout; W2^T is parked in the stage
   // 0 also when one sequence's activations do not fit a CTA's shared memory (the caller trains on another path)
-  if ((size_t)seq_scratch(seq_len, prompt_len, ntoken, d_ff, n_layers).total * sizeof(float) + 64 > (size_t)TSMEM_MAX) return 0;
+  if ((size_t)(seq_scratch(seq_len, prompt_len, ntoken, d_ff, n_layers).total + 4 + TSTAGE) * sizeof(float) > (size_t)TSMEM_MAX) return 0;
+  if (((ntoken + 3) & ~3) * TD > TSTAGE) return 0;   // the vocabulary head is parked in the same stage
   return (size_t)train_global(batch, ntoken, d_ff, n_layers, train_layout(ntoken, d_ff, n_layers).total).total;
 }
 
@@ -770,6 +810,8 @@ extern "C" int bfb200_train_step(const bfb200_train_args* ta, void* stream) {
   BFB_REQUIRE(ta->d_model == TD && ta->n_heads == TH, BFB200_ERR_UNSUPPORTED,
               "fused train step serves d_model 64 with 8 heads (got d=%d H=%d)", ta->d_model, ta->n_heads);
   BFB_REQUIRE(ta->ntoken >= 2 && ta->d_ff >= 1 && ta->n_layers >= 1, BFB200_ERR_INVALID_ARG, "bad model dimensions");
+  BFB_REQUIRE((ta->d_ff & 3) == 0 && ta->d_ff * TD <= TSTAGE, BFB200_ERR_UNSUPPORTED,
+              "fused train step takes d_ff a multiple of 4 up to %d (got %d)", TSTAGE / TD, ta->d_ff);
   BFB_REQUIRE(ta->batch >= 1 && ta->prompt_len >= 1 && ta->seq_len > ta->prompt_len, BFB200_ERR_INVALID_ARG,
               "bad batch shape (B=%d, T=%d, P=%d)", ta->batch, ta->seq_len, ta->prompt_len);
   BFB_REQUIRE(ta->seq_len <= ta->pe_len, BFB200_ERR_INVALID_ARG, "sequence longer than the positional table");
@@ -791,9 +833,10 @@ extern "C" int bfb200_train_step(const bfb200_train_args* ta, void* stream) {
   a.sc = seq_scratch(ta->seq_len, ta->prompt_len, ta->ntoken, ta->d_ff, ta->n_layers);
   a.gl = train_global(ta->batch, ta->ntoken, ta->d_ff, ta->n_layers, a.lay.total);
   a.slab_stride = (a.lay.total + 3) & ~3;
-  const size_t smem = (size_t)(a.sc.total + 4) * sizeof(float);
-  BFB_REQUIRE(smem + 64 <= (size_t)TSMEM_MAX, BFB200_ERR_UNSUPPORTED,
-              "one sequence's activations (%zu bytes) do not fit a CTA's shared memory", smem);
+  const size_t smem = (size_t)(a.sc.total + 4 + TSTAGE) * sizeof(float);
+  BFB_REQUIRE(smem <= (size_t)TSMEM_MAX && ((ta->ntoken + 3) & ~3) * TD <= TSTAGE, BFB200_ERR_UNSUPPORTED,
+              "one sequence's activations (%zu bytes) do not fit a CTA's shared memory, or the vocabulary (%d) exceeds %d",
+              smem, ta->ntoken, TSTAGE / TD);
   a.B = ta->batch; a.T = ta->seq_len; a.P = ta->prompt_len;
   a.lr = ta->lr; a.beta1 = ta->beta1; a.beta2 = ta->beta2; a.eps = ta->eps; a.weight_decay = ta->weight_decay;
   a.bias1 = 1.0f - powf(ta->beta1, (float)ta->step);
