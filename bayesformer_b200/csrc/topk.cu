@@ -7,6 +7,15 @@
 // bitonic-sorts its k survivors (k <= 4096) for the output.  1 M scores, k = 200: 62 blocks + 1 block, two launches
 // (the previous version bitonic-sorted 8,192 keys per block in three launches of ~90 us each).
 // HBM traffic: 4 B per score read once + 8 k B of candidates per block.
+//
+// Scores that do not fit one chunk take the ONE-LAUNCH path (topk_global_kernel): a cooperative grid of one CTA per SM
+// runs the same radix select on GLOBAL histograms — per round every CTA histograms the 12-bit digit of its slice in
+// shared memory, adds its non-empty bins to the round's global histogram, a grid barrier, then every CTA reads the
+// 4,096 bins and derives the same digit — and stops as soon as the keys at or above the chosen prefix fit one
+// block's sort buffer (typically after two rounds: sign / exponent / 3 mantissa bits, then 12 more mantissa bits).
+// Those candidates are appended to a global list, and CTA 0 bitonic-sorts them and writes the k best.
+// 1 M scores, k = 200: one launch, three grid barriers.  Keys are recomputed from the scores in every round
+// (4 B per score from L2), so the slice size is unbounded.
 #include "common.cuh"
 
 namespace bfb {
@@ -125,6 +134,131 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_select_kernel(
   for (int i = tid; i < k; i += TOPK_THREADS) keys_out[i] = sout[i];
 }
 
+
+// ---- one-launch path ------------------------------------------------------------------------------------------
+constexpr int TOPK_CAND = 4096;   // most candidates the final sort takes
+struct TopkGlobalWs {             // zeroed before the launch
+  uint32_t hist[6][TOPK_BINS];
+  uint32_t barrier;               // arrivals, monotone over the barriers of one launch
+  uint32_t n_cand;
+  uint32_t pad[2];
+  uint64_t cand[TOPK_CAND];
+};
+
+__device__ __forceinline__ void topk_grid_barrier(uint32_t* counter, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    uint32_t seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_global_kernel(const float* __restrict__ scores, int64_t n, int k,
+                                                                   int64_t index_base, uint64_t* __restrict__ keys_out,
+                                                                   TopkGlobalWs* __restrict__ ws) {
+  __shared__ uint64_t sortbuf[TOPK_CAND];
+  __shared__ uint32_t misc[40];   // [0] chosen digit, [1] keys above it, [2] keys in it, [8..40) warp sums
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sortbuf);   // the select rounds' histogram: dead before the final sort
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t G = gridDim.x;
+  // slice of this CTA, a multiple of the block size so that every warp-wide vote below sees full warps
+  const int64_t per = ((n + G - 1) / G + TOPK_THREADS - 1) / TOPK_THREADS * TOPK_THREADS;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per;
+  uint64_t prefix = 0ull, mask = 0ull;
+  uint32_t kk = (uint32_t)k;
+  uint32_t barriers = 0u;
+#pragma unroll 1
+  for (int r = 0; r < 6; ++r) {
+    const int shift = r < 5 ? 52 - 12 * r : 0;
+    const uint32_t nb = r < 5 ? 4096u : 16u;
+    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
+    __syncthreads();
+    for (int64_t g = lo + tid; g < hi; g += TOPK_THREADS) {
+      const bool valid = g < n;
+      const uint64_t key = valid ? pack_key(__ldg(scores + g), (uint64_t)(index_base + g)) : 0ull;
+      const bool in = valid && (key & mask) == prefix;
+      const uint32_t digit = (uint32_t)(key >> shift) & (nb - 1u);
+      const uint32_t act = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const uint32_t peers = __match_any_sync(act, digit);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS)
+      if (hist[i] != 0u) atomicAdd(&ws->hist[r][i], hist[i]);
+    topk_grid_barrier(&ws->barrier, ++barriers * G);
+    // every CTA derives the same digit from the global histogram: suffix sums, four bins per thread
+    const uint32_t b0 = (uint32_t)tid * 4u;
+    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(&ws->hist[r][b0]));
+    const uint32_t h0 = h.x, h1 = h.y, h2 = h.z, h3 = h.w;
+    uint32_t incl = h0 + h1 + h2 + h3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += up;
+    }
+    if (lane == 0) misc[8 + warp] = incl;
+    __syncthreads();
+    uint32_t higher_warps = 0u;
+    for (int w = warp + 1; w < TOPK_THREADS / 32; ++w) higher_warps += misc[8 + w];
+    const uint32_t a3 = incl + higher_warps - (h0 + h1 + h2 + h3), a2 = a3 + h3, a1 = a2 + h2, a0 = a1 + h1;
+    if (a3 < kk && kk <= a3 + h3) { misc[0] = b0 + 3; misc[1] = a3; misc[2] = h3; }
+    else if (a2 < kk && kk <= a2 + h2) { misc[0] = b0 + 2; misc[1] = a2; misc[2] = h2; }
+    else if (a1 < kk && kk <= a1 + h1) { misc[0] = b0 + 1; misc[1] = a1; misc[2] = h1; }
+    else if (a0 < kk && kk <= a0 + h0) { misc[0] = b0; misc[1] = a0; misc[2] = h0; }
+    __syncthreads();
+    prefix |= (uint64_t)misc[0] << shift;
+    mask |= (uint64_t)(nb - 1u) << shift;
+    kk -= misc[1];
+    // keys >= prefix (on the masked bits): the (k - kk) already known to be above, plus this bin
+    const uint32_t at_or_above = ((uint32_t)k - kk) + misc[2];
+    __syncthreads();
+    if (at_or_above <= (uint32_t)TOPK_CAND) break;   // (the last round leaves exactly k)
+  }
+  // candidates: every key whose fixed bits are >= the prefix
+  for (int64_t g = lo + tid; g < hi; g += TOPK_THREADS) {
+    const bool valid = g < n;
+    const uint64_t key = valid ? pack_key(__ldg(scores + g), (uint64_t)(index_base + g)) : 0ull;
+    const bool keep = valid && (key & mask) >= prefix;
+    const uint32_t act = __ballot_sync(0xffffffffu, keep);
+    uint32_t pos = 0u;
+    if (lane == 0 && act != 0u) pos = atomicAdd(&ws->n_cand, (uint32_t)__popc(act));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (keep) {
+      const uint32_t at = pos + (uint32_t)__popc(act & ((1u << lane) - 1u));
+      if (at < (uint32_t)TOPK_CAND) ws->cand[at] = key;
+    }
+  }
+  topk_grid_barrier(&ws->barrier, ++barriers * G);
+  if (blockIdx.x != 0) return;
+  uint32_t nc;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(nc) : "l"(&ws->n_cand) : "memory");
+  nc = nc < (uint32_t)TOPK_CAND ? nc : (uint32_t)TOPK_CAND;
+  int p2 = 1;
+  while (p2 < (int)nc) p2 <<= 1;
+  for (int i = tid; i < p2; i += TOPK_THREADS) sortbuf[i] = i < (int)nc ? __ldcg(&ws->cand[i]) : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= p2; size <<= 1) {   // bitonic sort, descending
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < p2 / 2; t += TOPK_THREADS) {
+        const int l0 = ((t / stride) * (stride << 1)) + (t % stride);
+        const int h0 = l0 + stride;
+        const bool desc = ((l0 & size) == 0);
+        const uint64_t x = sortbuf[l0], y = sortbuf[h0];
+        if ((x < y) == desc) { sortbuf[l0] = y; sortbuf[h0] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += TOPK_THREADS) keys_out[i] = sortbuf[i];
+}
+
 __global__ void unpack_keys_kernel(const uint64_t* __restrict__ keys, int k, float* __restrict__ scores,
                                    int64_t* __restrict__ indices) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,7 +274,8 @@ static size_t topk_ws_bytes(int64_t n, int k) {
   // two ping-pong candidate buffers; the first level writes blocks_for(n) * k keys
   const int64_t lvl1 = blocks_for(n) * k;
   const int64_t lvl2 = blocks_for(lvl1) * k;
-  return (size_t)(lvl1 + lvl2) * sizeof(uint64_t) + 256;
+  const size_t levels = (size_t)(lvl1 + lvl2) * sizeof(uint64_t) + 256;
+  return levels > sizeof(TopkGlobalWs) + 256 ? levels : sizeof(TopkGlobalWs) + 256;
 }
 
 static int run_topk(const float* scores, const uint64_t* keys, int64_t n, int k, int64_t index_base,
@@ -158,6 +293,24 @@ static int run_topk(const float* scores, const uint64_t* keys, int64_t n, int k,
     BFB_DEV(workspace);
   }
   uint64_t* buf_a = (uint64_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  if (scores != nullptr && nb > 1) {   // one cooperative launch: global-histogram radix select
+    int dev = 0, sms = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop && sms > 0) {
+      TopkGlobalWs* gws = reinterpret_cast<TopkGlobalWs*>(buf_a);
+      cudaError_t e = cudaMemsetAsync(gws, 0, offsetof(TopkGlobalWs, cand), st);
+      BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+      int64_t grid = (n + TOPK_THREADS - 1) / TOPK_THREADS;
+      if (grid > sms) grid = sms;
+      void* args[] = {(void*)&scores, (void*)&n, (void*)&k, (void*)&index_base, (void*)&keys_out, (void*)&gws};
+      e = cudaLaunchCooperativeKernel((const void*)topk_global_kernel, dim3((unsigned)grid), dim3(TOPK_THREADS), args, 0, st);
+      BFB_REQUIRE(e == cudaSuccess, BFB200_ERR_CUDA, "cooperative launch of topk_global_kernel failed: %s", cudaGetErrorString(e));
+      BFB_LAUNCH_CHECK("topk_global_kernel", st);
+      return BFB200_OK;
+    }
+  }
   uint64_t* buf_b = buf_a + blocks_for(n) * k;
   const uint64_t* cur_keys = keys;
   bool from_scores = scores != nullptr;

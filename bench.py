@@ -635,7 +635,7 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
     del x, probs
     scores = torch.randn(1_000_000, device=dev)
     ms = timed(lambda: engine.topk_keys(scores, K_TOP))
-    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident; radix select, 62 blocks + 1 block (two launches)"}
+    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident; one cooperative launch: radix select over global histograms, three grid barriers"}
     # MC-batched tensor-core GEMMs at the scaled configuration's shapes (d = 512, F = 2048; one chunk of
     # 256 sequences x 256 tokens = 65,536 token rows), against the measured dense bf16 matmul peak
     tc_peak = peaks["bf16_tflops"]

@@ -155,6 +155,32 @@ def test_topk_special_values_and_errors(engine, dev):
     assert engine.topk(all_equal, 200)[1].cpu().tolist() == list(range(200))
 
 
+@pytest.mark.parametrize("kind", ["normal", "all_equal", "wide", "few_values", "narrow"])
+@pytest.mark.parametrize("n,k,base", [(16385, 200, 0), (1000000, 200, 7), (2000003, 1000, 123456), (40000, 4096, 0)])
+def test_topk_one_launch_path(engine, dev, kind, n, k, base):
+    """Scores beyond one 16,384-key chunk take the cooperative one-launch radix select over global histograms
+    (csrc/topk.cu topk_global_kernel): bit-exact against the rule of torch.topk with ties towards the lowest index, on
+    distributions that stress each stage — every key equal (all six rounds, down to the index bits), values spread over
+    the whole exponent range (thousands of non-empty bins per CTA), a handful of distinct values (huge tie bins), and a
+    narrow band (candidates cut only by the low mantissa bits)."""
+    rng = np.random.default_rng(n + k)
+    if kind == "normal":
+        scores = rng.standard_normal(n).astype(np.float32)
+    elif kind == "all_equal":
+        scores = np.full(n, 0.69314718, dtype=np.float32)
+    elif kind == "wide":
+        scores = (rng.standard_normal(n) * np.exp(rng.uniform(-40, 40, n))).astype(np.float32)
+    elif kind == "few_values":
+        scores = rng.integers(0, 5, n).astype(np.float32) * 0.25
+    else:
+        scores = (1.0 + rng.random(n) * 1e-4).astype(np.float32)
+    keys = engine.topk_keys(torch.from_numpy(scores).to(dev), k, index_base=base)
+    vals, idx = engine.unpack_keys(keys)
+    want = R.topk_lowest_index(scores, k)
+    assert (idx.cpu().numpy() - base).tolist() == want.tolist()
+    assert np.array_equal(vals.cpu().numpy(), scores[want])
+
+
 def test_topk_sharded_merge_equals_global(engine, dev):
     """per-shard keys with global index bases + merge == single-device top-k (the multi-GPU exchange)."""
     rng = np.random.default_rng(5)
