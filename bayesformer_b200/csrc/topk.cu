@@ -4,9 +4,8 @@
 // A block takes a chunk of 16,384 keys into shared memory and finds its k-th largest key by RADIX SELECT — six
 // histogram rounds over 12-bit digits, most significant first, each narrowing the candidates to the bin that holds
 // the k-th key — then compacts the k keys >= that threshold.  Levels repeat until one block remains; the last one
-// bitonic-sorts its k survivors (k <= 4096) for the output.  1 M scores, k = 200: 62 blocks + 1 block, two launches
-// (the previous version bitonic-sorted 8,192 keys per block in three launches of ~90 us each).
-// HBM traffic: 4 B per score read once + 8 k B of candidates per block.
+// bitonic-sorts its k survivors (k <= 4096) for the output.  This block-level path serves inputs of up to one chunk and
+// bfb200_merge_topk (candidate keys of several ranks).
 //
 // Scores that do not fit one chunk take the ONE-LAUNCH path (topk_global_kernel): a cooperative grid of one CTA per SM
 // runs the same radix select on GLOBAL histograms — per round every CTA histograms the 12-bit digit of its slice in

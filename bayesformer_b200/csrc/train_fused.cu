@@ -272,7 +272,6 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
   float* G = a.scratch + gl.slab + (size_t)b * a.slab_stride;
   const float inv_sqrt_dh = rsqrtf((float)TDH);
   const float sqrt_d = sqrtf((float)TD);
-  float& s_loss = S[sc.total];   // one extra float behind the activations
   // Weight stage (48 KB behind the activations): a phase that multiplies by a weight matrix first prefetches it into
   // registers with coalesced loads (one L2 round trip for the whole CTA), does its weight-free work, then parks it here,
   // so that the per-thread reduction loops read shared memory instead of paying the L2 latency once per unrolled batch.
@@ -290,7 +289,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
 #define FOR_T(i, n) for (int i = tid; i < (n); i += TTHREADS)
 
   // ---- forward ----------------------------------------------------------------------------------------------
-  if (tid == 0) s_loss = 0.f;
+  __shared__ int s_tok[TMAXT];
+  __shared__ float s_lossv[TMAXT];   // per predicted position, summed in order
+  if (tid < T) s_tok[tid] = (int)a.tokens[(int64_t)tid * B + b];
   FOR_T(i, V * TD / 4) st4(G + lay.emb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));   // embedding rows are accumulated at the end
   // embedding, bayes dropout E, sqrt(d) scale, positional encoding, nn.Dropout (transformer.py:355-362, :269-272)
   FOR_T(i, T * (TD / 4)) {
@@ -460,12 +461,16 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     float z = 0.f;
     for (int v = lane; v < V; v += 32) z += __expf(lg[v] - mx);
     const float lse = mx + __logf(warp_sum(z));
-    if (lane == 0) atomicAdd(&s_loss, lse - lg[target]);
+    if (lane == 0) s_lossv[q] = lse - lg[target];
     __syncwarp();
     for (int v = lane; v < V; v += 32) lg[v] = (__expf(lg[v] - lse) - (v == target ? 1.f : 0.f)) * inv_np;
   }
   cta_sync();
-  if (tid == 0) a.scratch[gl.loss + b] = s_loss * inv_np;
+  if (tid == 0) {
+    float ls = 0.f;
+    for (int q = 0; q < NPL; ++q) ls += s_lossv[q];
+    a.scratch[gl.loss + b] = ls * inv_np;
+  }
 
   // ---- backward ---------------------------------------------------------------------------------------------
   float* DX = S + sc.dx;
@@ -711,14 +716,26 @@ __global__ void __launch_bounds__(TTHREADS, 1) train_seq_kernel(const TrainArgs 
     }
     cta_sync();
   }
-  // embedding: through nn.Dropout, the sqrt(d) scale and the bayes mask into the rows of the table (the same token may
-  // occur twice in a sequence: accumulate)
+  // embedding: through nn.Dropout, the sqrt(d) scale and the bayes mask into the rows of the table.  A token may occur
+  // several times in a sequence: the thread of its FIRST occurrence sums all of them in position order (deterministic,
+  // no atomics); rows of tokens the sequence does not contain stay zero.
   FOR_T(i, T * TD) {
     const int t = i / TD, f = i % TD;
     float g = drop1(a, row0 + t, TS_PE, (uint32_t)f, a.thr_train, a.p_train, DX[i]) * sqrt_d;
-    g = drop1(a, row0 + t, TS_EMBED, (uint32_t)f, a.thr_bayes, a.p_bayes, g);
-    const int tok = (int)a.tokens[(int64_t)t * B + b];
-    if (g != 0.f) atomicAdd(G + lay.emb + tok * TD + f, g);
+    DX[i] = drop1(a, row0 + t, TS_EMBED, (uint32_t)f, a.thr_bayes, a.p_bayes, g);
+  }
+  __syncthreads();
+  FOR_T(i, T * TD) {
+    const int t = i / TD, f = i % TD;
+    const int tok = s_tok[t];
+    bool first = true;
+    for (int u = 0; u < t; ++u) first = first && s_tok[u] != tok;
+    if (first) {
+      float acc = 0.f;
+      for (int u = t; u < T; ++u)
+        if (s_tok[u] == tok) acc += DX[u * TD + f];
+      G[lay.emb + tok * TD + f] = acc;
+    }
   }
 #undef FOR_T
 }
@@ -731,8 +748,8 @@ __global__ void __launch_bounds__(256) train_adam_kernel(const TrainArgs a) {
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < sg.count; i += gridDim.y * blockDim.x) {
     const int k = sg.offset + i;
     float g = 0.f;
-#pragma unroll 4
-    for (int b = 0; b < a.B; ++b) g += slab[(size_t)b * a.slab_stride + k];
+#pragma unroll 8
+    for (int b = 0; b < a.B; ++b) g += __ldcs(slab + (size_t)b * a.slab_stride + k);
     a.grad[k] = g;
     const float m = a.beta1 * a.adam_m[k] + (1.0f - a.beta1) * g;
     const float v = a.beta2 * a.adam_v[k] + (1.0f - a.beta2) * g * g;
@@ -856,7 +873,7 @@ extern "C" int bfb200_train_step(const bfb200_train_args* ta, void* stream) {
   BFB_LAUNCH_CHECK("train_transpose_kernel", st);
   train_seq_kernel<<<a.B, TTHREADS, smem, st>>>(a);
   BFB_LAUNCH_CHECK("train_seq_kernel", st);
-  train_adam_kernel<<<dim3(a.n_segs, 8), 256, 0, st>>>(a);
+  train_adam_kernel<<<dim3(a.n_segs, 32), 256, 0, st>>>(a);   // 8,192 threads per segment: one element each for all but huge vocabularies
   BFB_LAUNCH_CHECK("train_adam_kernel", st);
   return BFB200_OK;
 }

@@ -4,7 +4,8 @@ Behavioural mirror of the reference's `src/libs/tokenizer.py` (Tokenizer ABC :9-
 CharacterLevelTokenizer :28-62, ReversedPairingTokenizer :343-380) written from its
 observable behaviour: same vocabularies and ids (14 and 114 symbols), same
 cleaning rule, same "reversed digit pair" encoding of `abc+def=`.  Known answers
-from the reference docstrings (:221-223, :289) are pinned in tests/test_tokenizer.py.
+from the reference docstrings (:221-223, :289) are pinned in tests/test_host_logic.py
+(test_tokenizer_and_get_batch_known_answers) and tests/golden/tokenizer.json.
 
 `encode_pool` / `encode_batch_numpy` are the vectorised entry points used by the
 pool-scoring path: they tokenise a whole pool once, instead of the

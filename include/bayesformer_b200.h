@@ -49,12 +49,13 @@ enum { BFB200_SCHEME_GREEDY = 0, BFB200_SCHEME_SAMPLING = 1, BFB200_SCHEME_DROPO
 enum {
   BFB200_COMPUTE_FP32 = 0, /* fp32 CUDA-core FMA everywhere (1e-3 parity class) */
   BFB200_COMPUTE_F16 = 1   /* 16-bit operands on tcgen05 tensor cores (kind::f16), fp32 accumulate in TMEM, fp32
-                              residual stream / softmax / LayerNorm statistics: the north star's 1e-2 parity
+                              softmax / LayerNorm statistics: the north star's 1e-2 parity
                               class.  Operands are IEEE fp16 (saturating): bf16's 8-bit mantissa moves the
                               trained model's mid-range probabilities by up to 5 %, fp16 keeps them within
-                              1 % (measured, DESIGN.md).  Served by the
-                              fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 40
-                              (the reference notebooks' model).  Other models with heads of width 64 and
+                              1 % (measured, DESIGN.md section 3).  Served by the
+                              fused MC-forward kernel: d_model 64, 8 heads, F <= 64, V <= 128, P + N - 1 <= 128
+                              (the reference notebooks' model; operands split into hi + lo parts, residual
+                              stream as an fp16 pair).  Other models with heads of width 64 and
                               sequences of at most 256 tokens (the scaled configuration) run the layered
                               tensor-core path: TMA-fed tcgen05 GEMMs + tcgen05 attention, fp32 residual stream */,
   BFB200_COMPUTE_BF16 = 2  /* layered tensor-core path with bf16 operands (heads of width 64, len <= 256) */
@@ -251,8 +252,9 @@ int bfb200_mc_score_transformer(const bfb200_transformer* model, const bfb200_mc
 /*
  * 16-bit weight image of the tensor-core paths (model->compute = F16 / BF16), written into model->fused_image's
  * buffer.  Fused class: every nn.Linear weight of src/model/transformer.py as fp16 in the 128-byte-swizzled K-major
- * shared-memory layout tcgen05.mma reads, followed by the fp32 LayerNorm / bias vectors and the first 16 rows of
- * `pe`.  Layered tensor-core path: plain row-major 16-bit copies [W_qkv | W_out | FFN W1 | FFN W2 | head] that the
+ * shared-memory layout tcgen05.mma reads (W_out stacked with the merged matrix (W1 gamma1) W_out, W1 scaled by
+ * gamma1, lo parts of W_qkv and W2), followed by the fp32 LayerNorm / bias / folding vectors and a global-only tail
+ * (vocabulary head, padded head bias, W_qkv lo rows) that the kernel streams per use; DESIGN.md section 5.  Layered tensor-core path: plain row-major 16-bit copies [W_qkv | W_out | FFN W1 | FFN W2 | head] that the
  * GEMM kernel reads through TMA.  _bytes returns 0 when no tensor-core path serves the model's shape.  Re-pack
  * after every weight update.
  */

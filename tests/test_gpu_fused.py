@@ -502,8 +502,8 @@ def test_select_samples_on_a_char_level_pool_runs_the_fused_kernel(engine, dev):
 def test_specialised_kernels_equal_the_generic_kernel_bit_for_bit(engine, dev, c2, bayes):
     """The FAST instantiations (default sites / no site, Philox masks, greedy decoding, no side channels) compile the
     other branches out; asking for the log-probs routes the same call through the generic instantiation.  Same seed
-    => identical masks => the scores and the decoded tokens must agree exactly, for sequence lengths on both sides of
-    the per-length instantiations (4..8, 16, 40)."""
+    => identical masks => the scores and the decoded tokens must agree exactly, for short and long sequences
+    (one streamed pair phase serves every length up to 128)."""
     z, sd = c2
     model = H.build_model(sd, float(z["p"]) if bayes else None, bayes).to(dev)
     pack = model.native_pack(dev, "fp16")
