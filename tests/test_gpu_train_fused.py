@@ -114,3 +114,77 @@ def test_train_uses_the_fused_step_and_learns(dev):
     finally:
         del os.environ["BFB200_FUSED_TRAIN"]
     assert abs(va_loss[-1] - va2[-1]) <= 0.25 * va2[-1]       # different dropout streams: same training, statistically
+
+
+def test_fused_step_gradient_with_dropout_matches_finite_differences(dev):
+    """With the dropout sites ON the masks cannot be compared with torch's, but they are a deterministic function of
+    (seed, step, row, site, feature): the loss of one step is an ordinary function of the weights, and the gradient the
+    kernel computes (masks re-drawn in its backward pass) must be that function's derivative.  For EVERY parameter
+    tensor: central difference of the kernel's own loss (lr = 0 leaves the weights untouched) along the direction
+    sign(gradient) against sum |gradient| — a directional derivative, so the ReLU kinks and the fp32 rounding of the
+    loss stay second-order."""
+    from bayesformer_b200 import engine
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    tok = ReversedPairingTokenizer()
+    torch.manual_seed(8)
+    model = MyTransformer(tok.ntokens, 64, 8, 8, 2, bayes_dropout=0.3, bayes=True).to(dev)
+    tokens, p_len = _batches(tok, 1, 12, seed=2)[0]
+    tokens = tokens.to(dev)
+    trainer = engine.FusedTrainer(model, 0.0)
+    trainer.WEIGHT_DECAY = 0.0
+
+    def loss_and_grad():
+        trainer.step_count = 0          # same step id => same masks
+        trainer.loss.zero_()
+        trainer.step(tokens, p_len, 0.1, 0.3, seed=77)
+        return float(trainer.loss.item()), trainer.grad.clone()
+
+    base, grad = loss_and_grad()
+    again, grad2 = loss_and_grad()
+    assert base == again and torch.equal(grad, grad2)     # the step is bit-reproducible
+    eps = 1e-3
+    checked = 0
+    for param, seg in zip(trainer._params, trainer._segment_view()):
+        g = grad[seg.offset:seg.offset + seg.count].view_as(param)
+        want = float(g.abs().sum())
+        if want < 1e-3:
+            continue                     # e.g. a tensor whose gradient is (almost) masked out: nothing to resolve
+        d = torch.sign(g)
+        with torch.no_grad():
+            param.add_(d, alpha=eps)
+            up, _ = loss_and_grad()
+            param.add_(d, alpha=-2 * eps)
+            down, _ = loss_and_grad()
+            param.add_(d, alpha=eps)
+        fd = (up - down) / (2 * eps)
+        assert abs(fd - want) <= 3e-2 * want + 2e-3, (tuple(param.shape), seg.offset, fd, want)
+        checked += 1
+    assert checked >= 40                 # per-head projections, W_out, both LayerNorms, FFN, embedding, head
+
+
+def test_fused_step_large_batch_and_longest_sequence(dev):
+    """250 sequences of 16 tokens (the class limit) in one step = 250 CTAs and gradient slabs; against eager autograd."""
+    from bayesformer_b200 import engine
+    from bayesformer_b200.libs.tokenizer import ReversedPairingTokenizer
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    tok = ReversedPairingTokenizer()
+    torch.manual_seed(13)
+    eager = MyTransformer(tok.ntokens, 64, 8, 8, 2, dropout=0.0).to(dev).train()
+    fused = copy.deepcopy(eager)
+    g = torch.Generator().manual_seed(1)
+    tokens = torch.randint(0, tok.ntokens, (16, 250), generator=g).to(dev)
+    p_len = 9
+    with torch.enable_grad():
+        out = eager._module_forward(tokens)
+        loss = nn.CrossEntropyLoss()(out[p_len - 1:-1].reshape(-1, tok.ntokens), tokens[p_len:].reshape(-1))
+        loss.backward()
+    trainer = engine.FusedTrainer(fused, 1e-3)
+    trainer.step(tokens, p_len, 0.0, 0.0, seed=1)
+    assert abs(float(trainer.loss.item()) - float(loss.item())) <= 1e-4 * abs(float(loss.item()))
+    ref = torch.cat([p.grad.reshape(-1) for p in (eager.embedding.weight,)])
+    np.testing.assert_allclose(trainer.grad[:ref.numel()].cpu().numpy(), ref.cpu().numpy(), rtol=2e-3, atol=2e-7)
+    with pytest.raises(ValueError):
+        trainer.step(torch.zeros((17, 4), dtype=torch.int64, device=dev), 8, 0.0, 0.0, seed=1)   # beyond the class: caller falls back
