@@ -66,7 +66,7 @@ if __name__ == "__main__":
     S = dict(attn_lo=True, w2_lo=True, v_lo=True, wv_lo=True)
     E.VARIANTS = {"shipped": S, "no_qk8": dict(S, qk8=False), "no_wqk_lo": dict(S, wqk_lo=False),
                   "no_qk8_wqk": dict(S, qk8=False, wqk_lo=False), "no_qk8_wqk_xlo": dict(S, qk8=False, wqk_lo=False, xlo_qk=False),
-                  "no_w2lo": dict(S, w2_lo=False), "shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
+                  "no_w2lo": dict(S, w2_lo=False), "no_xlo_qk": dict(S, xlo_qk=False), "shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
                   "attn+w2+m+w1": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True),
                   "attn+w2+m+w1+v+wv": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True),
                   "all": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True, head_lo=True, wout_lo=True)}
