@@ -239,6 +239,17 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_global_kernel(const float* 
   uint32_t nc;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(nc) : "l"(&ws->n_cand) : "memory");
   nc = nc < (uint32_t)TOPK_CAND ? nc : (uint32_t)TOPK_CAND;
+  if (nc <= (uint32_t)TOPK_THREADS) {   // few candidates (the usual case): rank sort, one pass and no barriers in it
+    const uint64_t mine = tid < (int)nc ? __ldcg(&ws->cand[tid]) : 0ull;
+    sortbuf[tid] = mine;
+    __syncthreads();
+    if (tid < (int)nc) {
+      int rank = 0;   // keys are distinct: the number of larger keys is the output position
+      for (int j = 0; j < (int)nc; ++j) rank += sortbuf[j] > mine ? 1 : 0;
+      if (rank < k) keys_out[rank] = mine;
+    }
+    return;
+  }
   int p2 = 1;
   while (p2 < (int)nc) p2 <<= 1;
   for (int i = tid; i < p2; i += TOPK_THREADS) sortbuf[i] = i < (int)nc ? __ldcg(&ws->cand[i]) : 0ull;

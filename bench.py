@@ -634,8 +634,17 @@ def aux_kernel_benchmarks(dev, peaks: dict, peak_src: str) -> dict:
                                                "frac": b / ms / 1e6 / hbm, "peak_source": peak_src}
     del x, probs
     scores = torch.randn(1_000_000, device=dev)
-    ms = timed(lambda: engine.topk_keys(scores, K_TOP))
-    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident; one cooperative launch: radix select over global histograms, three grid barriers"}
+    # the library call with a preallocated workspace, as a C caller makes it (engine.topk_keys adds two allocations)
+    from bayesformer_b200 import _lib as _l
+    _lb = _l.load()
+    _keys = torch.empty(K_TOP, dtype=torch.int64, device=dev)
+    _wsb = _lb.bfb200_topk_workspace_bytes(scores.numel(), K_TOP)
+    _ws = torch.empty(_wsb, dtype=torch.uint8, device=dev)
+    _st = torch.cuda.current_stream(dev).cuda_stream
+    ms = timed(lambda: _l.check(_lb.bfb200_topk(scores.data_ptr(), scores.numel(), K_TOP, 0, _keys.data_ptr(), _ws.data_ptr(),
+                                                 _wsb, _st)))
+    assert torch.equal(_keys, engine.topk_keys(scores, K_TOP))
+    out["topk(1M, k=200)"] = {"ms": ms, "note": "4 MB input: L2-resident; one cooperative launch: radix select over global histograms (two rounds), three grid barriers, rank sort of the candidates"}
     # MC-batched tensor-core GEMMs at the scaled configuration's shapes (d = 512, F = 2048; one chunk of
     # 256 sequences x 256 tokens = 65,536 token rows), against the measured dense bf16 matmul peak
     tc_peak = peaks["bf16_tflops"]
