@@ -66,7 +66,7 @@ struct GemmArgs {
   int resid;               // two-SM kernel: out16 = acc (+ bias) + R16, a 16-bit matrix shaped like the output whose tiles the
                            // TMA producer streams through the operand ring (map_r)
   RowStats* stats_out;     // with resid: per-row (sum, sum of squares) of the fp32 result, accumulated atomically
-  const RowStats* stats_in;  // row-affine mode: out = rstd_r * (acc - mean_r * col_s[n]) + col_c[n], (mean, rstd) from the
+  const RowStats* stats_in;  // row-affine mode: out = rstd_r * acc + col_c[n] (weight rows centred, so acc carries no mean term), rstd from the
   const float* col_s;      //   (sum, sum of squares) of a row of `stats_width` values — LayerNorm folded into this product
   const float* col_c;
   float stats_inv_width, stats_eps;
@@ -93,7 +93,7 @@ template <uint32_t F> struct Epi {
 // The arithmetic of one 32-column chunk of one accumulator row.  FULL: all 32 columns are inside the matrix and the
 // per-column vectors are 16-byte aligned (128-bit broadcast loads, no guards).
 //   plain     : v = acc (+ bias) (ReLU)
-//   affine    : v = rstd (acc - mean col_s) + col_c (ReLU)            LayerNorm folded into this product
+//   affine    : v = rstd acc + col_c (ReLU)                           LayerNorm folded into this product (centred weight rows)
 //   residual  : v += R16 row (read from the ring slot TMA filled), and the row's running sum / sum of squares
 template <bool FULL, uint32_t F>
 __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&acc)[32], float (&v)[32], int n0, float r_mean,
@@ -112,11 +112,9 @@ __device__ __forceinline__ void chunk_math(const GemmArgs& g, const uint32_t (&a
     }
   };
   if (Epi<F>::affine(g)) {
-    float cs_[32];
-    load32(g.col_s, cs_);
-    load32(g.col_c, v);
+    load32(g.col_c, v);   // the weight rows are centred (fold_ln_pack_kernel): acc is already (v - mean) (W g)^T
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(r_rstd, fmaf(-r_mean, cs_[i], __uint_as_float(acc[i])), v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(r_rstd, __uint_as_float(acc[i]), v[i]);
   } else if (Epi<F>::bias(g)) {
     load32(g.bias, v);
 #pragma unroll

@@ -779,7 +779,13 @@ __global__ void to16_kernel(const float* __restrict__ src, uint16_t* __restrict_
   }
 }
 
-// one warp per output row n of layer l
+// LayerNorm folded into the product that consumes it:  W LN(v) + b = rstd (v - mean) (W g)^T + (W beta + b).  The
+// mean term costs nothing when the ROWS of W g are centred: with W'[n, :] = (W g)[n, :] - avg_k (W g)[n, k],
+// v W'[n, :]^T = v (W g)[n, :]^T - (sum_k v_k) avg = (v - mean) (W g)[n, :]^T exactly, so the product's epilogue is
+// rstd * acc + col_c — one FMA per element, like a bias.  Rounding W' to 16 bits leaves a row sum of ~5e-3 rms(W')
+// instead of 0 (returned in col_s for inspection): against the product's own scale sqrt(K) rms(W') that is 2e-4 of
+// mean / std of the row — below the operands' rounding noise, and the epilogue ignores it.
+// One warp per output row n of layer l.
 __global__ void __launch_bounds__(256) fold_ln_pack_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int64_t rows_total, int N, int K, uint32_t fmt,
@@ -792,9 +798,12 @@ __global__ void __launch_bounds__(256) fold_ln_pack_kernel(const float* __restri
   const float* w = W + r * K;
   const float* g = gamma + l * K;
   const float* be = beta + l * K;
+  float tot = 0.f;
+  for (int k = lane; k < K; k += 32) tot += w[k] * g[k];
+  const float avg = warp_sum(tot) / (float)K;
   float s = 0.f, c = 0.f;
   for (int k = lane; k < K; k += 32) {
-    const float wg = w[k] * g[k];
+    const float wg = w[k] * g[k] - avg;
     uint16_t h;
     float back;
     if (fmt == umma::kFmtF16) {
