@@ -655,22 +655,23 @@ __device__ __forceinline__ void fused_issue(const IssueCtx c, int layer, uint64_
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + 2u * FD, gb + C_XHI + 8u * k, dlv + 2 * k, id64, 1u);
   } else if (kind == PR_MERGED) {
     // columns [0, 64) = attn W_out^T ; [64, 64 + fp) = attn ((W1 g1) W_out)^T + x (W1 g1)^T
-    const uint64_t da = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES), dom = umma::smem_desc_sw128(wl + c.off_om);
-    const uint64_t dal = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES);
+    // The attention output sits in two tiles: features 0..31 (heads 0..3) in the L tile, features 32..63 in the Q tile,
+    // each row as [fp16 hi of its 32 features | their lo parts]: K steps 0, 1 read the L tile, 2, 3 the Q tile; the lo
+    // operand of a step starts 64 bytes (descriptor + 4) behind its hi operand.
+    const uint64_t daL = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES), daQ = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES);
+    const uint64_t dom = umma::smem_desc_sw128(wl + c.off_om);
     const uint64_t dw1 = umma::smem_desc_sw128(wl + c.off_w1);
     const uint32_t id_om = umma::instr_desc_f16(FROWS, FD + fp), id_fp = umma::instr_desc_f16(FROWS, fp);
-    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, da + 2 * k, dom + 2 * k, id_om, k > 0);
-    if (c.attn_lo)
-      for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, dal + 2 * k, dom + 2 * k, id_om, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, (k < 2 ? daL : daQ) + 2 * (k & 1), dom + 2 * k, id_om, k > 0);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, (k < 2 ? daL : daQ) + 4 + 2 * (k & 1), dom + 2 * k, id_om, 1u);
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + FD, gb + C_XHI + 8u * k, dw1 + 2 * k, id_fp, 1u);
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + FD, gb + C_XLO + 8u * k, dw1 + 2 * k, id_fp, 1u);
   } else if (kind == PR_WOUT) {
-    const uint64_t da = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES), dom = umma::smem_desc_sw128(wl + c.off_om);
-    const uint64_t dal = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES);
+    const uint64_t daL = umma::smem_desc_sw128(tile0 + T_L * TILE_BYTES), daQ = umma::smem_desc_sw128(tile0 + T_Q * TILE_BYTES);
+    const uint64_t dom = umma::smem_desc_sw128(wl + c.off_om);
     const uint32_t id64 = umma::instr_desc_f16(FROWS, FD);
-    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, da + 2 * k, dom + 2 * k, id64, k > 0);
-    if (c.attn_lo)
-      for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, dal + 2 * k, dom + 2 * k, id64, 1u);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, (k < 2 ? daL : daQ) + 2 * (k & 1), dom + 2 * k, id64, k > 0);
+    for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(gb + C_ACC, (k < 2 ? daL : daQ) + 4 + 2 * (k & 1), dom + 2 * k, id64, 1u);
   } else if (kind == PR_FFN1) {
     // unmerged flow: LayerNorm1 output (hi at columns [64, 96), lo at [96, 128) of the accumulator window) times W1
     const uint64_t dw1 = umma::smem_desc_sw128(wl + c.off_w1);
@@ -901,122 +902,117 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
       product(KindC<PR_QKV>{}, l, -1);
-      // accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V -> fp16 tiles, and their fp16 rounding remainders
-      // as e5m2 bytes: Q and K in the L tile (chunk of (row, head): 8 bytes of Q, 8 of K), V in the V-remainder tile.
-      // This half takes heads [4h, 4h + 4) of each matrix, 16 columns = 2 heads per trip.
-#pragma unroll 1   // rolled on purpose: the kernel is instruction-fetch sensitive (measured: unrolled 44.9 ms per pass, rolled 44.1)
-      for (uint32_t trip = 0; trip < 6; ++trip) {
-        const uint32_t mat = trip >> 1;                                  // 0 Q, 1 K, 2 V
-        const uint32_t c0 = 64u * mat + 32u * (uint32_t)h + 16u * (trip & 1u);
-        uint32_t r[16];
-        umma::tmem_ld16(tA + c0, r);
-        umma::tmem_ld_wait();
-        uint8_t* dst = mat == 0 ? TQ : (mat == 1 ? TK : TV);
-        const uint32_t ch = (c0 & 63u) >> 3;
-        uint32_t w[8];
+      // ---- causal attention (transformer.py:58-65), in fp32, FOUR HEADS AT A TIME ----
+      // The accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V stay in tensor memory; per pass hp the fp32
+      // values of heads [4 hp, 4 hp + 4) are copied into the Q / K / V tiles (128 rows x 4 heads x 8 floats = 16 KB each:
+      // the same three tiles hold either half) and the pairs of those heads are worked off with plain fp32 FMAs — no
+      // operand rounding, no remainders to carry, a third of the instructions of the split-fp16 form.  (row, head hh)
+      // occupies the two 16-byte chunks 2 hh, 2 hh + 1 of the row in the usual 128-byte swizzle: the stores of eight
+      // consecutive rows and the loads of a quarter-warp (two consecutive rows x four heads) are conflict-free.
+      // The output of pass 0 goes straight into the L tile as the merged product's A operand (bytes [0,64) of a row:
+      // fp16 hi of features 0..31, bytes [64,128): their lo parts); pass 1's output belongs in the Q tile, which other
+      // items still read, so it waits in registers for the barrier.
+      uint4 keep_hi[2], keep_lo[2];
+      uint32_t keep_off[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll 1
+      for (uint32_t hp = 0; hp < 2; ++hp) {
+        if (hp == 1) umma::group_sync(bar_id, FGROUP_THREADS);   // pass 0 has read its last K / V row
+        // this thread copies heads 2 h, 2 h + 1 of the pass (16 accumulator columns per matrix)
+#pragma unroll 1
+        for (uint32_t mat = 0; mat < 3; ++mat) {
+          uint32_t r[16];
+          umma::tmem_ld16(tA + 64u * mat + 32u * hp + 16u * (uint32_t)h, r);
+          umma::tmem_ld_wait();
+          uint8_t* dst = mat == 0 ? TQ : (mat == 1 ? TK : TV);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = umma::pack_f16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, ch + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
-        constexpr uint32_t kNegOne = 0xBC00BC00u;
-        uint32_t e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          e[i] = umma::pack_e5m2x2(fh_ll(w[i], kNegOne, __uint_as_float(r[2 * i])), fh_hl(w[i], kNegOne, __uint_as_float(r[2 * i + 1])));
-        const uint4 lo8 = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-        if (mat < 2) {
-          *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch) + 8u * mat) = make_uint2(lo8.x, lo8.y);
-          *reinterpret_cast<uint2*>(TL + umma::sw128_offset(row, ch + 1) + 8u * mat) = make_uint2(lo8.z, lo8.w);
-        } else {
-          *reinterpret_cast<uint2*>(TVL + vlo_offset(row, ch)) = make_uint2(lo8.x, lo8.y);
-          *reinterpret_cast<uint2*>(TVL + vlo_offset(row, ch + 1)) = make_uint2(lo8.z, lo8.w);
+          for (uint32_t c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, 4u * (uint32_t)h + c)) =
+                make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         }
-      }
-      umma::tc_fence_before_sync();
-      umma::group_sync(bar_id, FGROUP_THREADS);
-
-      // ---- causal attention (transformer.py:58-65) ----
-      {
-        // Work item = (query position, sequence, head), query-major (the lanes of a warp walk the same number of keys),
-        // heaviest queries first; a tile holds at most 128 x 8 items, i.e. at most four per thread.  K, V and their
-        // remainders are streamed from shared memory in ONE pass over the keys: the softmax is taken relative to the first
-        // key's score instead of the row maximum (it is shift-invariant); in the rare case that a score exceeds the
-        // reference by more than 14 octaves the accumulators are rescaled and the reference moves, so the weights stay
-        // within fp16 range.  The loops are rolled on purpose (the kernel is instruction-fetch sensitive).
-        // The attention output's hi part overwrites the query's Q chunk in place; its lo part belongs in the L tile,
-        // whose chunks other items still read (K remainders), so it waits in registers for the barrier.
-        const int npairs = nseq * FH;
+        umma::tc_fence_before_sync();
+        umma::group_sync(bar_id, FGROUP_THREADS);
+        // Work item = (query position, sequence, head of the pass), query-major (the lanes of a warp walk the same
+        // number of keys), heaviest queries first; at most 128 x 4 items, two per thread: item gt and, from the other
+        // end of the list, item 511 - gt, so that every thread visits about the same number of keys.  ONE pass over the
+        // keys: the softmax is taken relative to the first key's score (it is shift-invariant); in the rare case that a
+        // score exceeds the reference by more than 14 octaves the accumulators are rescaled and the reference moves.
+        const int npairs = nseq * 4;
         const int nq = prune ? 1 : len;                      // last layer: only the last query is live
         const int nitems = npairs * nq;
         const float inv_npairs = __fdividef(1.0f, (float)npairs);
-        uint4 lo_keep[4];
-        uint32_t lo_off[4];
 #pragma unroll 1
-        for (int u = 0; u < 4; ++u) {
-          const int it = gt + u * FGROUP_THREADS;
-          uint4 wl = make_uint4(0u, 0u, 0u, 0u);
-          uint32_t keep_off = 0xFFFFFFFFu;
+        for (int u = 0; u < 2; ++u) {
+          const int it = u == 0 ? gt : 2 * FGROUP_THREADS - 1 - gt;
+          uint32_t off_out = 0xFFFFFFFFu;
+          uint4 w = make_uint4(0u, 0u, 0u, 0u), wl = w;
           if (it < nitems) {
-            int b = (int)(((float)it + 0.5f) * inv_npairs);  // query block = it / npairs (exact: it < 1024, npairs <= 256)
+            const int b = (int)(((float)it + 0.5f) * inv_npairs);  // query block = it / npairs (exact: it < 512, npairs <= 128)
             const int p = it - b * npairs;
-            const int b2 = b ^ ((b >> 1) & 1);               // blocks 2m, 2m + 1 swapped for odd m: the two halves of the
-            b = b2 < nq ? b2 : b;                            // group (items it and it + 128) get equal numbers of key visits
             const int t = len - 1 - b;
-            const int sl = p >> 3, hd = p & 7;
-            const uint32_t qoff = umma::sw128_offset((uint32_t)(sl + t * spt), (uint32_t)hd);
-            const uint4 qw = *reinterpret_cast<const uint4*>(TQ + qoff);
-            const uint4 ql = widen_lo8(*reinterpret_cast<const uint2*>(TL + qoff));
+            const int sl = p >> 2, hd = p & 3;
+            const uint32_t qrow = (uint32_t)(sl + t * spt);
+            const uint32_t qoff = umma::sw128_offset(qrow, 2u * (uint32_t)hd);
+            const float4 q0 = *reinterpret_cast<const float4*>(TQ + qoff);
+            const float4 q1 = *reinterpret_cast<const float4*>(TQ + (qoff ^ 16u));
             float ref = 0.f, z = 0.f;
             float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            uint32_t c2[4] = {0u, 0u, 0u, 0u};
             uint32_t krow = (uint32_t)sl;
 #pragma unroll kKeyUnroll
             for (int j = 0; j <= t; ++j, krow += (uint32_t)spt) {
-              const uint32_t koff = umma::sw128_offset(krow, (uint32_t)hd);
-              const float sj = score_hilo(qw, ql, *reinterpret_cast<const uint4*>(TK + koff),
-                                          widen_lo8(*reinterpret_cast<const uint2*>(TL + koff + 8u)));
+              const uint32_t koff = umma::sw128_offset(krow, 2u * (uint32_t)hd);
+              const float4 k0 = *reinterpret_cast<const float4*>(TK + koff);
+              const float4 k1 = *reinterpret_cast<const float4*>(TK + (koff ^ 16u));
+              const float sj = fminf(fmaxf(((q0.x * k0.x + q0.y * k0.y) + (q0.z * k0.z + q0.w * k0.w)) +
+                                               ((q1.x * k1.x + q1.y * k1.y) + (q1.z * k1.z + q1.w * k1.w)),
+                                           -3.0e38f), 3.0e38f);
               ref = j == 0 ? sj : ref;
               float arg = (sj - ref) * qk_scale_log2e;
               if (arg > 14.0f) {   // rare
                 const float f = ex2_approx(-arg);
-                const uint32_t f2 = umma::pack_f16x2(f, f);
                 z *= f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) o[c] *= f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) c2[c] = hfma2(c2[c], f2, 0u);
                 ref = sj;
                 arg = 0.f;
               }
               const float e = ex2_approx(arg);
               z += e;
-              const uint32_t ph = umma::pack_f16x2(e, 0.f);                                  // e = hi + lo to 2^-22
-              const uint32_t pw = umma::pack_f16x2(e - umma::unpack_f16x2(ph).x, 0.f);
-              pv_step<false>(ph, pw, *reinterpret_cast<const uint4*>(TV + koff),
-                             widen_lo8(*reinterpret_cast<const uint2*>(TVL + (koff >> 1))), o, c2);
+              const float4 v0 = *reinterpret_cast<const float4*>(TV + koff);
+              const float4 v1 = *reinterpret_cast<const float4*>(TV + (koff ^ 16u));
+              o[0] = fmaf(e, v0.x, o[0]); o[1] = fmaf(e, v0.y, o[1]); o[2] = fmaf(e, v0.z, o[2]); o[3] = fmaf(e, v0.w, o[3]);
+              o[4] = fmaf(e, v1.x, o[4]); o[5] = fmaf(e, v1.y, o[5]); o[6] = fmaf(e, v1.z, o[6]); o[7] = fmaf(e, v1.w, o[7]);
             }
-            pv_finish(o, c2, __fdividef(1.0f, z));
+            const float inv_z = __fdividef(1.0f, z);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] *= inv_z;
             if (fl & BFB200_SITE_HEAD_OUT) {   // transformer.py:116-122
               const RowRng prr = make_row_rng(ms, s0 + (uint32_t)sl);
-              const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, (uint32_t)(hd >> 2)) >> (8 * (hd & 3))) & 0xFFu;
+              const uint32_t k = (half_keep_mask(ms, prr, (uint32_t)t, sb + 4u, hp) >> (8 * hd)) & 0xFFu;
 #pragma unroll
               for (int c = 0; c < 8; ++c) o[c] = ((k >> c) & 1u) ? o[c] * ms.scale : 0.f;
             }
-            uint4 w;
             umma::split_f16x2(o[0], o[1], w.x, wl.x); umma::split_f16x2(o[2], o[3], w.y, wl.y);
             umma::split_f16x2(o[4], o[5], w.z, wl.z); umma::split_f16x2(o[6], o[7], w.w, wl.w);
-            *reinterpret_cast<uint4*>(TQ + qoff) = w;   // in place: other items read only K / V rows, never this Q chunk
-            keep_off = qoff;
+            off_out = umma::sw128_offset(qrow, (uint32_t)hd);   // hi chunk; the lo chunk is four chunks (64 bytes) further
+            if (hp == 0) {
+              *reinterpret_cast<uint4*>(TL + off_out) = w;
+              *reinterpret_cast<uint4*>(TL + (off_out ^ 64u)) = wl;
+            }
           }
+          if (hp == 1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // (register select: keeps the arrays out of local memory)
-            if (u == k) { lo_keep[k] = wl; lo_off[k] = keep_off; }
+            for (int k = 0; k < 2; ++k)   // (register select: keeps the arrays out of local memory)
+              if (u == k) { keep_hi[k] = w; keep_lo[k] = wl; keep_off[k] = off_out; }
+          }
         }
-        umma::group_sync(bar_id, FGROUP_THREADS);   // every K remainder has been read
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (lo_off[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(TL + lo_off[k]) = lo_keep[k];
       }
+      umma::group_sync(bar_id, FGROUP_THREADS);   // every Q / K / V row of pass 1 has been read
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (keep_off[k] != 0xFFFFFFFFu) {
+          *reinterpret_cast<uint4*>(TQ + keep_off[k]) = keep_hi[k];
+          *reinterpret_cast<uint4*>(TQ + (keep_off[k] ^ 64u)) = keep_lo[k];
+        }
 
       if (!live) {
         // dead rows of the last layer: take part in the barriers of the products (thread 0 of the group still issues
