@@ -56,7 +56,6 @@ constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows
 // shared-memory tiles of a group: Q (then the attention output), K, the 8-bit remainders of Q and K, V (between the
 // pair phases: landing zone of the next QKV product's W_lo rows)
 constexpr int T_Q = 0, T_K = 1, T_L = 2, T_V = 3, FTILES = 4;
-constexpr uint32_t VLO_BYTES = FROWS * FD;    // per group: V's 8-bit remainders (then landing zone of W_qkv's lo V rows)
 constexpr uint32_t WLO_QK_BYTES = 2 * FD * 128, WLO_V_BYTES = FD * 128;   // lo image of one layer's W_qkv: Q and K rows, V rows
 constexpr uint32_t WLO_BYTES = WLO_QK_BYTES + WLO_V_BYTES;
 constexpr uint32_t HEAD_BYTES = FMAXV * 128;  // vocabulary head: streamed per tile into the dead Q tile
@@ -65,10 +64,10 @@ constexpr uint32_t C_XHI = 0, C_XLO = 32, C_ACC = 64;
 constexpr size_t kFusedSmemMax = 227 * 1024;
 constexpr uint32_t kBarrierBytes = 64;
 #ifndef BFB_KEY_UNROLL
-#define BFB_KEY_UNROLL 2   // key loop of the pair phase (measured)
+#define BFB_KEY_UNROLL 1   // key loop of the pair phase (measured: rolled 39.3 ms per pass, x2 40.1, x4 39.4 — instruction fetch)
 #endif
 constexpr int kKeyUnroll = BFB_KEY_UNROLL;
-constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)FGROUPS * VLO_BYTES;
+constexpr uint32_t kTilesBytes = (uint32_t)(FGROUPS * FTILES) * TILE_BYTES;
 
 struct FusedLayout {
   uint32_t fp;            // F rounded up to 16
@@ -265,74 +264,6 @@ using umma::fh_hh;
 using umma::fh_lh;
 using umma::fh_hl;
 
-// d + a . b over the 8 fp16 values of two packed words (fp32 accumulation; products of halves are exact)
-__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b, float d) {   // two chains of four (latency)
-  float e = fh_ll(a.z, b.z, 0.f);
-  d = fh_ll(a.x, b.x, d);
-  e = fh_hh(a.z, b.z, e);
-  d = fh_hh(a.x, b.x, d);
-  e = fh_ll(a.w, b.w, e);
-  d = fh_ll(a.y, b.y, d);
-  e = fh_hh(a.w, b.w, e);
-  d = fh_hh(a.y, b.y, d);
-  return d + e;
-}
-// the 8-bit remainders of a Q or K head row (8 bytes) as packed fp16
-__device__ __forceinline__ uint4 widen_lo8(const uint2& w) {
-  return make_uint4(umma::e5m2x4_to_f16x2_lo(w.x), umma::e5m2x4_to_f16x2_hi(w.x), umma::e5m2x4_to_f16x2_lo(w.y),
-                    umma::e5m2x4_to_f16x2_hi(w.y));
-}
-__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-constexpr uint32_t kOneOne = 0x3C003C00u;   // (1.0h, 1.0h)
-// q . k with q = qh + ql, k = kh + kl (fp16 + 8-bit remainders): qh . kh with fp32 accumulation, the cross terms
-// ql . kh + qh . kl (2^-11 of the result) as packed-half FMAs; the ql . kl term is below 2^-22 of |q||k|.  The clamp
-// keeps an overflowing cross term (|q||k| beyond 1e8) from turning the row into NaNs.
-__device__ __forceinline__ float score_hilo(const uint4& qh, const uint4& ql, const uint4& kh, const uint4& kl) {
-  uint32_t c = hfma2(ql.x, kh.x, 0u), c1 = hfma2(qh.x, kl.x, 0u);   // two chains of four (latency)
-  c = hfma2(ql.y, kh.y, c);
-  c1 = hfma2(qh.y, kl.y, c1);
-  c = hfma2(ql.z, kh.z, c);
-  c1 = hfma2(qh.z, kl.z, c1);
-  c = hfma2(ql.w, kh.w, c);
-  c1 = hfma2(qh.w, kl.w, c1);
-  c = hfma2(c, kOneOne, c1);
-  const float s = fh_hl(c, kOneOne, fh_ll(c, kOneOne, dot8_f16(qh, kh, 0.f)));
-  return fminf(fmaxf(s, -3.0e38f), 3.0e38f);
-}
-// One key of the PV product with weight p = ph + pw (halves `HI` of the packed words) and value row v = vh + vl:
-// o += ph * vh in fp32; the cross terms pw * vh + ph * vl accumulate in the packed halves c2 (folded into o at the end)
-template <bool HI>
-__device__ __forceinline__ void pv_step(uint32_t ph, uint32_t pw, const uint4& vh, const uint4& vl, float (&o)[8],
-                                        uint32_t (&c2)[4]) {
-  const uint32_t phd = __byte_perm(ph, 0u, HI ? 0x3232u : 0x1010u), pwd = __byte_perm(pw, 0u, HI ? 0x3232u : 0x1010u);
-  if (HI) {
-    o[0] = fh_hl(ph, vh.x, o[0]); o[1] = fh_hh(ph, vh.x, o[1]); o[2] = fh_hl(ph, vh.y, o[2]); o[3] = fh_hh(ph, vh.y, o[3]);
-    o[4] = fh_hl(ph, vh.z, o[4]); o[5] = fh_hh(ph, vh.z, o[5]); o[6] = fh_hl(ph, vh.w, o[6]); o[7] = fh_hh(ph, vh.w, o[7]);
-  } else {
-    o[0] = fh_ll(ph, vh.x, o[0]); o[1] = fh_lh(ph, vh.x, o[1]); o[2] = fh_ll(ph, vh.y, o[2]); o[3] = fh_lh(ph, vh.y, o[3]);
-    o[4] = fh_ll(ph, vh.z, o[4]); o[5] = fh_lh(ph, vh.z, o[5]); o[6] = fh_ll(ph, vh.w, o[6]); o[7] = fh_lh(ph, vh.w, o[7]);
-  }
-  c2[0] = hfma2(phd, vl.x, hfma2(pwd, vh.x, c2[0]));
-  c2[1] = hfma2(phd, vl.y, hfma2(pwd, vh.y, c2[1]));
-  c2[2] = hfma2(phd, vl.z, hfma2(pwd, vh.z, c2[2]));
-  c2[3] = hfma2(phd, vl.w, hfma2(pwd, vh.w, c2[3]));
-}
-// o = (o + c2) * inv_z -> fp16 hi + lo words (the attention output of one (row, head): A operand of the W_out product)
-__device__ __forceinline__ void pv_finish(float (&o)[8], const uint32_t (&c2)[4], float inv_z) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    o[2 * i] = fh_ll(c2[i], kOneOne, o[2 * i]) * inv_z;
-    o[2 * i + 1] = fh_hl(c2[i], kOneOne, o[2 * i + 1]) * inv_z;
-  }
-}
-// V's 8-bit remainders of (row, head) sit at HALF the byte offset of the (row, head) chunk in a swizzled fp16 tile
-// (rows of 64 bytes, 8-byte pieces permuted by row & 7: conflict-free for the stores of consecutive rows and the loads
-// of consecutive heads), so one offset per key row addresses V, its remainders and K.
-__device__ __forceinline__ uint32_t vlo_offset(uint32_t row, uint32_t head) { return umma::sw128_offset(row, head) >> 1; }
 __device__ __forceinline__ float ex2_approx(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -643,16 +574,13 @@ __device__ __forceinline__ void fused_issue(const IssueCtx c, int layer, uint64_
   const uint32_t wl = c.img_u32 + (uint32_t)layer * c.layer_bytes;
   const uint32_t fp = c.fp;
   if (kind == PR_QKV) {
-    // [Q | K | V] = x W_qkv^T with x = hi + lo from TMEM, W_qkv = hi + lo (lo rows of Q, K in the V tile, of V in the
-    // V-remainder tile; the x_lo W_lo term is dropped)
+    // [Q | K | V] = x W_qkv^T with x = hi + lo from TMEM; the Q and K rows of W_qkv additionally as hi + lo (their lo
+    // rows were streamed into the V tile; the x_lo W_lo term is dropped)
     const uint64_t dw = umma::smem_desc_sw128(wl), dl = umma::smem_desc_sw128(tile0 + T_V * TILE_BYTES);
-    const uint64_t dlv = umma::smem_desc_sw128(c.tiles_u32 + (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)G * VLO_BYTES);
     const uint32_t id192 = umma::instr_desc_f16(FROWS, 3 * FD), id128 = umma::instr_desc_f16(FROWS, 2 * FD);
-    const uint32_t id64 = umma::instr_desc_f16(FROWS, FD);
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XHI + 8u * k, dw + 2 * k, id192, k > 0);
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XLO + 8u * k, dw + 2 * k, id192, 1u);
     for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC, gb + C_XHI + 8u * k, dl + 2 * k, id128, 1u);
-    for (int k = 0; k < 4; ++k) umma::mma_f16_ts(gb + C_ACC + 2u * FD, gb + C_XHI + 8u * k, dlv + 2 * k, id64, 1u);
   } else if (kind == PR_MERGED) {
     // columns [0, 64) = attn W_out^T ; [64, 64 + fp) = attn ((W1 g1) W_out)^T + x (W1 g1)^T
     // The attention output sits in two tiles: features 0..31 (heads 0..3) in the L tile, features 32..63 in the Q tile,
@@ -742,7 +670,6 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   uint8_t* TK = smem + (uint32_t)(g * FTILES + T_K) * TILE_BYTES;
   uint8_t* TL = smem + (uint32_t)(g * FTILES + T_L) * TILE_BYTES;
   uint8_t* TV = smem + (uint32_t)(g * FTILES + T_V) * TILE_BYTES;
-  uint8_t* TVL = smem + (uint32_t)(FGROUPS * FTILES) * TILE_BYTES + (uint32_t)g * VLO_BYTES;
   const float* params = reinterpret_cast<const float*>(img + lay.off_params);
   float2* red = reinterpret_cast<float2*>(TK);   // LayerNorm exchange: K is dead whenever it is in use
 
@@ -767,9 +694,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
   const int64_t tile_first = (int64_t)blockIdx.x * FGROUPS + g, tile_step = (int64_t)gridDim.x * FGROUPS;
   const uint8_t* wlo_src = a.image + lay.off_wlo;
   auto stream_wlo = [&](int layer) {   // one thread: W_qkv lo rows of `layer` -> V tile (Q, K rows) and V-remainder tile (V rows)
-    umma::mbar_expect_tx(&bar_wlo[g], WLO_BYTES);
+    // (the lo rows of W_v are packed in the image too but not used: with V kept in fp32 the W_v remainder moves the
+    //  worst probability error by < 0.1 of the tolerance — tools/fused_accuracy.py — and costs 1.9 % of the pass)
+    umma::mbar_expect_tx(&bar_wlo[g], WLO_QK_BYTES);
     umma::bulk_g2s(TV, wlo_src + (uint32_t)layer * WLO_BYTES, WLO_QK_BYTES, &bar_wlo[g]);
-    umma::bulk_g2s(TVL, wlo_src + (uint32_t)layer * WLO_BYTES + WLO_QK_BYTES, WLO_V_BYTES, &bar_wlo[g]);
   };
   if (gt == 0 && tile_first < a.n_tiles) stream_wlo(0);   // for the first QKV product
   umma::mbar_wait(bar_image, 0);
@@ -918,16 +846,20 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       for (uint32_t hp = 0; hp < 2; ++hp) {
         if (hp == 1) umma::group_sync(bar_id, FGROUP_THREADS);   // pass 0 has read its last K / V row
         // this thread copies heads 2 h, 2 h + 1 of the pass (16 accumulator columns per matrix)
-#pragma unroll 1
-        for (uint32_t mat = 0; mat < 3; ++mat) {
-          uint32_t r[16];
-          umma::tmem_ld16(tA + 64u * mat + 32u * hp + 16u * (uint32_t)h, r);
+        {
+          uint32_t rq[16], rk[16], rv[16];   // the three loads travel together: one tensor-memory latency per pass
+          const uint32_t c0 = tA + 32u * hp + 16u * (uint32_t)h;
+          umma::tmem_ld16(c0, rq);
+          umma::tmem_ld16(c0 + 64u, rk);
+          umma::tmem_ld16(c0 + 128u, rv);
           umma::tmem_ld_wait();
-          uint8_t* dst = mat == 0 ? TQ : (mat == 1 ? TK : TV);
 #pragma unroll
-          for (uint32_t c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(dst + umma::sw128_offset(row, 4u * (uint32_t)h + c)) =
-                make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          for (uint32_t c = 0; c < 4; ++c) {
+            const uint32_t off = umma::sw128_offset(row, 4u * (uint32_t)h + c);
+            *reinterpret_cast<uint4*>(TQ + off) = make_uint4(rq[4 * c], rq[4 * c + 1], rq[4 * c + 2], rq[4 * c + 3]);
+            *reinterpret_cast<uint4*>(TK + off) = make_uint4(rk[4 * c], rk[4 * c + 1], rk[4 * c + 2], rk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(TV + off) = make_uint4(rv[4 * c], rv[4 * c + 1], rv[4 * c + 2], rv[4 * c + 3]);
+          }
         }
         umma::tc_fence_before_sync();
         umma::group_sync(bar_id, FGROUP_THREADS);

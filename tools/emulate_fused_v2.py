@@ -16,7 +16,7 @@ def hilo8(t):
     return hi.double() + lo.double()
 
 
-def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=False, v_lo=False, wv_lo=False, head_lo=False, wout_lo=False, qk8=True, wqk_lo=True, xlo_qk=True):
+def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=False, v_lo=False, wv_lo=False, head_lo=False, wout_lo=False, qk8=True, wqk_lo=True, xlo_qk=True, exact_qkv=False, h_lo=True, xlo_v=True):
     D = R.model_dims(sd); d, Hh, dh, L = D["d"], D["H"], D["dh"], D["L"]
     n = src.shape[0]; scale = 1.0 / (1.0 - p)
     x = sd["embedding.weight"].double()[src]
@@ -28,11 +28,11 @@ def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=F
         wq = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_q.weight"] for h in range(Hh)]).double()
         wk = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_k.weight"] for h in range(Hh)]).double()
         wv = torch.cat([sd[f"{pre}self_attn.heads.{h}.W_v.weight"] for h in range(Hh)]).double()
-        fq = hilo8 if qk8 else r16
+        fq = (lambda t: t) if exact_qkv else (hilo8 if qk8 else r16)
         fw = hilo if wqk_lo else r16
         xq = x if xlo_qk else r16(x)
         q = fq(xq @ fw(wq).t()); k = fq(xq @ fw(wk).t())
-        v = (hilo if v_lo else r16)(x @ (hilo if wv_lo else r16)(wv).t())
+        v = ((lambda t: t) if exact_qkv else (hilo if v_lo else r16))((x if xlo_v else r16(x)) @ (hilo if wv_lo else r16)(wv).t())
         S = x.shape[1]
         qh = q.view(n, S, Hh, dh).permute(1, 2, 0, 3); kh = k.view(n, S, Hh, dh).permute(1, 2, 0, 3)
         vh = v.view(n, S, Hh, dh).permute(1, 2, 0, 3)
@@ -53,7 +53,7 @@ def forward_v2(sd, src, keeps, p, attn_lo=False, w2_lo=False, mlo=False, w1_lo=F
         acc = x @ w1g.t() + o @ M16.t()
         hdn = torch.relu(rstd * (acc - mean * col_s) + col_c)
         W2 = sd[f"{pre}ff.net.2.weight"].double()
-        ff = hilo(hdn) @ (hilo if w2_lo else r16)(W2).t() + sd[f"{pre}ff.net.2.bias"].double()
+        ff = (hilo if h_lo else r16)(hdn) @ (hilo if w2_lo else r16)(W2).t() + sd[f"{pre}ff.net.2.bias"].double()
         y = x + ff
         x = torch.nn.functional.layer_norm(y, (d,), sd[f"{pre}norm2.weight"].double(), sd[f"{pre}norm2.bias"].double(), 1e-5)
         x = x * keeps[1 + i].double() * scale
@@ -66,7 +66,11 @@ if __name__ == "__main__":
     S = dict(attn_lo=True, w2_lo=True, v_lo=True, wv_lo=True)
     E.VARIANTS = {"shipped": S, "no_qk8": dict(S, qk8=False), "no_wqk_lo": dict(S, wqk_lo=False),
                   "no_qk8_wqk": dict(S, qk8=False, wqk_lo=False), "no_qk8_wqk_xlo": dict(S, qk8=False, wqk_lo=False, xlo_qk=False),
-                  "no_w2lo": dict(S, w2_lo=False), "no_xlo_qk": dict(S, xlo_qk=False), "shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
+                  "no_w2lo": dict(S, w2_lo=False), "no_xlo_qk": dict(S, xlo_qk=False),
+                  "new": dict(S, exact_qkv=True), "new_no_wqk": dict(S, exact_qkv=True, wqk_lo=False), "new_no_wv": dict(S, exact_qkv=True, wv_lo=False),
+                  "new_no_wqkv": dict(S, exact_qkv=True, wqk_lo=False, wv_lo=False), "new_no_w2": dict(S, exact_qkv=True, w2_lo=False),
+                  "new_no_hlo": dict(S, exact_qkv=True, h_lo=False), "new_no_attnlo": dict(S, exact_qkv=True, attn_lo=False),
+                  "new_no_wqkv_w2": dict(S, exact_qkv=True, wqk_lo=False, wv_lo=False, w2_lo=False), "shipped_v2": dict(), "attn_lo": dict(attn_lo=True), "attn+w2": dict(attn_lo=True, w2_lo=True),
                   "attn+w2+m+w1": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True),
                   "attn+w2+m+w1+v+wv": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True),
                   "all": dict(attn_lo=True, w2_lo=True, mlo=True, w1_lo=True, v_lo=True, wv_lo=True, head_lo=True, wout_lo=True)}
