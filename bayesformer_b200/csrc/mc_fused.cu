@@ -10,8 +10,9 @@
 //   * row phases    — read the fp32 accumulator row from TMEM (tcgen05.ld 32x32b), do bias / ReLU / residual /
 //                     LayerNorm / dropout in registers and leave the next product's A operand IN TENSOR MEMORY
 //                     (tcgen05.st; the "TS" form of tcgen05.mma reads it from there) as fp16 hi + lo parts;
-//   * pair phase    — thread = (sequence, head[, query subset]): causal softmax(QK^T / sqrt(dh)) V from the fp16
-//                     Q / K / V tiles in shared memory (a head's 8 values are exactly one 16-byte swizzle chunk);
+//   * pair phase    — causal softmax(QK^T / sqrt(dh)) V in fp32 on CUDA cores, FOUR HEADS AT A TIME: the fp32 Q / K / V
+//                     values of half the heads are copied from the accumulator into the three 16 KB tiles, work item =
+//                     (query, sequence, head), one streamed pass over the keys; then the other half;
 //   * score phase   — 8 or 16 threads per sequence: log-softmax over the vocabulary, probabilities, max /
 //                     margin / entropy, greedy arg-max or inverse-CDF sample.
 //
@@ -20,11 +21,10 @@
 // multiplied twice into the same fp32 accumulator:
 //   - the residual stream x lives in TMEM as fp16 hi + lo (64 columns, 2^-22 relative): it is at once the residual and
 //     the A operand of the QKV, FFN1 and vocabulary-head products;
-//   - the FFN hidden row and the attention output likewise; W_qkv and W2 have a lo image too (W_qkv's is streamed per
-//     layer from L2 into the dead V tiles by bulk copies);
-//   - Q, K and V reach the pair phase as fp16 + an 8-bit (e5m2) remainder; the score and PV products take the cross
-//     terms with packed-half FMAs (the remainders' products need no fp32 accumulation).
-// What stays single fp16: W_out, W1, the vocabulary head's weights.
+//   - the FFN hidden row and the attention output likewise; the Q / K rows of W_qkv and W2 have a lo image too
+//     (W_qkv's is streamed per layer from L2 into the dead V tile by a bulk copy);
+//   - Q, K and V never leave fp32: attention works on the accumulator's values.
+// What stays single fp16: W_v, W_out, W1, the vocabulary head's weights.
 //
 // With the reference's default dropout sites W_out and FFN1 are ONE product (`merged`): FFN1(LN1(v)), v = x + attn W_out^T,
 // needs v only through its row statistics and through v (W1 g1)^T = x (W1 g1)^T + attn ((W1 g1) W_out)^T.
@@ -53,8 +53,9 @@ constexpr int FTHREADS = FGROUPS * FGROUP_THREADS;
 constexpr int FMAXLEN = 128;    // longest sequence the fused path takes (one sequence per 128-row tile)
 constexpr int FMAXV = 128;
 constexpr uint32_t TILE_BYTES = FROWS * 128;  // one fp16 operand tile (128 rows x 64 halves)
-// shared-memory tiles of a group: Q (then the attention output), K, the 8-bit remainders of Q and K, V (between the
-// pair phases: landing zone of the next QKV product's W_lo rows)
+// shared-memory tiles of a group: Q, K, V hold the fp32 values of four heads at a time during attention (V afterwards:
+// landing zone of the next QKV product's W_lo rows; Q afterwards: attention output of heads 4..7 as [hi | lo], then the
+// streamed vocabulary head); L: attention output of heads 0..3 as [hi | lo]
 constexpr int T_Q = 0, T_K = 1, T_L = 2, T_V = 3, FTILES = 4;
 constexpr uint32_t WLO_QK_BYTES = 2 * FD * 128, WLO_V_BYTES = FD * 128;   // lo image of one layer's W_qkv: Q and K rows, V rows
 constexpr uint32_t WLO_BYTES = WLO_QK_BYTES + WLO_V_BYTES;
