@@ -547,6 +547,10 @@ __device__ __forceinline__ void ln_finish(float (&v)[HW], float2 own, float2 oth
 // debug build only (make EXTRA=-DBFB_FUSED_TIMING): cycles one observer thread per group spends in the product
 // round trips (barrier -> MMA issue -> completion wait), and in total
 __device__ unsigned long long bfb_fused_dbg[8];
+__device__ unsigned long long bfb_fused_phase[16];   // cycles per phase, summed over the observer lanes
+#define BFB_PHASE(i) do { const long long _n = clock64(); ph[i] += _n - ph_last; ph_last = _n; } while (0)
+#else
+#define BFB_PHASE(i) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -742,6 +746,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 #ifdef BFB_FUSED_TIMING
   long long dbg[3] = {0, 0, 0};   // observer lanes: round-trip cycles, round trips
   const long long t_begin = clock64();
+  long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ph_last = t_begin;
 #endif
   // One product: operands are in TMEM (tcgen05.st of this group's threads) or shared memory -> accumulators in TMEM.
   // next_wlo >= 0: the V tiles are dead from here on, so the issuing thread starts the bulk copies of that layer's
@@ -819,6 +824,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       store_hilo_half(tXh, tXl, x);
     }
 
+    BFB_PHASE(0);
     for (int l = 0; l < a.n_layers; ++l) {
       const float* pl = params + (uint32_t)l * lay.params_per_layer;
       const uint32_t sb = 1u + BFB200_SITES_PER_LAYER * (uint32_t)l;
@@ -831,6 +837,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 
       // ---- Q, K, V = x W^T for all heads (transformer.py:54-57): one N = 192 product ----
       product(KindC<PR_QKV>{}, l, -1);
+      BFB_PHASE(1);
       // ---- causal attention (transformer.py:58-65), in fp32, FOUR HEADS AT A TIME ----
       // The accumulator columns [0,64) = Q, [64,128) = K, [128,192) = V stay in tensor memory; per pass hp the fp32
       // values of heads [4 hp, 4 hp + 4) are copied into the Q / K / V tiles (128 rows x 4 heads x 8 floats = 16 KB each:
@@ -845,7 +852,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       uint32_t keep_off[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll 1
       for (uint32_t hp = 0; hp < 2; ++hp) {
+        BFB_PHASE(3);
         if (hp == 1) umma::group_sync(bar_id, FGROUP_THREADS);   // pass 0 has read its last K / V row
+        BFB_PHASE(4);
         // this thread copies heads 2 h, 2 h + 1 of the pass (16 accumulator columns per matrix)
         {
           uint32_t rq[16], rk[16], rv[16];   // the three loads travel together: one tensor-memory latency per pass
@@ -863,7 +872,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           }
         }
         umma::tc_fence_before_sync();
+        BFB_PHASE(2);
         umma::group_sync(bar_id, FGROUP_THREADS);
+        BFB_PHASE(4);
         // Work item = (query position, sequence, head of the pass), query-major (the lanes of a warp walk the same
         // number of keys), heaviest queries first; at most 128 x 4 items, two per thread: item gt and, from the other
         // end of the list, item 511 - gt, so that every thread visits about the same number of keys.  ONE pass over the
@@ -939,7 +950,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
           }
         }
       }
+      BFB_PHASE(3);
       umma::group_sync(bar_id, FGROUP_THREADS);   // every Q / K / V row of pass 1 has been read
+      BFB_PHASE(4);
 #pragma unroll
       for (int k = 0; k < 2; ++k)
         if (keep_off[k] != 0xFFFFFFFFu) {
@@ -966,6 +979,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       if (merged) {
         // ---- W_out and FFN1 in one product; residual from the block input; LayerNorm1 folded (transformer.py:125, :231-232) ----
         product(KindC<PR_MERGED>{}, l, next_wlo);
+        BFB_PHASE(5);
         {
           float v[HW];
           tmem_load_half(tA + h * HW, v);
@@ -1032,6 +1046,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
       }
 
       // ---- FFN: Linear(F -> d) + bias, residual from the block input, LayerNorm2, layer-out dropout ----
+      BFB_PHASE(6);
       uint4 rnd_out[4];   // FAST == 1: the layer-out site's random words, drawn while the FFN2 product runs
       product_ov(KindC<PR_FFN2>{}, l, -1, prune,   // last layer: the Q tile is dead now and receives the vocabulary head
                  [&] {
@@ -1039,6 +1054,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
                    philox_half_raw(rnd_out, ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h);
                    return fold_raw(rnd_out);
                  });
+      BFB_PHASE(7);
       {
         const uint32_t k_resid = (fl & BFB200_SITE_FFN_RESID) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 3u, (uint32_t)h) : 0u;
         const uint32_t k_out = (!FAST && (fl & BFB200_SITE_LAYER_OUT)) ? half_keep_mask(ms, rr, (uint32_t)pos, sb + 0u, (uint32_t)h) : 0u;
@@ -1058,10 +1074,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
         store_hilo_half(tXh, tXl, v);   // next block's input / the vocabulary head's operand
       }
       }   // live
+      BFB_PHASE(8);
     }
 
     // ---- vocabulary head on every row (only the last position is consumed, active_learning.py:146) ----
     product(KindC<PR_HEAD>{}, 0, -1);
+    BFB_PHASE(9);
     const int stage_stride = FMAXV + a.tps;
     float* stage = reinterpret_cast<float*>(TK);  // K + L tiles: 32 KB (dead between the last W_out product and the next QKV product)
     {
@@ -1085,10 +1103,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     umma::tc_fence_before_sync();
     umma::group_sync(bar_id, FGROUP_THREADS);
 
+    BFB_PHASE(10);
     // ---- log-softmax, probabilities, score, next token (transformer.py:375; active_learning.py:146-152) ----
     if (a.tps == 16) score_phase<16, FAST == 1 || FAST == 2>(a, stage, stage_stride, gt, nseq, s0, len);
     else             score_phase<8, FAST == 1 || FAST == 2>(a, stage, stage_stride, gt, nseq, s0, len);
     // the staging rows are rewritten only after the next tile's first product: barriers in between order it
+    BFB_PHASE(11);
   }
 
 #ifdef BFB_FUSED_TIMING
@@ -1097,6 +1117,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
     atomicAdd(&bfb_fused_dbg[1], (unsigned long long)dbg[1]);
     atomicAdd(&bfb_fused_dbg[3], (unsigned long long)(clock64() - t_begin));
     atomicAdd(&bfb_fused_dbg[4], 1ull);
+    for (int i = 0; i < 12; ++i) atomicAdd(&bfb_fused_phase[i], (unsigned long long)ph[i]);
   }
 #endif
   umma::tc_fence_before_sync();
@@ -1107,6 +1128,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
 }  // namespace
 
 #ifdef BFB_FUSED_TIMING
+extern "C" int bfb200_debug_fused_phases(unsigned long long* out12, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out12, bfb_fused_phase, sizeof(unsigned long long) * 12);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(bfb_fused_phase, z, sizeof(z));
+  }
+  return 0;
+}
 extern "C" int bfb200_debug_fused_timing(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out8, bfb_fused_dbg, sizeof(unsigned long long) * 8);

@@ -249,15 +249,6 @@ __device__ __forceinline__ float add_hilo_h(uint32_t hi, uint32_t lo, float acc)
   constexpr uint32_t kOne = 0x3C003C00u;
   return fh_hl(lo, kOne, fh_hl(hi, kOne, acc));
 }
-// two fp32 -> two e5m2 bytes (a in the low byte), round to nearest, saturating; and four e5m2 bytes -> two f16x2
-// words (e5m2 is the upper byte of the fp16 with the same value, so the widening is a byte permute)
-__device__ __forceinline__ uint32_t pack_e5m2x2(float a, float b) {
-  uint16_t r;
-  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t e5m2x4_to_f16x2_lo(uint32_t w) { return __byte_perm(w, 0u, 0x1404u); }
-__device__ __forceinline__ uint32_t e5m2x4_to_f16x2_hi(uint32_t w) { return __byte_perm(w, 0u, 0x3424u); }
 
 
 }  // namespace umma

@@ -21,3 +21,13 @@ print(f"{obs} observer lanes; {n / obs:.0f} product round trips each; {rt / n:.0
       f"({post / n:.0f} of them after the group barrier); {rt / tot:.1%} of a thread's time")
 print(f"issuing thread: barrier exit -> tcgen05.commit issued {iss / calls:.0f} cycles (tcgen05.fence {fence / calls:.0f}), "
       f"barrier exit -> completion seen {done / calls:.0f} cycles")
+ph = (C.c_ulonglong * 12)()
+lib.bfb200_debug_fused_phases(ph, 1)
+engine.mc_score_transformer(pk, pr, 5, 20, "dropout", "margin", seed=1)
+lib.bfb200_debug_fused_phases(ph, 1)
+names = ["embedding", "QKV product", "copy Q/K/V to shared", "attention pairs", "attention barriers + output write", "merged product",
+         "LN1 stats + FFN hidden", "FFN2 product (+ layer-out draws)", "LN2 + dropout (incl. dead warps' products)", "head product",
+         "head epilogue + barrier", "score phase"]
+tot_ph = sum(ph[i] for i in range(12))
+for i in range(12):
+    print(f"  {names[i]:45s} {100.0 * ph[i] / tot_ph:5.1f} %")
