@@ -678,13 +678,10 @@ int launch_gemm_tc_ex(const void* A, int64_t a_pitch, const void* W, const float
   BFB_REQUIRE(out32 == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(out32) & 15u) == 0),
               BFB200_ERR_UNSUPPORTED, "fp32 GEMM output needs a row pitch (%lld) that is a multiple of 4 elements and a "
               "16-byte aligned buffer", (long long)ldc);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  int sms = 0, cur_dev = 0;   // per call: the attribute belongs to the CURRENT device (a process may drive several)
+  cudaGetDevice(&cur_dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
+  if (sms <= 0) sms = 148;
   static const bool one_sm_only = getenv("BFB200_GEMM_1SM") != nullptr;   // A/B switch for measurements
   const bool two_sm = N > 128 && !one_sm_only;
   const int BN = N > 128 ? 256 : 128;

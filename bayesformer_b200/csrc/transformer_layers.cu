@@ -10,15 +10,11 @@
 
 namespace bfb {
 
-static int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+static int sm_count() {   // of the CURRENT device, asked per call (a process may drive several devices)
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
 }
 
 static int stride_grid(int64_t blocks_needed, int blocks_per_sm) {

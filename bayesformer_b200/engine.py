@@ -305,7 +305,9 @@ class PackedTransformer:
         F = first.ff.net[0].out_features if L else 4
 
         def dev(t):
-            return t.detach().to(device=device, dtype=torch.float32).contiguous()
+            # an OWNED copy: a no-copy view of a live parameter would follow in-place updates (optimizer steps, graph
+            # replays) while the stacked / 16-bit copies below do not, leaving the pack half fresh
+            return t.detach().to(device=device, dtype=torch.float32, copy=True).contiguous()
 
         def stack(fn):
             return torch.stack([dev(fn(layer)) for layer in module.layers]).contiguous() if L else None

@@ -181,6 +181,33 @@ def test_topk_one_launch_path(engine, dev, kind, n, k, base):
     assert np.array_equal(vals.cpu().numpy(), scores[want])
 
 
+def test_topk_and_scoring_on_two_devices_in_one_process(engine):
+    """Kernel attributes (dynamic shared memory opt-in, cooperative launch, SM count) belong to a device, not to the
+    process: the same process drives cuda:0 and then cuda:1.  Needs two GPUs (skipped otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    rng = np.random.default_rng(4)
+    scores = rng.standard_normal(300000).astype(np.float32)
+    want = R.topk_lowest_index(scores, 4096)
+    small = scores[:9000]
+    want_small = R.topk_lowest_index(small, 300)
+    for d in ("cuda:0", "cuda:1", "cuda:0"):
+        _, idx = engine.topk(torch.from_numpy(scores).to(d), 4096)          # cooperative one-launch path
+        assert idx.cpu().numpy().tolist() == want.tolist()
+        _, idx = engine.topk(torch.from_numpy(small).to(d), 300)            # one-block path (128 KB of dynamic smem)
+        assert idx.cpu().numpy().tolist() == want_small.tolist()
+    z = H.load("c2_transformer.npz")
+    sd = H.state_dict_from(z)
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        model = H.build_model(sd, float(z["p"]), True).to(d)
+        prompts = torch.from_numpy(z["prompts"]).to(d)
+        res = engine.mc_score_transformer(engine.scoring_pack(model, torch.device(d), prompts.shape[0], 5), prompts, 5, 4,
+                                          "dropout", "margin", seed=3)
+        outs.append(res.pool_scores.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_topk_sharded_merge_equals_global(engine, dev):
     """per-shard keys with global index bases + merge == single-device top-k (the multi-GPU exchange)."""
     rng = np.random.default_rng(5)
