@@ -906,9 +906,11 @@ __global__ void __launch_bounds__(FTHREADS, 1) mc_forward_kernel(const FusedArgs
               const uint32_t koff = umma::sw128_offset(krow, 2u * (uint32_t)hd);
               const float4 k0 = *reinterpret_cast<const float4*>(TK + koff);
               const float4 k1 = *reinterpret_cast<const float4*>(TK + (koff ^ 16u));
-              const float sj = fminf(fmaxf(((q0.x * k0.x + q0.y * k0.y) + (q0.z * k0.z + q0.w * k0.w)) +
-                                               ((q1.x * k1.x + q1.y * k1.y) + (q1.z * k1.z + q1.w * k1.w)),
-                                           -3.0e38f), 3.0e38f);
+              // two explicit FMA chains (intrinsics are never re-contracted: every instantiation of the kernel rounds the
+              // score the same way, which the FAST-vs-generic bit-equality test relies on)
+              const float sa = __fmaf_rn(q0.w, k0.w, __fmaf_rn(q0.z, k0.z, __fmaf_rn(q0.y, k0.y, __fmul_rn(q0.x, k0.x))));
+              const float sb2 = __fmaf_rn(q1.w, k1.w, __fmaf_rn(q1.z, k1.z, __fmaf_rn(q1.y, k1.y, __fmul_rn(q1.x, k1.x))));
+              const float sj = fminf(fmaxf(__fadd_rn(sa, sb2), -3.0e38f), 3.0e38f);
               ref = j == 0 ? sj : ref;
               float arg = (sj - ref) * qk_scale_log2e;
               if (arg > 14.0f) {   // rare
