@@ -258,3 +258,38 @@ def test_weight_image_signature_tracks_versions_sites_and_explicit_marks():
     for layer in m.layers:
         layer.ff.bayes_dropout = 0.3                     # a latent dropout site switched on (in every layer)
     assert engine._param_signature(m, dev) != s2
+
+
+def test_train_step_layout_functions_are_consistent():
+    """The pure layout functions of the fused fine-tune step (no GPU): the flat layout covers every parameter of the
+    notebook model exactly once in the documented order, and shapes outside the step's class are reported by a zero
+    scratch size (the caller then trains on another path) rather than by a launch failure."""
+    from bayesformer_b200 import _lib
+    from bayesformer_b200.model.transformer import MyTransformer
+
+    lib = _lib.load()
+    V, F, L = 114, 8, 2
+    model = MyTransformer(V, 64, 8, F, L, bayes_dropout=0.3, bayes=True)
+    n = int(lib.bfb200_train_state_floats(V, F, L))
+    assert n == sum(p.numel() for p in model.parameters())
+    off = lambda layer, which: int(lib.bfb200_train_flat_offset(V, F, L, layer, which))
+    sizes = {0: V * 64, 1: 3 * 64 * 64, 2: 64 * 64, 3: 64, 4: 64, 5: F * 64, 6: F, 7: 64 * F, 8: 64, 9: 64, 10: 64,
+             11: V * 64, 12: V}
+    spans = [(off(0, 0), sizes[0])]
+    for layer in range(L):
+        spans += [(off(layer, w), sizes[w]) for w in range(1, 11)]
+    spans += [(off(0, 11), sizes[11]), (off(0, 12), sizes[12])]
+    spans.sort()
+    assert spans[0][0] == 0 and all(a + s == b for (a, s), (b, _) in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] == n
+    assert all(o % 4 == 0 for o, s in spans if s >= 4)                 # float4 access in the kernel
+    assert int(lib.bfb200_train_flat_offset(V, F, L, 0, 13)) == -1
+    ok = int(lib.bfb200_train_scratch_floats(20, 9, 4, V, F, L))
+    assert ok > 20 * n                                                  # one gradient slab per sequence
+    assert int(lib.bfb200_train_scratch_floats(40, 9, 4, V, F, L)) > ok
+    for bad in ((20, 17, 4, V, F, L),      # longer than the class's 16 tokens
+                (20, 9, 9, V, F, L),       # no answer rows
+                (0, 9, 4, V, F, L),
+                (20, 9, 4, V, 6, L),       # d_ff not a multiple of 4
+                (20, 9, 4, 400, F, L),     # vocabulary beyond the head stage
+                (20, 16, 4, V, 64, 12)):   # activations of one sequence beyond a CTA's shared memory
+        assert int(lib.bfb200_train_scratch_floats(*bad)) == 0, bad
